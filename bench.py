@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- the mesh-and-pressure step of LagrangianVoronoi.jl on B200.
+
+One "step" = the hot path of one reference time step on one batch of synthetic input:
+2 x remesh! (move.jl:20 and relaxation.jl:72 each call it) + 1 x find_pressure!
+(pressure.jl:215-225: operator assembly + niter = 10 x (RHS assembly + Krylov solve to
+atol = rtol = 1e-6, itmax = 1000)), on the periodic random-jittered generator box of
+SURVEY.md section 8(d) (splitmix64 lattice jitter, Taylor-Green fields, rho = 1, dt = 0.1 dr).
+
+  value     device-resident throughput (inputs already in HBM), Mcell-steps/s over all ranks
+  e2e       the same step through the host-buffer C ABI (pinned host arrays, H2D/D2H inside)
+  roofline  the dominant kernel (CSR Voronoi-Laplacian matvec) against the measured HBM peak
+  cpu_baseline / --impl reference   the CPU restatement of the reference (oracle/, OpenMP) on the
+            box's host cores -- the real `julia -t N` cannot run here (no Julia in the image)
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Under torchrun one rank drives one GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mesh+pressure step throughput (2 x Voronoi remesh + find_pressure, 10 x CG solve)"
+UNIT = "Mcell-steps/s"
+MATVEC_BYTES_PER_CELL = 100.0   # rowptr 4 + 6*(col 4 + w 8) + diag 8 + x 8 + y 8
+CG_BYTES_PER_CELL_ITER = 172.0  # matvec 100 + 3 vector updates x 24
+REMESH_BYTES_PER_CELL = 250.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=4096, help="lattice side M per GPU; n = M*M cells (4096 -> 16M)")
+    ap.add_argument("--c0", type=float, default=10.0, help="sound speed of the synthetic fields (c2 = c0^2)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--niter", type=int, default=10)
+    ap.add_argument("--cpu-side", type=int, default=1024, help="lattice side of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = max(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows if len(r) > 3 + k)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_step_rate(side, c0, niter, seed, steps=1, threads=0):
+    """The oracle (CPU restatement of the reference, OpenMP) on a bounded sample of the workload."""
+    from oracle import oracle as orc
+    from lvb200 import synthetic
+    orc.build()
+    if threads:
+        orc.set_threads(threads)
+    dr = 1.0 / side
+    xy = synthetic.jittered_lattice(side, seed)
+    n = side * side
+    g = orc.OracleGrid((0.0, 0.0), (1.0, 1.0), dr, xperiodic=True, yperiodic=True)
+    g.set_points(xy)
+    assert g.remesh() == 0
+    area = g.area()
+    v, P = synthetic.taylor_green_fields(xy)
+    g.set("rho", 1.0); g.set("mass", area); g.set("c2", c0 * c0); g.set("v", v)
+    t_rem = t_pr = 0.0
+    iters_total = 0
+    for _ in range(steps):
+        g.set("P", P)
+        t0 = time.perf_counter()
+        assert g.remesh() == 0
+        assert g.remesh() == 0
+        t1 = time.perf_counter()
+        iters, _ = g.find_pressure(0.1 * dr, niter, rtol=1e-6, atol=1e-6, itmax=1000, solver="minres")
+        t2 = time.perf_counter()
+        t_rem += t1 - t0
+        t_pr += t2 - t1
+        iters_total += int(iters.sum())
+    total = t_rem + t_pr
+    return {"value": n * steps / total / 1e6, "unit": UNIT, "cores": orc.get_threads(), "kind": "port",
+            "sample": f"{steps} step(s) of the same workload at {n} cells (M={side}), MINRES restatement, "
+                      f"{iters_total // steps} Krylov iterations/step",
+            "remesh_mcells_s": 2 * n * steps / t_rem / 1e6, "krylov_mcell_iters_s": n * iters_total / t_pr / 1e6,
+            "s_per_step_sample": total / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    for _ in range(args.warmup and 1):
+        cpu_step_rate(min(args.cpu_side, 256), args.c0, args.niter, args.seed, 1)
+    res = cpu_step_rate(args.cpu_side, args.c0, args.niter, args.seed, max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * res["s_per_step_sample"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"periodic jittered lattice, bounded sample M={args.cpu_side} of the {args.side}^2-cell step, "
+                                   f"c0={args.c0}, niter={args.niter}; CPU restatement of the reference (not Julia)"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lvb200 as lv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for this path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    M = args.side
+    n = M * M
+    dr = 1.0 / M
+    dt = 0.1 * dr
+    # every rank owns an independent periodic box (replicas) until the strip decomposition lands
+    xy = lv.synthetic.jittered_lattice(M, args.seed + rank)
+    g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), dr, xperiodic=True, yperiodic=True, device=local)
+    stream = torch.cuda.current_stream()
+    g.set_stream(stream.cuda_stream)
+    g.set_points(xy)
+    xy_dev = torch.from_numpy(xy).to(dev)
+    g.remesh_dev(xy_dev)
+    solver = lv.PressureSolver(g)
+    _, _, area, _ = g.mesh_download(n, edges=False)
+    v, P = lv.synthetic.taylor_green_fields(xy)
+    f_host = {"mass": area.copy(), "rho": np.ones(n), "c2": np.full(n, args.c0 ** 2), "P": P, "v": v}
+    f_dev = {k: torch.from_numpy(np.ascontiguousarray(a)).to(dev) for k, a in f_host.items()}
+    for k, a in f_host.items():
+        getattr(g, k)[...] = a
+
+    def step_dev():
+        g.remesh_dev(xy_dev)
+        g.remesh_dev(xy_dev)
+        solver.upload_fields(f_dev["mass"], f_dev["rho"], f_dev["c2"], f_dev["P"], f_dev["v"], device=True)
+        iters, _ = solver.find_pressure_dev(dt, args.niter)
+        return int(iters.sum())
+
+    def step_e2e():
+        g.P[...] = P
+        lv.remesh(g)
+        lv.remesh(g)
+        lv.find_pressure(solver, dt, args.niter)
+        return int(solver.iters.sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    g.prof_reset()
+    g.prof_enable(True)
+    l0 = g.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record(stream)
+        iters_total = 0
+        for _ in range(args.steps):
+            iters_total += step_dev()
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = g.launch_count() - l0
+    prof = {k: g.prof_get(k) for k in ("cells", "clip", "assemble", "matvec", "vecops")}
+    g.prof_enable(False)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        ev1.record(stream)
+        barrier()
+        ms_e = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+        te = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        nnz = int(g.rowptr[-1])
+        h2d = 2 * n * 16 + n * 8 * 6                     # 2 x positions + mass, rho, c2, P, v(2)
+        d2h = 2 * ((n + 1) * 8 + nnz * 40 + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
+        e2e = {"value": world * n * args.steps / (float(te.item()) / 1e3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, peak_src = peaks()
+    mv_ms, mv_cnt = prof["matvec"]
+    mv_avg = mv_ms / max(mv_cnt, 1)
+    achieved = MATVEC_BYTES_PER_CELL * n / (mv_avg * 1e-3) / 1e9 if mv_avg > 0 else 0.0
+    rem_ms = prof["cells"][0] + prof["clip"][0]
+    pr_ms = prof["assemble"][0] + prof["matvec"][0] + prof["vecops"][0]
+    line = {
+        "metric": METRIC, "value": world * n * args.steps / (ms_max / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic periodic random-jittered box, {n} cells per GPU (M={M}), dr=1/{M}, h=2dr, r_max=10dr, "
+                               f"Taylor-Green v/P, rho=1, c0={args.c0}, dt=0.1dr; step = 2 x remesh + find_pressure(niter={args.niter}, "
+                               f"CG rtol=atol=1e-6, itmax=1000)",
+                   "cells_per_gpu": n, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": "inputs larger than L2 (no flush needed)", "krylov_iters_per_step": iters_total // args.steps},
+        "submetrics": {"remesh_mcells_s": 2 * n * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
+                       "cg_mcell_iters_s": n * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
+                       "s_per_step": ms_max / args.steps / 1e3,
+                       "phase_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}},
+        "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
+                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if hbm else None, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0, "avg_launch_ms": mv_avg, "launches": mv_cnt,
+                     "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_CELL * n, "traffic": None},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu:
+        res = cpu_step_rate(args.cpu_side, args.c0, args.niter, args.seed, 1)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["detail"] = {k: res[k] for k in ("remesh_mcells_s", "krylov_mcell_iters_s", "s_per_step_sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

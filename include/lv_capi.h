@@ -1,0 +1,148 @@
+/*
+ * lv_capi.h -- C ABI of liblvb200.so, the B200 (sm_100a) implementation of
+ * LagrangianVoronoi.jl's per-timestep mesh-and-pressure hot path.
+ *
+ * The reference (pure Julia) has no FFI of its own; the drop-in boundary is its Julia call
+ * surface.  Each entry point below names the reference body it replaces (file:line relative
+ * to /root/reference/src).  The Julia shim that binds these symbols with `ccall` is in
+ * julia/LagrangianVoronoiB200.jl and described in INTEGRATION.md; the Python host mirror in
+ * lagrangianvoronoi.jl_b200/ binds the same symbols with ctypes.
+ *
+ * Conventions
+ *  - every function returns an int32 status (LV_OK, ...); text via lv_last_error()
+ *  - pointers are caller-owned HOST buffers unless the name ends in _dev (device pointers on
+ *    the handle's GPU); the library owns all other device memory behind the opaque handle
+ *  - generator labels are 1-based int64 at the boundary (Julia indices); labels <= 0 are the
+ *    wall codes UP=-1 RIGHT=-2 DOWN=-3 LEFT=-4 (polygon.jl:4-7)
+ *  - positions / vectors are interleaved double[2n] (= Vector{SVector{2,Float64}})
+ *  - LvEdge is the 40-byte isbits layout of `Edge` (geometry.jl:82-87)
+ *  - host-buffer calls are synchronous; *_dev calls are asynchronous on the handle's stream
+ *    and report device-side failures at the next lv_sync()/host-buffer call
+ *  - one caller thread per handle; no callbacks cross the boundary
+ */
+#ifndef LV_CAPI_H
+#define LV_CAPI_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LvContext *LvHandle;
+
+typedef struct LvEdge { double v1[2]; double v2[2]; int64_t label; } LvEdge; /* geometry.jl:82-87 */
+
+/* VoronoiGrid{T}(boundary_rect, dr; h, r_max, xperiodic, yperiodic)  voronoigrid.jl:26-28.
+ * h <= 0 selects the default 2dr, r_max <= 0 the default 10dr. */
+typedef struct LvGridDesc {
+    double dr, h, r_max;
+    int32_t xperiodic, yperiodic;
+    double bmin[2], bmax[2]; /* boundary_rect */
+} LvGridDesc;
+
+enum {
+    LV_OK = 0,
+    LV_EINVAL = 1,     /* invalid argument (also ArgumentError("h must be positive"), neighborlist.jl:19-21) */
+    LV_EDESTROYED = 2, /* "The Voronoi Mesh has been destroyed."  voronoigrid.jl:63-65 */
+    LV_ENAN = 3,       /* NaN/Inf position or velocity ("Velocity field invalidated." move.jl:24-26) */
+    LV_ECUDA = 4,      /* CUDA / NCCL failure, see lv_last_error */
+    LV_ECAPACITY = 5   /* caller buffer too small (nnz > cap) or polygon exceeded the internal limit */
+};
+
+enum { LV_SOLVER_CG = 0, LV_SOLVER_MINRES = 1 };
+
+/* profiling slots for lv_prof_get */
+enum {
+    LV_PROF_CELLS = 0,   /* K1: cell-list build (count, scan, fill, bucket order) */
+    LV_PROF_CLIP = 1,    /* K2: half-plane clipping kernel */
+    LV_PROF_ASSEMBLE = 2,/* K3: operator + RHS assembly */
+    LV_PROF_MATVEC = 3,  /* K4: Voronoi-Laplacian matvec (+ fused dot) */
+    LV_PROF_VECOPS = 4,  /* K5: fused Krylov vector updates */
+    LV_PROF_COUNT = 5
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* replaces the VoronoiGrid constructor + CellList constructor (voronoigrid.jl:26-49,
+ * neighborlist.jl:18-43).  `device` is the CUDA ordinal. */
+int32_t lv_create(const LvGridDesc *desc, int32_t device, LvHandle *out);
+int32_t lv_destroy(LvHandle h);
+const char *lv_last_error(LvHandle h); /* h may be NULL: error of the last failed lv_create */
+/* examples/piston.jl:43-47 mutates grid.boundary_rect / grid.cropping_rect at run time */
+int32_t lv_set_rects(LvHandle h, const double bmin[2], const double bmax[2], const double cmin[2],
+                     const double cmax[2]);
+/* cell-list geometry (neighborlist.jl:23-25) and the length of the truncated magic_path */
+int32_t lv_grid_info(LvHandle h, int64_t *n1, int64_t *n2, double origin[2], int64_t *npath);
+int32_t lv_magic_path(LvHandle h, int64_t cap, int64_t *i1, int64_t *i2, double *rr, int64_t *count);
+/* run on a caller-provided cudaStream_t (NULL restores the handle's own stream) */
+int32_t lv_set_stream(LvHandle h, void *cuda_stream);
+int32_t lv_sync(LvHandle h); /* stream-synchronise and report any pending device-side status */
+
+/* ---- remesh!(grid)  voronoigrid.jl:89-108 ----------------------------------------------- */
+/* Host-buffer form.  xy[2n] in; out: rowptr[n+1] (0-based offsets), edges[cap] in the storage
+ * order the reference leaves in p.edges after sort_edges! (IO.jl:35-48), *nnz, and optionally
+ * area[n] (polygon.jl:114-122) and centroid[2n] (polygon.jl:210-219).  rowptr/edges/area/
+ * centroid may each be NULL (edges NULL: the mesh stays device-resident only). */
+int32_t lv_remesh(LvHandle h, int64_t n, const double *xy, int64_t *rowptr, LvEdge *edges, int64_t cap,
+                  int64_t *nnz, double *area, double *centroid);
+/* Device-resident form: positions already in HBM, results stay in HBM. */
+int32_t lv_remesh_dev(LvHandle h, int64_t n, const double *xy_dev);
+int32_t lv_mesh_nnz(LvHandle h, int64_t *nnz); /* synchronises */
+int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area,
+                         double *centroid);
+/* face lengths len(e) (geometry.jl:136) and midpoints (geometry.jl:145) in the same CSR order */
+int32_t lv_mesh_faces(LvHandle h, double *length, double *midpoint, int64_t cap);
+
+/* ---- pressure system  pressure.jl:84-225 ------------------------------------------------ */
+/* PressureSolver(grid) (pressure.jl:150-158): workspace for the current n */
+int32_t lv_pressure_create(LvHandle h);
+int32_t lv_pressure_destroy(LvHandle h);
+/* per-polygon fields read by the solve, label order, any pointer may be NULL to keep the
+ * resident value: mass[n] rho[n] c2[n] P[n] v[2n] */
+int32_t lv_fields_upload(LvHandle h, const double *mass, const double *rho, const double *c2,
+                         const double *P, const double *v);
+int32_t lv_fields_upload_dev(LvHandle h, const double *mass_dev, const double *rho_dev,
+                             const double *c2_dev, const double *P_dev, const double *v_dev);
+int32_t lv_pressure_download(LvHandle h, double *P_out);
+/* refresh!(A, grid, dt) (pressure.jl:104-117) on the resident fields */
+int32_t lv_pressure_assemble(LvHandle h, double dt);
+/* copy of A.neighbors / A.lr_ratios / A.diagonal in label order; col is 1-based (rowptr[n+1],
+ * col/w[cap]); for parity tests of the assembly */
+int32_t lv_pressure_operator(LvHandle h, int64_t *rowptr, int64_t *col, double *w, int64_t cap,
+                             double *diag);
+/* mul!(y, A, x) (pressure.jl:119-130), x and y in label order */
+int32_t lv_pressure_matvec(LvHandle h, const double *x, double *y);
+/* refresh!(solver, dt, gp_step, boundary_velocity) (pressure.jl:162-203).  vbc_wall[4][2] is
+ * the boundary velocity per wall code (row -label-1), NULL = zero_vbc (pressure.jl:205).
+ * Outputs b[n], GP[2n] in label order (either may be NULL). */
+int32_t lv_pressure_rhs(LvHandle h, double dt, int32_t gp_step, const double *vbc_wall, double *b,
+                        double *GP);
+/* find_pressure!(solver, dt, niter; boundary_velocity) (pressure.jl:215-225).
+ * Reference defaults: niter 10, rtol = atol = 1e-6, itmax 1000 (pressure.jl:219).
+ * Host form gathers the fields, solves and writes P_out[n]; iters_out[niter] and
+ * relres_out[niter] (true relative residual ||b - A P|| / ||b|| after each pass) may be NULL. */
+int32_t lv_find_pressure(LvHandle h, double dt, int32_t niter, double rtol, double atol, int32_t itmax,
+                         int32_t solver, const double *mass, const double *rho, const double *c2,
+                         const double *P_in, const double *v, const double *vbc_wall, double *P_out,
+                         int32_t *iters_out, double *relres_out);
+/* Device-resident form on the fields uploaded with lv_fields_upload*; P stays resident. */
+int32_t lv_find_pressure_dev(LvHandle h, double dt, int32_t niter, double rtol, double atol,
+                             int32_t itmax, int32_t solver, const double *vbc_wall, int32_t *iters_out,
+                             double *relres_out);
+/* one Krylov solve A x = b on the assembled operator (label order, x holds the initial guess) */
+int32_t lv_pressure_solve(LvHandle h, int32_t solver, const double *b, double *x, double rtol,
+                          double atol, int32_t itmax, int32_t *iters, double *relres);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+int32_t lv_prof_enable(LvHandle h, int32_t on);
+int32_t lv_prof_reset(LvHandle h);
+/* accumulated CUDA-event milliseconds and launch count of one profiling slot */
+int32_t lv_prof_get(LvHandle h, int32_t slot, double *ms, int64_t *launches);
+/* total kernels launched by this handle since creation */
+int64_t lv_launch_count(LvHandle h);
+/* device memory currently owned by the handle, in bytes */
+int64_t lv_device_bytes(LvHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,177 @@
+// lv_internal.cuh -- shared declarations of liblvb200 (sm_100a only).
+//
+// Data layout in HBM (everything structure-of-arrays, indexed by "slot"):
+//   A slot is one entry of the bucket-sorted cell list: every generator contributes one
+//   primary slot plus one slot per periodic image that falls inside the padded cell list
+//   (voronoigrid.jl:130-147).  Slots are ordered by (bucket, label) -- exactly the order in
+//   which `julia -t 1` finds labels inside a bucket -- so slot order is also a spatial order
+//   and all per-cell data (mesh rows, pressure vectors) live in it.  Labels are mapped back
+//   only at the C-ABI boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/lv_capi.h"
+
+#define LV_IMAGE_BIT 0x80000000u // set in ent_label[] for periodic-image slots
+
+struct LvPathNode { // neighborlist.jl:6-9, truncated table (see lv_capi.cu:build_magic_path)
+    int i1, i2;
+    double rr;
+};
+
+struct LvGridParams { // passed by value to kernels
+    double h;            // cell-list bucket size (neighborlist.jl:16)
+    double rr_max;       // r_max^2 (voronoigrid.jl:40)
+    double ox, oy;       // cell-list origin (neighborlist.jl:23)
+    double cminx, cminy, cmaxx, cmaxy; // cropping_rect (voronoigrid.jl:29-33)
+    double xperiod, yperiod;           // voronoigrid.jl:31-32
+    int xper, yper;
+    int n1, n2;          // buckets per axis (neighborlist.jl:24-25)
+    int npath;           // nodes in the truncated magic_path table
+};
+
+struct LvProfSlot {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct LvContext {
+    int device = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::string err;
+    // grid (voronoigrid.jl:14-25)
+    double dr = 0, h = 0, r_max = 0;
+    double bmin[2], bmax[2], cmin[2], cmax[2];
+    LvGridParams gp{};
+    LvPathNode *d_path = nullptr;
+    LvPathNode *h_path = nullptr;
+    int64_t ncell = 0;
+    // generators (label order)
+    int64_t n = 0;
+    double2 *d_xy = nullptr;     // owned copy of the positions (host-buffer path)
+    const double2 *xy = nullptr; // positions used by the last remesh (d_xy or caller's)
+    int64_t cap_n = 0;
+    // cell list
+    int *d_cell_cnt = nullptr;   // [ncell+1] counts, then fill cursors
+    int *d_cell_start = nullptr; // [ncell+1] exclusive scan
+    int64_t nslot = 0, cap_slot = 0;
+    unsigned *d_ent_label = nullptr; // [nslot] 0-based label | LV_IMAGE_BIT
+    double2 *d_ent_xy = nullptr;     // [nslot] ORIGINAL position of the label (q.x)
+    int *d_prim_of_label = nullptr;  // [n] label -> primary slot (-1: outside the cell list)
+    // mesh (slot order)
+    int *d_rowptr = nullptr; // [nslot+1]
+    int64_t nnz = 0, cap_nnz = 0;
+    int *d_col = nullptr;    // [nnz] neighbour primary slot, or wall code -1..-4
+    double2 *d_v1 = nullptr, *d_v2 = nullptr; // [nnz] edge end points (clockwise, polygon.jl:51-97)
+    double *d_area = nullptr;                 // [nslot]
+    double2 *d_cen = nullptr;                 // [nslot]
+    unsigned long long *d_tile_state = nullptr; // look-back scan state of the clip kernel
+    int64_t cap_tiles = 0;
+    int *d_flags = nullptr; // [8] device status words, see LvFlag
+    int *h_flags = nullptr; // pinned mirror
+    int clip_level = 0;     // polygon capacity level that last succeeded
+    bool mesh_valid = false;
+    // scratch for scans / label-order staging
+    void *d_scratch = nullptr;
+    int64_t cap_scratch = 0;
+    // pressure (slot order)
+    bool pr_valid = false;
+    int64_t pr_cap = 0;
+    double *d_mass = nullptr, *d_rho = nullptr, *d_c2 = nullptr, *d_P = nullptr;
+    double2 *d_v = nullptr, *d_GP = nullptr;
+    double *d_diag = nullptr, *d_w = nullptr; // operator: diagonal [nslot], weights [nnz]
+    int64_t cap_w = 0;
+    double *d_b = nullptr;
+    double *d_vec[8] = {nullptr}; // Krylov workspace vectors
+    double *d_red = nullptr;      // reduction partials + scalars
+    double *h_red = nullptr;      // pinned
+    bool assembled = false;
+    // instrumentation
+    bool prof_on = false;
+    LvProfSlot prof[LV_PROF_COUNT];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct ProfPending { int slot; cudaEvent_t a, b; };
+    std::vector<ProfPending> prof_pending; // recorded, not yet resolved (no sync in the hot loop)
+    std::vector<cudaEvent_t> prof_free;
+    int64_t launches = 0;
+    int64_t dev_bytes = 0;
+    int num_sms = 148;
+};
+
+enum LvFlag { LVF_DESTROYED = 0, LVF_NAN = 1, LVF_OVERFLOW = 2, LVF_TICKET = 3, LVF_NNZ = 4, LVF_CONV = 5 };
+
+// ---- error helpers -------------------------------------------------------------------------
+int lv_set_error(LvContext *c, int code, const char *fmt, ...);
+#define LV_CUDA(c, expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return lv_set_error((c), LV_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                          \
+    } while (0)
+#define LV_TRY(expr)                       \
+    do {                                   \
+        int _s = (expr);                   \
+        if (_s != LV_OK) return _s;        \
+    } while (0)
+
+int lv_ensure(LvContext *c, void **ptr, int64_t *cap, int64_t need, size_t elt); // grow-only device buffer
+int lv_alloc(LvContext *c, void **ptr, size_t bytes);
+void lv_free(LvContext *c, void *ptr, size_t bytes);
+
+struct LvProfScope { // CUDA-event bracket on the handle's stream; resolved lazily by lv_prof_resolve
+    LvContext *c;
+    int slot;
+    cudaEvent_t a = nullptr;
+    LvProfScope(LvContext *c_, int slot_);
+    ~LvProfScope();
+};
+void lv_prof_resolve(LvContext *c); // synchronises the pending event pairs and accumulates them
+
+// ---- phases (each launches on c->stream) -----------------------------------------------------
+int lv_cells_build(LvContext *c);                          // K1  lv_cells.cu
+int lv_clip_run(LvContext *c);                             // K2  lv_clip.cu
+int lv_exclusive_scan_i32(LvContext *c, const int *in, int *out, int64_t n); // out[n] = total
+int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area,
+                      double *centroid); // lv_capi.cu
+// pressure (lv_pressure.cu)
+int lv_pr_ensure(LvContext *c);
+int lv_pr_assemble(LvContext *c, double dt);
+int lv_pr_matvec(LvContext *c, const double *x, double *y); // slot-order device vectors
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall);
+int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres);
+int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver,
+                        const double *vbc_wall, int32_t *iters_out, double *relres_out);
+int lv_gather_to_slots(LvContext *c, const double *src_label_dev, double *dst_slot, int ncomp, double fill);
+int lv_scatter_to_labels(LvContext *c, const double *src_slot, double *dst_label_dev, int ncomp);
+
+// ---- device helpers shared by kernels ---------------------------------------------------------
+__device__ __forceinline__ double lv_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
+
+// y = x + get_arrow(q, x)   voronoigrid.jl:116-125 with the caller's `x + arrow` (voronoigrid.jl:72)
+__device__ __forceinline__ double2 lv_neighbor_pos(const LvGridParams &g, double2 x, double2 q) {
+    double vx = q.x - x.x, vy = q.y - x.y;
+    if (g.xper && (fabs(vx) > 0.5 * g.xperiod)) {
+        double s = lv_sign(vx) * g.xperiod;
+        vx = vx - s * 1.0;
+        vy = vy - s * 0.0;
+    }
+    if (g.yper && (fabs(vy) > 0.5 * g.yperiod)) {
+        double s = lv_sign(vy) * g.yperiod;
+        vx = vx - s * 0.0;
+        vy = vy - s * 1.0;
+    }
+    return make_double2(x.x + vx, x.y + vy);
+}
+
+// findkey  neighborlist.jl:47-52 (1-based bucket coordinates); false when not representable
+__device__ __forceinline__ bool lv_findkey(const LvGridParams &g, double2 x, int &i1, int &i2) {
+    double q1 = floor((x.x - g.ox) / g.h), q2 = floor((x.y - g.oy) / g.h);
+    if (!isfinite(q1) || !isfinite(q2)) return false; // floor(Int, NaN/Inf) throws InexactError
+    // far outside the cell list: any out-of-bounds value behaves the same (checkbounds fails)
+    i1 = fabs(q1) < 1.0e9 ? (int)q1 + 1 : (q1 < 0.0 ? -(1 << 30) : (1 << 30));
+    i2 = fabs(q2) < 1.0e9 ? (int)q2 + 1 : (q2 < 0.0 ? -(1 << 30) : (1 << 30));
+    return true;
+}

@@ -1,0 +1,683 @@
+// lv_pressure.cu -- K3/K4/K5: the semi-implicit pressure system on the Voronoi stencil.
+//
+// Replaces pressure.jl:89-225 of the reference: operator assembly (refresh!(A,...),
+// :104-117), the matrix-free matvec mul! (:119-130), the right-hand side (refresh!(solver,...),
+// :162-203) and the find_pressure! fixed-point loop (:215-225) whose inner Krylov.jl MINRES call
+// is replaced by an FP64 conjugate-gradient iteration that never leaves the device.
+// All vectors live in slot order (see lv_internal.cuh); image slots are empty rows (diag = 0,
+// b = 0, x = 0) and take no part in the system.
+#include "lv_internal.cuh"
+
+#define PR_BLOCK 256
+
+// scalars kept on the device between kernels (doubles in c->d_red[0..15])
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_COUNT = 16 };
+
+// ---- label <-> slot permutation --------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(PR_BLOCK) k_gather_slots(int nslot, const unsigned *__restrict__ ent_label,
+                                                           const double *__restrict__ src, double *__restrict__ dst, double fill) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslot) return;
+    const unsigned e = ent_label[s];
+    if (e & LV_IMAGE_BIT) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) dst[(size_t)NC * s + k] = fill;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NC; k++) dst[(size_t)NC * s + k] = src[(size_t)NC * e + k];
+    }
+}
+template <int NC>
+__global__ void __launch_bounds__(PR_BLOCK) k_scatter_labels(int64_t n, const int *__restrict__ prim, const double *__restrict__ src,
+                                                             double *__restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = prim[i];
+#pragma unroll
+    for (int k = 0; k < NC; k++) dst[(size_t)NC * i + k] = src[(size_t)NC * s + k];
+}
+
+int lv_gather_to_slots(LvContext *c, const double *src, double *dst, int ncomp, double fill) {
+    const int ns = (int)c->nslot;
+    if (ns == 0) return LV_OK;
+    const int nb = (ns + PR_BLOCK - 1) / PR_BLOCK;
+    if (ncomp == 1) k_gather_slots<1><<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_ent_label, src, dst, fill);
+    else k_gather_slots<2><<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_ent_label, src, dst, fill);
+    c->launches++;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+int lv_scatter_to_labels(LvContext *c, const double *src, double *dst, int ncomp) {
+    if (c->n == 0) return LV_OK;
+    const int nb = (int)((c->n + PR_BLOCK - 1) / PR_BLOCK);
+    if (ncomp == 1) k_scatter_labels<1><<<nb, PR_BLOCK, 0, c->stream>>>(c->n, c->d_prim_of_label, src, dst);
+    else k_scatter_labels<2><<<nb, PR_BLOCK, 0, c->stream>>>(c->n, c->d_prim_of_label, src, dst);
+    c->launches++;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------
+int lv_pr_ensure(LvContext *c) {
+    if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
+    const int64_t need = c->cap_slot;
+    if (c->pr_cap < need || !c->d_mass) {
+        double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_vec[0], &c->d_vec[1],
+                          &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
+        for (double **p : one) {
+            int64_t cap = *p ? c->pr_cap : 0;
+            LV_TRY(lv_ensure(c, (void **)p, &cap, need, sizeof(double)));
+        }
+        int64_t cap = c->d_v ? c->pr_cap : 0;
+        LV_TRY(lv_ensure(c, (void **)&c->d_v, &cap, need, sizeof(double2)));
+        cap = c->d_GP ? c->pr_cap : 0;
+        LV_TRY(lv_ensure(c, (void **)&c->d_GP, &cap, need, sizeof(double2)));
+        c->pr_cap = need;
+        // neutral defaults so that image slots never produce NaN
+        LV_CUDA(c, cudaMemsetAsync(c->d_mass, 0, sizeof(double) * (size_t)need, c->stream));
+        LV_CUDA(c, cudaMemsetAsync(c->d_P, 0, sizeof(double) * (size_t)need, c->stream));
+        LV_CUDA(c, cudaMemsetAsync(c->d_v, 0, sizeof(double2) * (size_t)need, c->stream));
+        c->pr_valid = false;
+    }
+    if (c->cap_w < c->cap_nnz || !c->d_w) LV_TRY(lv_ensure(c, (void **)&c->d_w, &c->cap_w, c->cap_nnz, sizeof(double)));
+    if (!c->d_red) LV_TRY(lv_alloc(c, (void **)&c->d_red, sizeof(double) * (SC_COUNT + 2 * 4096)));
+    return LV_OK;
+}
+
+// ---- K3: operator assembly  pressure.jl:104-117 ------------------------------------------------
+__global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned *__restrict__ ent_label,
+                                                       const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                       const int *__restrict__ col, const double2 *__restrict__ v1,
+                                                       const double2 *__restrict__ v2, const double *__restrict__ mass,
+                                                       const double *__restrict__ rho, const double *__restrict__ c2,
+                                                       double *__restrict__ diag, double *__restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (ent_label[i] & LV_IMAGE_BIT) { diag[i] = 0.0; return; }
+    const double ri = rho[i];
+    diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
+    const double2 x = ent_xy[i];
+    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    for (int k = r0; k < r1; k++) {
+        const int j = col[k];
+        if (j < 0) { w[k] = 0.0; continue; } // wall edge: not part of neighbors(p, grid)
+        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
+        const double2 a = v1[k], b = v2[k];
+        const double ex = a.x - b.x, ey = a.y - b.y, dx = x.x - y.x, dy = x.y - y.y;
+        const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy)); // lr_ratio  polygon.jl:228-232
+        w[k] = lrr * (0.5 / ri + 0.5 / rho[j]);                             // pressure.jl:113
+    }
+}
+
+int lv_pr_assemble(LvContext *c, double dt) {
+    LV_TRY(lv_pr_ensure(c));
+    if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
+    LvProfScope prof(c, LV_PROF_ASSEMBLE);
+    const int ns = (int)c->nslot;
+    if (ns > 0) {
+        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_ent_label, c->d_ent_xy, c->d_rowptr,
+                                                                             c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
+                                                                             c->d_diag, c->d_w);
+        c->launches++;
+        LV_CUDA(c, cudaGetLastError());
+    }
+    c->assembled = true;
+    return LV_OK;
+}
+
+// ---- block reduction helper ---------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r; // valid in thread 0
+}
+
+// ---- K4: matvec  pressure.jl:119-130, with optional fused dot(x, y) partial ----------------------
+template <bool DOT>
+__global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                     const double *__restrict__ w, const double *__restrict__ diag,
+                                                     const double *__restrict__ x, double *__restrict__ y,
+                                                     double *__restrict__ partial, const double *__restrict__ scal) {
+    __shared__ double sm[32];
+    if (DOT && scal[SC_CONV] != 0.0) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double xi = x[i];
+        double yi = diag[i] * xi;
+        const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        for (int k = r0; k < r1; k++) {
+            const int j = col[k];
+            const double xj = j >= 0 ? x[j] : xi;
+            yi += w[k] * (xi - xj);
+        }
+        y[i] = yi;
+        if (DOT) acc += xi * yi;
+    }
+    if (DOT) {
+        const double s = block_sum(acc, sm);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
+static inline int pr_grid(const LvContext *c, int64_t n) {
+    int64_t nb = (n + PR_BLOCK - 1) / PR_BLOCK;
+    int64_t cap = (int64_t)c->num_sms * 8;
+    if (cap > 4096) cap = 4096;
+    return (int)(nb < cap ? (nb < 1 ? 1 : nb) : cap);
+}
+
+int lv_pr_matvec(LvContext *c, const double *x, double *y) {
+    if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
+    LvProfScope prof(c, LV_PROF_MATVEC);
+    const int ns = (int)c->nslot;
+    if (ns == 0) return LV_OK;
+    k_matvec<false><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, x, y, nullptr, c->d_red);
+    c->launches++;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// ---- right-hand side  pressure.jl:162-203 ---------------------------------------------------------
+struct Vbc { double w[8]; };
+
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned *__restrict__ ent_label,
+                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                   const int *__restrict__ col, const double2 *__restrict__ v1,
+                                                   const double2 *__restrict__ v2, const double *__restrict__ area,
+                                                   const double *__restrict__ mass, const double *__restrict__ rho,
+                                                   const double *__restrict__ c2, const double *__restrict__ P,
+                                                   const double2 *__restrict__ v, double *__restrict__ b, double2 *__restrict__ GP) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
+    const double2 x = ent_xy[i];
+    const double Pi = P[i];
+    const double2 vi = v[i];
+    double bi = (area[i] * Pi) / ((rho[i] * c2[i]) * (dt * dt)); // pressure.jl:171
+    double gx = 0.0, gy = 0.0;
+    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    for (int k = r0; k < r1; k++) { // neighbors(p, grid)
+        const int j = col[k];
+        if (j < 0) continue;
+        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
+        const double2 a = v1[k], c = v2[k];
+        const double ex = a.x - c.x, ey = a.y - c.y, dx = x.x - y.x, dy = x.y - y.y;
+        const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy));
+        const double mx = 0.5 * (a.x + c.x), my = 0.5 * (a.y + c.y);
+        const double2 vj = v[j];
+        bi -= (lrr / dt) * ((vi.x - vj.x) * (mx - y.x) + (vi.y - vj.y) * (my - y.y)); // :177
+        const double s = lrr * (Pi - P[j]);
+        gx -= s * (mx - x.x); // :178
+        gy -= s * (my - x.y);
+    }
+    for (int k = r0; k < r1; k++) { // boundaries(p)
+        const int j = col[k];
+        if (j >= 0) continue;
+        const double2 a = v1[k], c = v2[k];
+        const double sx = a.y - c.y, sy = c.x - a.x; // dS  :181
+        const int wl = -j - 1;
+        const double bx = wl < 4 ? vbc.w[2 * wl] : 0.0, by = wl < 4 ? vbc.w[2 * wl + 1] : 0.0;
+        bi -= (sx * (bx - vi.x) + sy * (by - vi.y)) / dt; // :183
+    }
+    const double m = mass[i];
+    GP[i] = make_double2(gx / m, gy / m); // :185
+    b[i] = bi;
+}
+
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs2(LvGridParams g, int nslot, const unsigned *__restrict__ ent_label,
+                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                   const int *__restrict__ col, const double2 *__restrict__ v1,
+                                                   const double2 *__restrict__ v2, const double2 *__restrict__ GP,
+                                                   double *__restrict__ b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (ent_label[i] & LV_IMAGE_BIT) return;
+    const double2 x = ent_xy[i];
+    const double2 gi = GP[i];
+    double bi = b[i];
+    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    for (int k = r0; k < r1; k++) {
+        const int j = col[k];
+        if (j < 0) continue;
+        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
+        const double2 a = v1[k], c = v2[k];
+        const double ex = a.x - c.x, ey = a.y - c.y, dx = x.x - y.x, dy = x.y - y.y;
+        const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy));
+        const double mx = 0.5 * (a.x + c.x), my = 0.5 * (a.y + c.y);
+        const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);
+        const double2 gj = GP[j];
+        bi += lrr * ((gi.x - gj.x) * (mx - zx) + (gi.y - gj.y) * (my - zy)); // :198
+    }
+    b[i] = bi;
+}
+
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
+    LV_TRY(lv_pr_ensure(c));
+    if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
+    LvProfScope prof(c, LV_PROF_ASSEMBLE);
+    const int ns = (int)c->nslot;
+    if (ns == 0) return LV_OK;
+    Vbc vbc;
+    for (int k = 0; k < 8; k++) vbc.w[k] = vbc_wall ? vbc_wall[k] : 0.0;
+    const int nb = (ns + PR_BLOCK - 1) / PR_BLOCK;
+    k_rhs1<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_col, c->d_v1, c->d_v2,
+                                           c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b, c->d_GP);
+    c->launches++;
+    if (gp_step) {
+        k_rhs2<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_GP,
+                                               c->d_b);
+        c->launches++;
+    }
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// ---- K5: conjugate gradients, scalars resident on the device ------------------------------------------
+// r = b - A x ; p = r ; partial(r.r), partial(b.b)
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_init(int nslot, const double *__restrict__ b, const double *__restrict__ Ax,
+                                                      double *__restrict__ r, double *__restrict__ p, double *__restrict__ partial,
+                                                      int nblk_max) {
+    __shared__ double sm[32];
+    double rr = 0.0, bb = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double bi = b[i];
+        const double ri = bi - Ax[i];
+        r[i] = ri;
+        p[i] = ri;
+        rr += ri * ri;
+        bb += bi * bi;
+    }
+    const double s1 = block_sum(rr, sm);
+    const double s2 = block_sum(bb, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s1; partial[nblk_max + blockIdx.x] = s2; }
+}
+
+// one block: finish reductions and update the scalars.  mode 0: init, 1: alpha, 2: beta, 3: residual check
+__global__ void __launch_bounds__(256) k_cg_scalars(int mode, int nblk, int nblk_max, const double *__restrict__ partial,
+                                                    double *__restrict__ scal, double rtol, double atol) {
+    __shared__ double sm[32];
+    if (mode != 0 && mode != 3 && scal[SC_CONV] != 0.0) return;
+    double a = 0.0, b2 = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
+    const double s1 = block_sum(a, sm);
+    const double s2 = block_sum(b2, sm);
+    if (threadIdx.x != 0) return;
+    if (mode == 0) {
+        scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_BNORM2] = s2;
+        const double tol = atol + rtol * sqrt(s1); // Krylov: eps = atol + rtol*||r0||
+        scal[SC_TOL] = tol;
+        scal[SC_ITER] = 0.0;
+        scal[SC_CONV] = (sqrt(s1) <= tol) ? 1.0 : 0.0;
+    } else if (mode == 1) {
+        scal[SC_PAP] = s1;
+        scal[SC_ALPHA] = scal[SC_RR] / s1;
+    } else if (mode == 2) {
+        const double rr_old = scal[SC_RR];
+        scal[SC_BETA] = s1 / rr_old;
+        scal[SC_RR] = s1;
+        scal[SC_ITER] += 1.0;
+        if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
+    } else {
+        scal[SC_RES2] = s1; scal[SC_BNORM2] = s2;
+    }
+}
+
+// x += alpha p ; r -= alpha Ap ; partial(r.r)
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xr(int nslot, const double *__restrict__ scal, const double *__restrict__ p,
+                                                           const double *__restrict__ Ap, double *__restrict__ x,
+                                                           double *__restrict__ r, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    if (scal[SC_CONV] != 0.0) return;
+    const double alpha = scal[SC_ALPHA];
+    double rr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[i];
+        r[i] = ri;
+        rr += ri * ri;
+    }
+    const double s = block_sum(rr, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// p = r + beta p
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_p(int nslot, const double *__restrict__ scal, const double *__restrict__ r,
+                                                          double *__restrict__ p) {
+    if (scal[SC_CONV] != 0.0 && scal[SC_ITER] == 0.0) return;
+    // after convergence beta is stale but p is never used again
+    if (scal[SC_CONV] != 0.0) return;
+    const double beta = scal[SC_BETA];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) p[i] = r[i] + beta * p[i];
+}
+
+// residual check: partial(|b - Ax|^2), partial(|b|^2)
+__global__ void __launch_bounds__(PR_BLOCK) k_resid(int nslot, const double *__restrict__ b, const double *__restrict__ Ax,
+                                                    double *__restrict__ partial, int nblk_max) {
+    __shared__ double sm[32];
+    double rr = 0.0, bb = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double bi = b[i], d = bi - Ax[i];
+        rr += d * d;
+        bb += bi * bi;
+    }
+    const double s1 = block_sum(rr, sm);
+    const double s2 = block_sum(bb, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s1; partial[nblk_max + blockIdx.x] = s2; }
+}
+
+// A x = b with x = c->d_P (initial guess in, solution out), b = c->d_b
+int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres) {
+    if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
+    if (solver != LV_SOLVER_CG) return lv_set_error(c, LV_EINVAL, "solver %d not available (LV_SOLVER_CG only)", solver);
+    const int ns = (int)c->nslot;
+    if (iters) *iters = 0;
+    if (relres) *relres = 0.0;
+    if (ns == 0) return LV_OK;
+    cudaStream_t st = c->stream;
+    double *x = c->d_P, *b = c->d_b, *r = c->d_vec[0], *p = c->d_vec[1], *Ap = c->d_vec[2];
+    double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
+    const int NBMAX = 4096;
+    const int nb = pr_grid(c, ns);
+    auto matvec_plain = [&](const double *in, double *out) {
+        LvProfScope prof(c, LV_PROF_MATVEC);
+        k_matvec<false><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, in, out, nullptr, scal);
+        c->launches++;
+    };
+    matvec_plain(x, Ap);
+    {
+        LvProfScope prof(c, LV_PROF_VECOPS);
+        k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
+        k_cg_scalars<<<1, 256, 0, st>>>(0, nb, NBMAX, partial, scal, rtol, atol);
+        c->launches += 2;
+    }
+    int done = 0;
+    const int BATCH = 32;
+    while (done < itmax) {
+        const int todo = itmax - done < BATCH ? itmax - done : BATCH;
+        for (int it = 0; it < todo; it++) {
+            {
+                LvProfScope prof(c, LV_PROF_MATVEC);
+                k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
+                c->launches++;
+            }
+            LvProfScope prof(c, LV_PROF_VECOPS);
+            k_cg_scalars<<<1, 256, 0, st>>>(1, nb, NBMAX, partial, scal, rtol, atol);
+            k_cg_update_xr<<<nb, PR_BLOCK, 0, st>>>(ns, scal, p, Ap, x, r, partial);
+            k_cg_scalars<<<1, 256, 0, st>>>(2, nb, NBMAX, partial, scal, rtol, atol);
+            k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
+            c->launches += 4;
+        }
+        done += todo;
+        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        LV_CUDA(c, cudaStreamSynchronize(st));
+        if (c->h_red[SC_CONV] != 0.0) break;
+    }
+    LV_CUDA(c, cudaGetLastError());
+    if (iters) *iters = (int)c->h_red[SC_ITER];
+    if (relres) { // true residual ||b - A x|| / ||b||
+        matvec_plain(x, Ap);
+        k_resid<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, partial, NBMAX);
+        k_cg_scalars<<<1, 256, 0, st>>>(3, nb, NBMAX, partial, scal, rtol, atol);
+        c->launches += 2;
+        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        LV_CUDA(c, cudaStreamSynchronize(st));
+        const double bn = c->h_red[SC_BNORM2], rn = c->h_red[SC_RES2];
+        *relres = bn > 0.0 ? sqrt(rn / bn) : sqrt(rn);
+    }
+    return LV_OK;
+}
+
+// find_pressure!  pressure.jl:215-225
+int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver, const double *vbc_wall,
+                        int32_t *iters_out, double *relres_out) {
+    LV_TRY(lv_pr_assemble(c, dt));
+    for (int it = 1; it <= niter; it++) {
+        LV_TRY(lv_pr_rhs(c, dt, it > 1, vbc_wall));
+        int iters = 0;
+        double relres = 0.0;
+        LV_TRY(lv_pr_solve(c, solver, rtol, atol, itmax, &iters, relres_out ? &relres : nullptr));
+        if (iters_out) iters_out[it - 1] = iters;
+        if (relres_out) relres_out[it - 1] = relres;
+    }
+    return LV_OK;
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t lv_pressure_create(LvHandle c) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return lv_pr_ensure(c);
+}
+int32_t lv_pressure_destroy(LvHandle c) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_vec[0], &c->d_vec[1],
+                      &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
+    for (double **p : one) { lv_free(c, *p, sizeof(double) * (size_t)c->pr_cap); *p = nullptr; }
+    lv_free(c, c->d_v, sizeof(double2) * (size_t)c->pr_cap); c->d_v = nullptr;
+    lv_free(c, c->d_GP, sizeof(double2) * (size_t)c->pr_cap); c->d_GP = nullptr;
+    lv_free(c, c->d_w, sizeof(double) * (size_t)c->cap_w); c->d_w = nullptr; c->cap_w = 0;
+    c->pr_cap = 0; c->pr_valid = false; c->assembled = false;
+    return LV_OK;
+}
+
+static int upload_fields(LvContext *c, const double *mass, const double *rho, const double *c2, const double *P, const double *v, bool dev) {
+    LV_TRY(lv_pr_ensure(c));
+    const int64_t n = c->n;
+    struct Item { const double *src; double *dst; int nc; double fill; };
+    Item items[] = {{mass, c->d_mass, 1, 0.0}, {rho, c->d_rho, 1, 1.0}, {c2, c->d_c2, 1, 1.0}, {P, c->d_P, 1, 0.0}, {v, (double *)c->d_v, 2, 0.0}};
+    // label-order staging on the device (scratch is also used by scans, so use a private buffer)
+    void *stage = nullptr;
+    if (!dev) LV_TRY(lv_alloc(c, &stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)));
+    int st = LV_OK;
+    for (const Item &it : items) {
+        if (!it.src) continue;
+        const double *src_dev = it.src;
+        if (!dev) {
+            cudaError_t e = cudaMemcpyAsync(stage, it.src, sizeof(double) * (size_t)it.nc * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) { st = lv_set_error(c, LV_ECUDA, "field upload failed: %s", cudaGetErrorString(e)); break; }
+            src_dev = (const double *)stage;
+        }
+        if ((st = lv_gather_to_slots(c, src_dev, it.dst, it.nc, it.fill)) != LV_OK) break;
+    }
+    if (!dev) { cudaStreamSynchronize(c->stream); lv_free(c, stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)); }
+    if (st == LV_OK && mass && rho && c2) c->pr_valid = true;
+    if (mass || rho || c2) c->assembled = false;
+    return st;
+}
+
+int32_t lv_fields_upload(LvHandle c, const double *mass, const double *rho, const double *c2, const double *P, const double *v) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return upload_fields(c, mass, rho, c2, P, v, false);
+}
+int32_t lv_fields_upload_dev(LvHandle c, const double *mass, const double *rho, const double *c2, const double *P, const double *v) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return upload_fields(c, mass, rho, c2, P, v, true);
+}
+
+static int download_slots(LvContext *c, const double *src_slot, double *dst_host, int nc) {
+    const int64_t n = c->n;
+    if (n == 0) return LV_OK;
+    void *stage = nullptr;
+    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)nc * (size_t)n));
+    int st = lv_scatter_to_labels(c, src_slot, (double *)stage, nc);
+    if (st == LV_OK) {
+        cudaError_t e = cudaMemcpyAsync(dst_host, stage, sizeof(double) * (size_t)nc * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "download failed: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(c->stream);
+    lv_free(c, stage, sizeof(double) * (size_t)nc * (size_t)n);
+    return st;
+}
+
+int32_t lv_pressure_download(LvHandle c, double *P_out) {
+    if (!c || !P_out) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_P) return lv_set_error(c, LV_EINVAL, "no pressure workspace");
+    return download_slots(c, c->d_P, P_out, 1);
+}
+
+int32_t lv_pressure_assemble(LvHandle c, double dt) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return lv_pr_assemble(c, dt);
+}
+
+__global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+                                                 const int *__restrict__ rowptr_l, const int *__restrict__ col, const double *__restrict__ w,
+                                                 const double *__restrict__ diag, const unsigned *__restrict__ ent_label,
+                                                 long long *__restrict__ col_l, double *__restrict__ w_l, double *__restrict__ diag_l) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = prim[i];
+    diag_l[i] = diag[s];
+    int o = rowptr_l[i];
+    for (int k = rowptr[s]; k < rowptr[s + 1]; k++) {
+        const int j = col[k];
+        if (j < 0) continue;
+        col_l[o] = (long long)(ent_label[j] & ~LV_IMAGE_BIT) + 1;
+        w_l[o] = w[k];
+        o++;
+    }
+}
+__global__ void __launch_bounds__(256) k_op_deg(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+                                                const int *__restrict__ col, int *__restrict__ deg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = prim[i];
+    int d = 0;
+    for (int k = rowptr[s]; k < rowptr[s + 1]; k++) d += col[k] >= 0;
+    deg[i] = d;
+}
+
+int32_t lv_pressure_operator(LvHandle c, int64_t *rowptr, int64_t *col, double *w, int64_t cap, double *diag) {
+    if (!c || !rowptr) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
+    const int64_t n = c->n, nnz = c->nnz;
+    if (n == 0) { rowptr[0] = 0; return LV_OK; }
+    size_t o_deg = 0, o_rl = sizeof(int) * (size_t)(n + 2), o_col = (o_rl + sizeof(int) * (size_t)(n + 2) + 15) & ~(size_t)15;
+    size_t o_w = o_col + sizeof(long long) * (size_t)nnz, o_d = o_w + sizeof(double) * (size_t)nnz, total = o_d + sizeof(double) * (size_t)n + 64;
+    void *stage = nullptr;
+    LV_TRY(lv_alloc(c, &stage, total));
+    char *base = (char *)stage;
+    int *deg = (int *)(base + o_deg), *rl = (int *)(base + o_rl);
+    long long *col_l = (long long *)(base + o_col);
+    double *w_l = (double *)(base + o_w), *d_l = (double *)(base + o_d);
+    const int nb = (int)((n + 255) / 256);
+    int st = LV_OK;
+    std::string msg;
+    do {
+        k_op_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_col, deg);
+        c->launches++;
+        if ((st = lv_exclusive_scan_i32(c, deg, rl, n)) != LV_OK) break;
+        k_op_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, rl, c->d_col, c->d_w, c->d_diag, c->d_ent_label, col_l, w_l, d_l);
+        c->launches++;
+        int *h_rl = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+        cudaError_t e = cudaMemcpyAsync(h_rl, rl, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) {
+            for (int64_t i = 0; i <= n; i++) rowptr[i] = h_rl[i];
+            const int64_t m = h_rl[n];
+            if ((col || w) && cap < m) st = lv_set_error(c, LV_ECAPACITY, "operator buffer too small: %lld > %lld", (long long)m, (long long)cap);
+            else {
+                if (col) e = cudaMemcpy(col, col_l, sizeof(long long) * (size_t)m, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess && w) e = cudaMemcpy(w, w_l, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost);
+                if (e == cudaSuccess && diag) e = cudaMemcpy(diag, d_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+            }
+        }
+        free(h_rl);
+        if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "operator download failed: %s", cudaGetErrorString(e));
+    } while (0);
+    cudaStreamSynchronize(c->stream);
+    lv_free(c, stage, total);
+    return st;
+}
+
+int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
+    if (!c || !x || !y) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
+    const int64_t n = c->n;
+    if (n == 0) return LV_OK;
+    void *stage = nullptr;
+    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)n));
+    int st = LV_OK;
+    cudaError_t e = cudaMemcpyAsync(stage, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+    if (st == LV_OK) st = lv_gather_to_slots(c, (const double *)stage, c->d_vec[3], 1, 0.0);
+    if (st == LV_OK) st = lv_pr_matvec(c, c->d_vec[3], c->d_vec[4]);
+    cudaStreamSynchronize(c->stream);
+    lv_free(c, stage, sizeof(double) * (size_t)n);
+    if (st == LV_OK) st = download_slots(c, c->d_vec[4], y, 1);
+    return st;
+}
+
+int32_t lv_pressure_rhs(LvHandle c, double dt, int32_t gp_step, const double *vbc_wall, double *b, double *GP) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall));
+    if (b) LV_TRY(download_slots(c, c->d_b, b, 1));
+    if (GP) LV_TRY(download_slots(c, (const double *)c->d_GP, GP, 2));
+    return LV_OK;
+}
+
+int32_t lv_find_pressure_dev(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
+                             const double *vbc_wall, int32_t *iters_out, double *relres_out) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out);
+}
+
+int32_t lv_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
+                         const double *mass, const double *rho, const double *c2, const double *P_in, const double *v,
+                         const double *vbc_wall, double *P_out, int32_t *iters_out, double *relres_out) {
+    if (!c || !mass || !rho || !c2 || !P_in || !v || !P_out) return lv_set_error(c, LV_EINVAL, "null argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(upload_fields(c, mass, rho, c2, P_in, v, false));
+    LV_TRY(lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out));
+    return download_slots(c, c->d_P, P_out, 1);
+}
+
+int32_t lv_pressure_solve(LvHandle c, int32_t solver, const double *b, double *x, double rtol, double atol, int32_t itmax,
+                          int32_t *iters, double *relres) {
+    if (!c || !b || !x) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
+    const int64_t n = c->n;
+    if (n == 0) return LV_OK;
+    void *stage = nullptr;
+    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)n));
+    int st = LV_OK;
+    const double *srcs[2] = {b, x};
+    double *dsts[2] = {c->d_b, c->d_P};
+    for (int k = 0; k < 2 && st == LV_OK; k++) {
+        cudaError_t e = cudaMemcpyAsync(stage, srcs[k], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        if (st == LV_OK) st = lv_gather_to_slots(c, (const double *)stage, dsts[k], 1, 0.0);
+        cudaStreamSynchronize(c->stream);
+    }
+    lv_free(c, stage, sizeof(double) * (size_t)n);
+    if (st == LV_OK) st = lv_pr_solve(c, solver, rtol, atol, itmax, iters, relres);
+    if (st == LV_OK) st = download_slots(c, c->d_P, x, 1);
+    return st;
+}
+
+} // extern "C"

@@ -1,0 +1,77 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/lv_capi.h declares (no compute calls without a GPU), and the host mirror fails loudly
+when the device is missing instead of falling back to anything."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lv_capi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol(lv):
+    path = lv.build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    from lvb200 import _capi
+    assert sorted(_capi.SYMBOLS) == declared  # the ctypes binding covers the whole header
+
+
+def test_sass_is_sm100a_only(lv):
+    """The shipped library carries sm_100a code and nothing else (no multi-arch fallbacks)."""
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "--list-elf", lv.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu(lv):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lv.LvError) as ei:
+        lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 0.1)
+    assert ei.value.status == 4  # LV_ECUDA
+
+
+def test_argument_errors_match_reference(lv):
+    with pytest.raises(ValueError, match="h must be positive"):  # neighborlist.jl:19-21
+        lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 0.1, h=-1.0)
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, "lagrangianvoronoi.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), os.path.join(dirpath, f)
+
+
+def test_synthetic_generator_is_deterministic(lv):
+    import numpy as np
+    a = lv.synthetic.jittered_lattice(16, 0)
+    b = lv.synthetic.jittered_lattice(16, 0)
+    c = lv.synthetic.jittered_lattice(16, 1)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert a.shape == (256, 2) and a.min() > 0 and a.max() < 1
+    # splitmix64 known answers (mix64(1), mix64(2) from the published finaliser)
+    z = lv.synthetic.mix64(np.array([0, 1], dtype=np.uint64))
+    assert int(z[0]) == 0 and int(z[1]) == 0x5692161D100B05E5
+    # strip extraction keeps the global order
+    s = lv.synthetic.jittered_lattice(16, 0, rows=(4, 8))
+    full = a.reshape(16, 16, 2)[:, 4:8].reshape(-1, 2)
+    assert np.array_equal(s, full)

@@ -1,0 +1,179 @@
+"""CPU tests of the oracle (the restatement of the reference) -- no GPU needed.
+
+The reference ships no golden vectors for this path; the oracle is pinned by
+(1) the thresholds of the reference's only test, tests/taylorgreen.jl:112-114, reproduced end to
+end below, and (2) invariants that follow from the reference's definitions.
+"""
+import numpy as np
+import pytest
+
+from .conftest import make_points
+
+
+def _grid(oracle, kind, n_side, xper, yper, seed=0, **kw):
+    xy, dr, bmin, bmax = make_points(kind, n_side, seed)
+    g = oracle.OracleGrid(bmin, bmax, dr, xperiodic=xper, yperiodic=yper, **kw)
+    g.set_points(xy)
+    assert g.remesh() == 0
+    return g, xy, dr
+
+
+def test_magic_path_truncation_is_a_prefix(oracle):
+    """The truncated table (used by the GPU and, for large grids, the oracle) must equal the head of
+    the reference's full (2n1-1)(2n2-1) path up to the first node with rr > rr_max."""
+    for dr, bmax, per in [(1 / 20, (1.0, 1.0), True), (1 / 16, (2.0, 1.0), False), (1 / 30, (1.0, 0.5), True)]:
+        full = oracle.OracleGrid((0, 0), bmax, dr, xperiodic=per, yperiodic=per, full_path=True)
+        trunc = oracle.OracleGrid((0, 0), bmax, dr, xperiodic=per, yperiodic=per, full_path=False)
+        f1, f2, frr = full.magic_path()
+        t1, t2, trr = trunc.magic_path()
+        rr_max = (10 * dr) ** 2
+        k = int(np.argmax(frr > rr_max)) + 1  # prefix incl. the first node beyond rr_max
+        assert k > 1 and k <= len(t1)
+        assert np.array_equal(f1[:k], t1[:k]) and np.array_equal(f2[:k], t2[:k]) and np.array_equal(frr[:k], trr[:k])
+    # head of the order stated in SURVEY.md section 8(a2)
+    head = [(0, 0), (0, -1), (-1, 0), (1, 0), (0, 1), (-1, -1), (1, -1), (-1, 1), (1, 1), (0, -2), (-2, 0), (2, 0), (0, 2)]
+    assert list(zip(t1[:13].tolist(), t2[:13].tolist())) == head
+
+
+@pytest.mark.parametrize("kind,n_side", [("jitter", 48), ("poisson", 40)])
+def test_periodic_invariants(oracle, kind, n_side):
+    g, xy, dr = _grid(oracle, kind, n_side, True, True)
+    n = xy.shape[0]
+    rowptr, edges = g.mesh()
+    area = g.area()
+    assert abs(area.sum() - 1.0) < 1e-12                      # cells tile the torus
+    assert rowptr[-1] == 6 * n                                  # Euler characteristic of the torus
+    assert (edges["label"] > 0).all()                           # no wall edges on a periodic domain
+    rows = np.repeat(np.arange(1, n + 1), np.diff(rowptr))
+    pairs = set(zip(rows.tolist(), edges["label"].tolist()))
+    assert all((b, a) in pairs for a, b in pairs)               # adjacency is symmetric
+    # each polygon is a closed clockwise chain after sort_edges!
+    for i in range(0, n, 37):
+        e = edges[rowptr[i]:rowptr[i + 1]]
+        assert np.array_equal(e["v2"], np.roll(e["v1"], -1, axis=0))
+        x = xy[i]
+        cr = (e["v1"][:, 0] - x[0]) * (e["v2"][:, 1] - x[1]) - (e["v1"][:, 1] - x[1]) * (e["v2"][:, 0] - x[0])
+        assert (cr < 0).all()                                   # x is to the right of v1->v2 (clockwise)
+
+
+def test_walls_and_mixed_periodicity(oracle):
+    for xper, yper in [(False, False), (True, False), (False, True)]:
+        g, xy, dr = _grid(oracle, "rect2x1", 24, xper, yper, seed=3)
+        area = g.area()
+        assert abs(area.sum() - 2.0) < 1e-12
+        rowptr, edges = g.mesh()
+        lab = edges["label"]
+        codes = set(lab[lab <= 0].tolist())
+        expect = set()
+        if not xper:
+            expect |= {-2, -4}
+        if not yper:
+            expect |= {-1, -3}
+        assert codes == expect
+
+
+def test_hex_lattice_areas(oracle):
+    """populate_hex! (populate.jl:149-174): a*b = dr^2, so interior cells have area dr^2."""
+    dr = 1 / 40
+    g = oracle.OracleGrid((0, 0), (1, 1), dr, xperiodic=False, yperiodic=False)
+    assert g.populate_hex() == 0
+    x = g.get("x")
+    area = g.area()
+    interior = (x[:, 0] > 0.1) & (x[:, 0] < 0.9) & (x[:, 1] > 0.1) & (x[:, 1] < 0.9)
+    assert interior.sum() > 500
+    assert np.allclose(area[interior], dr * dr, rtol=1e-12)
+    rowptr, _ = g.mesh()
+    assert (np.diff(rowptr)[interior] == 6).all()
+
+
+def test_thread_count_independence(oracle):
+    """Bucket order is restored to the `julia -t 1` order, so results do not depend on OMP threads."""
+    xy, dr, bmin, bmax = make_points("jitter", 40, 1)
+    out = []
+    for nt in (1, 4):
+        oracle.set_threads(nt)
+        g = oracle.OracleGrid(bmin, bmax, dr, xperiodic=True, yperiodic=True)
+        g.set_points(xy)
+        assert g.remesh() == 0
+        out.append(g.mesh())
+    oracle.set_threads(0)
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1].tobytes() == out[1][1].tobytes()
+
+
+def test_destroyed_and_nan(oracle):
+    g = oracle.OracleGrid((0, 0), (1, 1), 1 / 50, xperiodic=False, yperiodic=False)
+    g.set_points(np.array([[0.5, 0.5], [0.52, 0.5]]))          # two cells in a 50x50 box: r_max exceeded
+    assert g.remesh() == 2
+    g.set_points(np.array([[0.5, np.nan], [0.52, 0.5]]))
+    assert g.remesh() == 3
+
+
+def test_pressure_operator_properties(oracle):
+    g, xy, dr = _grid(oracle, "jitter", 32, True, True, seed=2)
+    n = xy.shape[0]
+    area = g.area()
+    g.set("rho", 1.0); g.set("mass", area); g.set("c2", 100.0)
+    dt = 0.1 * dr
+    g.assemble(dt)
+    rowptr, col, w, diag = g.operator()
+    assert rowptr[-1] == 6 * n and (w > 0).all() and (diag > 0).all()
+    import scipy.sparse as sp
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    L = sp.csr_matrix((w, (rows, col - 1)), shape=(n, n))
+    assert abs(L - L.T).max() < 1e-12 * abs(L).max()            # each side computes its own face length
+    A = sp.diags(diag + np.asarray(L.sum(1)).ravel()) - L
+    x = np.random.default_rng(0).standard_normal(n)
+    assert np.allclose(g.matvec(x), A @ x, rtol=1e-12, atol=1e-9 * abs(A @ x).max())
+    assert x @ (A @ x) > 0
+
+
+def test_solvers_agree(oracle):
+    """MINRES restatement and CG converge to the same pressure (solution-level parity is solver independent)."""
+    from lvb200 import synthetic
+    g, xy, dr = _grid(oracle, "jitter", 32, True, True, seed=0)
+    area = g.area()
+    v, P = synthetic.taylor_green_fields(xy)
+    g.set("rho", 1.0); g.set("mass", area); g.set("c2", 100.0); g.set("v", v); g.set("P", P)
+    dt = 0.1 * dr
+    g.assemble(dt)
+    b, P0, _ = g.rhs(dt)
+    x_cg, it_cg = g.cg(b, P0, rtol=1e-13)
+    x_mr, it_mr = g.minres(b, P0, rtol=1e-13, atol=0.0, itmax=5000)
+    assert it_cg > 5 and it_mr > 5
+    assert np.linalg.norm(g.matvec(x_cg) - b) <= 1e-11 * np.linalg.norm(b)
+    assert np.abs(x_cg - x_mr).max() <= 1e-8 * np.abs(x_cg).max()
+
+
+def test_taylor_green_reference_thresholds(oracle):
+    """The reference's only test (tests/taylorgreen.jl): N = 80, 80 steps, hex seeding, the canonical
+    step!, and E_err < 1e-8, v_err < 0.01, P_err < 0.01 (:112-114).  This pins the restatement of the
+    remesh + pressure path (and of the callers either side of it) end to end."""
+    from lvb200 import synthetic
+    N = 80; Re = 400.0; rho0 = 1.0; dr = 1.0 / N; dt = 0.1 * dr; c0 = 50.0; gamma = 1.4; t_end = 0.1
+    P0 = rho0 * c0 ** 2 / gamma
+    g = oracle.OracleGrid((0, 0), (1, 1), dr, xperiodic=True, yperiodic=True)
+    assert g.populate_hex() == 0
+    x = g.get("x"); area = g.area()
+    v, P = synthetic.taylor_green_fields(x, 0.0, Re)
+    g.set("v", v); g.set("rho", rho0); g.set("mass", rho0 * area); g.set("P", P)
+    g.set("e", 0.5 * (v ** 2).sum(1) + P / (rho0 * (gamma - 1.0))); g.set("mu", 1.0 / Re)
+    t = 0.0; k = 0; E0 = None; errs = None
+    k_frame = max(round(t_end / (20 * dt)), 1)                   # simulation.jl:63-66, nframes = 20
+    while t < t_end:                                             # simulation.jl:69-89
+        k += 1
+        assert g.move(dt) == 0
+        g.stiffened_eos(gamma, P0)
+        g.find_pressure(dt)
+        g.pressure_step(dt); g.find_D(); g.viscous_step(dt, False); g.find_dv(dt)
+        assert g.relaxation_step(dt) == 0
+        if k % k_frame == 0:                                     # postproc!  tests/taylorgreen.jl:73-99
+            x = g.get("x"); area = g.area(); Pn = g.get("P"); vn = g.get("v"); m = g.get("mass"); e = g.get("e")
+            p_avg = (area * Pn).sum()
+            E = (m * e).sum()
+            E0 = E if E0 is None else E0
+            ve, Pe = synthetic.taylor_green_fields(x, t, Re)
+            errs = (E - E0, np.sqrt((area * ((vn - ve) ** 2).sum(1)).sum()), np.sqrt((area * (Pn - p_avg - Pe) ** 2).sum()))
+        t += dt
+    assert k == 80
+    E_err, v_err, P_err = errs
+    assert E_err < 1e-8 and v_err < 0.01 and P_err < 0.01

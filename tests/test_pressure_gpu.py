@@ -1,0 +1,123 @@
+"""GPU parity tests of the pressure path (K3 assembly, K4 matvec, RHS, K5 Krylov loop) through the
+C ABI against the oracle.
+
+Bar (north_star): pressure after a solve to 1e-10 residual within 1e-8 relative.  Assembly, matvec
+and RHS mirror the reference's operation order and are compared at 1e-13.
+"""
+import numpy as np
+import pytest
+
+from .conftest import make_points
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(lv, oracle, kind, n_side, xper, yper, seed, c0, rho_jump=False):
+    xy, dr, bmin, bmax = make_points(kind, n_side, seed)
+    og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=xper, yperiodic=yper)
+    og.set_points(xy); assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper)
+    g.set_points(xy); lv.remesh(g)
+    area = og.area()
+    v, P = lv.synthetic.taylor_green_fields(xy)
+    rho = np.ones(len(xy))
+    if rho_jump:
+        rho[xy[:, 1] > 0.5 * (bmin[1] + bmax[1])] = 7.0
+    mass = rho * area
+    c2 = np.full(len(xy), c0 * c0)
+    for name, val in (("rho", rho), ("mass", mass), ("c2", c2), ("v", v), ("P", P)):
+        og.set(name, val)
+        getattr(g, name)[...] = val
+    return g, og, xy, dr
+
+
+@pytest.mark.parametrize("kind,n_side,xper,yper,seed,rho_jump", [
+    ("jitter", 64, True, True, 0, False),
+    ("poisson", 48, False, False, 1, True),
+    ("rect2x1", 32, True, False, 2, True),
+])
+def test_operator_matvec_rhs(lv, oracle, kind, n_side, xper, yper, seed, rho_jump):
+    g, og, xy, dr = _setup(lv, oracle, kind, n_side, xper, yper, seed, 10.0, rho_jump)
+    dt = 0.1 * dr
+    s = lv.PressureSolver(g)
+    s.upload_fields(g.mass, g.rho, g.c2, g.P, g.v)
+    s.assemble(dt)
+    og.assemble(dt)
+    rp, col, w, diag = s.operator()
+    rp0, col0, w0, diag0 = og.operator()
+    assert np.array_equal(rp, rp0) and np.array_equal(col, col0)          # same stencil, same order
+    assert np.allclose(w, w0, rtol=1e-13, atol=0) and np.allclose(diag, diag0, rtol=1e-13, atol=0)
+    x = np.random.default_rng(1).standard_normal(len(xy))
+    y = lv.mul(np.zeros_like(x), s, x)
+    y0 = og.matvec(x)
+    assert np.allclose(y, y0, rtol=1e-12, atol=1e-12 * np.abs(y0).max())
+    vbc = np.array([[0.3, 0.0], [0.0, -0.2], [0.1, 0.1], [0.0, 0.4]])       # per wall code UP RIGHT DOWN LEFT
+    for gp_step in (False, True):
+        b, GP = s.rhs(dt, gp_step, vbc)
+        b0, _, GP0 = og.rhs(dt, gp_step, vbc)
+        assert np.allclose(b, b0, rtol=1e-12, atol=1e-12 * np.abs(b0).max())
+        assert np.allclose(GP, GP0, rtol=1e-12, atol=1e-12 * np.abs(GP0).max())
+
+
+@pytest.mark.parametrize("c0,n_side", [(10.0, 64), (1000.0, 48)])
+def test_solve_matches_oracle(lv, oracle, c0, n_side):
+    """Solve A P = b to a true relative residual of 1e-10 on both sides; P must agree to 1e-8 relative
+    (north_star).  c0 = 1000 is the near-incompressible taylorgreen setting (kappa ~ 1e5)."""
+    g, og, xy, dr = _setup(lv, oracle, "jitter", n_side, True, True, 0, c0)
+    dt = 0.1 * dr
+    s = lv.PressureSolver(g)
+    s.upload_fields(g.mass, g.rho, g.c2, g.P, g.v)
+    s.assemble(dt); og.assemble(dt)
+    b0, P0, _ = og.rhs(dt)
+    x_ref, _ = og.cg(b0, P0, rtol=1e-13, itmax=200000)
+    assert np.linalg.norm(og.matvec(x_ref) - b0) <= 1e-10 * np.linalg.norm(b0)
+    b, _ = s.rhs(dt)
+    x, iters, relres = s.solve(b, P0, rtol=1e-12, atol=0.0, itmax=200000)
+    assert iters > 5
+    assert relres <= 1e-10                                                  # true residual, recomputed
+    assert np.linalg.norm(og.matvec(x) - b0) <= 2e-10 * np.linalg.norm(b0)  # and checked by the oracle's operator
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+
+
+def test_find_pressure_fixed_point_loop(lv, oracle):
+    """find_pressure! (pressure.jl:215-225): 10 x (RHS + warm-started solve).  With tight tolerances the
+    result is solver independent; compare against the oracle's CG at the same settings."""
+    g, og, xy, dr = _setup(lv, oracle, "jitter", 48, True, True, 3, 50.0)
+    dt = 0.1 * dr
+    s = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    lv.find_pressure(s, dt, 10)
+    og.find_pressure(dt, 10, rtol=1e-12, atol=0.0, itmax=20000, solver="cg")
+    P_ref = og.get("P")
+    assert s.iters.shape == (10,) and (s.iters > 0).all()
+    assert np.abs(g.P - P_ref).max() <= 1e-8 * np.abs(P_ref).max()
+
+
+def test_find_pressure_with_walls_and_moving_lid(lv, oracle):
+    g, og, xy, dr = _setup(lv, oracle, "poisson", 40, False, False, 4, 20.0, rho_jump=True)
+    dt = 0.1 * dr
+    vbc = np.array([[1.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]])        # lid-driven cavity style
+    s = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    lv.find_pressure(s, dt, 3, boundary_velocity=lambda m, label: vbc[-label - 1])
+    og.find_pressure(dt, 3, rtol=1e-12, atol=0.0, itmax=20000, solver="cg", vbc_wall=vbc)
+    P_ref = og.get("P")
+    assert np.abs(g.P - P_ref).max() <= 1e-8 * np.abs(P_ref).max()
+
+
+def test_reference_default_tolerances_converge(lv):
+    """Reference settings (atol = rtol = 1e-6, itmax = 1000, niter = 10) at 256k cells: every pass
+    converges and the true residual is small; linearity of the operator as a size-independent check."""
+    M = 512
+    xy = lv.synthetic.jittered_lattice(M, 0)
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1.0 / M, xperiodic=True, yperiodic=True)
+    g.set_points(xy); lv.remesh(g)
+    v, P = lv.synthetic.taylor_green_fields(xy)
+    g.rho[...] = 1.0; g.mass[...] = lv.area(g); g.c2[...] = 100.0; g.v[...] = v; g.P[...] = P
+    s = lv.PressureSolver(g, verbose=True)
+    lv.find_pressure(s, 0.1 / M)
+    assert (s.iters < 1000).all() and (s.relres < 1e-4).all()
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal(M * M), rng.standard_normal(M * M)
+    ya, yb = lv.mul(np.zeros(M * M), s, a), lv.mul(np.zeros(M * M), s, b)
+    yab = lv.mul(np.zeros(M * M), s, 2.0 * a - 3.0 * b)
+    assert np.allclose(yab, 2.0 * ya - 3.0 * yb, rtol=1e-11, atol=1e-9 * np.abs(yab).max())
+    assert abs(a @ yb - b @ ya) <= 1e-10 * abs(a @ yb)                      # symmetric to rounding

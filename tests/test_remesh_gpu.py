@@ -1,0 +1,147 @@
+"""GPU parity tests of the remesh path (K1 + K2) through the C ABI against the oracle.
+
+Bar (BASELINE.json north_star): neighbour connectivity bit-exact; areas, face lengths and centroids
+within 1e-12 relative.  The kernel mirrors the reference's operation order, so vertices are in
+fact compared bit for bit as well.
+"""
+import numpy as np
+import pytest
+
+from .conftest import make_points
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # north_star tolerance for areas / face lengths / centroids
+
+
+def _both(lv, oracle, kind, n_side, xper, yper, seed=0):
+    xy, dr, bmin, bmax = make_points(kind, n_side, seed)
+    og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=xper, yperiodic=yper)
+    og.set_points(xy)
+    assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper)
+    g.set_points(xy)
+    lv.remesh(g)
+    return g, og, xy, dr
+
+
+def _assert_mesh_equal(g, og, lv, bitwise=True):
+    rowptr, edges = og.mesh()
+    assert np.array_equal(g.rowptr, rowptr)                       # same degree per polygon
+    assert np.array_equal(g.edges["label"], edges["label"])       # connectivity bit-exact, same edge order
+    if bitwise:
+        assert g.edges.tobytes() == edges.tobytes()               # vertices bit-identical
+    a_ref, c_ref = og.area(), og.centroid()
+    assert np.allclose(lv.area(g), a_ref, rtol=RTOL, atol=0)
+    assert np.allclose(lv.centroid(g), c_ref, rtol=RTOL, atol=RTOL * np.abs(c_ref).max())
+    ln = np.hypot(*(g.edges["v1"] - g.edges["v2"]).T)
+    ln_ref = np.hypot(*(edges["v1"] - edges["v2"]).T)
+    assert np.allclose(ln, ln_ref, rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("kind,n_side,xper,yper,seed", [
+    ("jitter", 64, True, True, 0),
+    ("jitter", 256, True, True, 1),
+    ("jitter", 37, True, True, 2),
+    ("poisson", 96, True, True, 0),
+    ("poisson", 64, False, False, 1),
+    ("rect2x1", 48, False, False, 2),
+    ("rect2x1", 40, True, False, 3),
+    ("rect2x1", 40, False, True, 4),
+    ("lattice", 32, True, True, 0),     # degenerate: decided by SIGNUM_EPS and cut order, still identical
+    ("lattice", 32, False, False, 0),
+])
+def test_remesh_matches_oracle(lv, oracle, kind, n_side, xper, yper, seed):
+    g, og, xy, dr = _both(lv, oracle, kind, n_side, xper, yper, seed)
+    _assert_mesh_equal(g, og, lv)
+
+
+def test_remesh_invariants_at_scale(lv):
+    """1M cells: size-independent properties (no oracle needed): torus Euler count, tiling, symmetry."""
+    M = 1024
+    xy = lv.synthetic.jittered_lattice(M, 0)
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1.0 / M, xperiodic=True, yperiodic=True)
+    g.set_points(xy)
+    lv.remesh(g)
+    n = M * M
+    assert g.rowptr[-1] == 6 * n
+    assert abs(lv.area(g).sum() - 1.0) < 1e-10
+    lab = g.edges["label"]
+    assert lab.min() >= 1 and lab.max() <= n
+    rows = np.repeat(np.arange(1, n + 1, dtype=np.int64), np.diff(g.rowptr))
+    fwd = np.sort(rows * (n + 1) + lab)
+    bwd = np.sort(lab * (n + 1) + rows)
+    assert np.array_equal(fwd, bwd)                                # adjacency symmetric
+    # idempotence: a second remesh of the same points reproduces the mesh bit for bit
+    e0 = g.edges.copy(); r0 = g.rowptr.copy()
+    lv.remesh(g)
+    assert np.array_equal(g.rowptr, r0) and g.edges.tobytes() == e0.tobytes()
+
+
+def test_empty_and_tiny_inputs(lv, oracle):
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 0.25)       # r_max = 2.5 covers the box
+    g.set_points(np.zeros((0, 2)))
+    lv.remesh(g)
+    assert g.rowptr.tolist() == [0] and g.edges.shape[0] == 0
+    xy = np.array([[0.31, 0.42]])
+    g.set_points(xy)
+    lv.remesh(g)                                                    # one polygon = the whole box, 4 wall edges
+    og = oracle.OracleGrid((0, 0), (1, 1), 0.25)
+    og.set_points(xy); assert og.remesh() == 0
+    _assert_mesh_equal(g, og, lv)
+    assert sorted(g.edges["label"].tolist()) == [-4, -3, -2, -1]
+    assert abs(lv.area(g)[0] - 1.0) < 1e-15
+    # a lone cell in a box wider than r_max: the reference throws (voronoigrid.jl:63-65), so do both
+    og2 = oracle.OracleGrid((0, 0), (1, 1), 0.1)
+    og2.set_points(xy); assert og2.remesh() == 2
+    g2 = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 0.1)
+    g2.set_points(xy)
+    with pytest.raises(lv.LvError, match="destroyed"):
+        lv.remesh(g2)
+
+
+def test_errors_match_reference(lv):
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1 / 50)
+    g.set_points(np.array([[0.5, 0.5], [0.52, 0.5]]))
+    with pytest.raises(lv.LvError, match="The Voronoi Mesh has been destroyed."):  # voronoigrid.jl:63-65
+        lv.remesh(g)
+    g.set_points(np.array([[0.5, np.nan], [0.52, 0.5]]))
+    with pytest.raises(lv.LvError) as ei:
+        lv.remesh(g)
+    assert ei.value.status == 3
+    # the handle stays usable after an error
+    xy, dr, bmin, bmax = make_points("jitter", 20, 0)
+    g2 = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=True, yperiodic=True)
+    g2.set_points(xy); lv.remesh(g2)
+    assert g2.rowptr[-1] == 6 * 400
+
+
+def test_crowded_bucket_and_capacity_retry(lv, oracle):
+    """Clustered generators: buckets with >16 labels (heap-sorted) and polygons that outgrow the
+    first shared-memory capacity level, forcing the kernel's retry path."""
+    rng = np.random.default_rng(5)
+    dr = 1 / 16
+    base = rng.random((200, 2))
+    th = np.linspace(0, 2 * np.pi, 40, endpoint=False)
+    ring = 0.5 + 0.07 * np.stack([np.cos(th), np.sin(th)], 1)     # 40 neighbours around one centre cell
+    cluster = 0.25 + 0.01 * rng.random((60, 2))                     # 60 generators inside one bucket
+    xy = np.concatenate([[[0.5, 0.5]], ring, cluster, base[(np.hypot(*(base - 0.5).T) > 0.12)]])
+    og = oracle.OracleGrid((0, 0), (1, 1), dr)
+    og.set_points(xy); assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), dr)
+    g.set_points(xy); lv.remesh(g)
+    assert np.diff(g.rowptr).max() >= 30
+    _assert_mesh_equal(g, og, lv)
+
+
+def test_set_rects_like_piston(lv, oracle):
+    """examples/piston.jl:43-47 moves a wall by mutating the rectangles without rebuilding the cell list."""
+    xy, dr, bmin, bmax = make_points("poisson", 32, 7)
+    xy = xy * np.array([0.8, 1.0])
+    og = oracle.OracleGrid(bmin, bmax, dr); og.set_points(xy)
+    og.set_rects((0, 0), (0.8, 1.0), (0, 0), (0.8, 1.0)); assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr); g.set_points(xy)
+    g.set_rects(lv.Rectangle((0, 0), (0.8, 1.0)), lv.Rectangle((0, 0), (0.8, 1.0)))
+    lv.remesh(g)
+    _assert_mesh_equal(g, og, lv)
+    assert abs(lv.area(g).sum() - 0.8) < 1e-12
