@@ -89,6 +89,10 @@ int32_t lv_remesh_dev(LvHandle h, int64_t n, const double *xy_dev);
 int32_t lv_mesh_nnz(LvHandle h, int64_t *nnz); /* synchronises */
 int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area,
                          double *centroid);
+/* which kernel produced the current mesh: level 0/1 = linked-slot kernel (12/16 slots), 2/3/4 =
+ * edge-list kernel (16/32/128 edges); anomalies = remeshes replayed by the edge-list kernel because
+ * the linked-slot kernel met a degenerate configuration (results are identical either way) */
+int32_t lv_clip_info(LvHandle h, int32_t *level, int64_t *anomalies);
 /* face lengths len(e) (geometry.jl:136) and midpoints (geometry.jl:145) in the same CSR order */
 int32_t lv_mesh_faces(LvHandle h, double *length, double *midpoint, int64_t cap);
 

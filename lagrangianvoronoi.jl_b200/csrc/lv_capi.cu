@@ -284,6 +284,13 @@ int32_t lv_remesh_dev(LvHandle c, int64_t n, const double *xy_dev) {
     return remesh_common(c, n);
 }
 
+int32_t lv_clip_info(LvHandle c, int32_t *level, int64_t *anomalies) {
+    if (!c) return LV_EINVAL;
+    if (level) *level = c->clip_last_level;
+    if (anomalies) *anomalies = c->clip_anomalies;
+    return LV_OK;
+}
+
 int32_t lv_mesh_nnz(LvHandle c, int64_t *nnz) {
     if (!c || !nnz) return LV_EINVAL;
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");

@@ -15,41 +15,15 @@
 // CSR offsets are produced in the same launch by a decoupled look-back scan over tiles
 // (dynamic tile ids from a ticket counter guarantee forward progress), so edges are written
 // straight to their final position: no second pass over the mesh.
-#include "lv_internal.cuh"
-
-#define SIGNUM_EPS 4.440892098500626e-16 // 2*eps(Float64)  polygon.jl:2
-#define BD_UP (-1)                       // polygon.jl:4-7
-#define BD_RIGHT (-2)
-#define BD_DOWN (-3)
-#define BD_LEFT (-4)
-
-struct ClipArgs {
-    LvGridParams g;
-    const LvPathNode *path;
-    const int *cell_start;
-    const unsigned *ent_label;
-    const double2 *ent_xy;
-    const int *prim_of_label;
-    int nslot;
-    int *rowptr;
-    int *col;
-    double2 *v1, *v2;
-    double *area;
-    double2 *cen;
-    unsigned long long *tile_state;
-    int *flags;
-    long long cap_nnz;
-};
+#include "lv_clip.cuh"
+#include <cstdlib>
+#include <cstring>
 
 __device__ __forceinline__ int signum(double x) { // polygon.jl:9-16
     if (x < -SIGNUM_EPS) return -1;
     else if (x > SIGNUM_EPS) return 1;
     return 0;
 }
-
-#define TS_AGG (1ull << 62)
-#define TS_INC (2ull << 62)
-#define TS_MASK ((1ull << 62) - 1)
 
 // shared-memory polygon: edge k of thread t at [k * BLOCK + t]
 template <int MAXE, int BLOCK>
@@ -180,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
             }
             if (p.ovf) break;
         }
-        if (p.ovf) { atomicOr(&a.flags[LVF_OVERFLOW], 1); p.m = 0; }
+        if (p.ovf) { atomicOr(&a.flags[LVF_OVERFLOW], OVF_POLY); p.m = 0; }
         // sort_edges!  IO.jl:35-48
         for (int i = 0; i < p.m; i++) {
             const double2 last = p.V2(i);
@@ -262,7 +236,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
         a.area[slot] = area;
         a.cen[slot] = cen;
         if (off + deg > a.cap_nnz) {
-            if (deg > 0) atomicOr(&a.flags[LVF_OVERFLOW], 2);
+            if (deg > 0) atomicOr(&a.flags[LVF_OVERFLOW], OVF_NNZ);
         } else {
             for (int k = 0; k < deg; k++) {
                 const int l = p.L(k);
@@ -295,11 +269,20 @@ static int launch_clip(LvContext *c, const ClipArgs &a) {
     return LV_OK;
 }
 
+// Capacity / exactness ladder.  Levels 0-1: linked-slot kernel (12 / 16 slots per polygon);
+// levels 2-4: edge-list kernel (16 / 32 / 128 edges).  A polygon that outgrows a level moves the
+// (sticky) capacity level up; an anomaly reported by the linked-slot kernel reruns this remesh
+// with the edge-list kernel, which replays the reference literally.
+// LV_CLIP_MODE=plain forces the edge-list kernel (used by the tests to cross-check both).
 int lv_clip_run(LvContext *c) {
     const int64_t nslot = c->nslot;
     // edge buffers: 6n on a torus (Euler), fewer with walls plus the wall edges; grow on demand
     int64_t need_nnz = 7 * nslot + 1024;
-    for (int attempt = 0; attempt < 6; attempt++) {
+    const char *mode = getenv("LV_CLIP_MODE");
+    const bool force_plain = mode && !strcmp(mode, "plain");
+    int level = c->clip_level;
+    if (force_plain && level < 2) level = 2;
+    for (int attempt = 0; attempt < 8; attempt++) {
         if (need_nnz > c->cap_nnz) {
             int64_t c1 = c->cap_nnz, c2 = c->cap_nnz, c3 = c->cap_nnz;
             LV_TRY(lv_ensure(c, (void **)&c->d_col, &c1, need_nnz, sizeof(int)));
@@ -307,8 +290,7 @@ int lv_clip_run(LvContext *c) {
             LV_TRY(lv_ensure(c, (void **)&c->d_v2, &c3, need_nnz, sizeof(double2)));
             c->cap_nnz = need_nnz;
         }
-        const int level = c->clip_level;
-        const int block = level == 0 ? 128 : (level == 1 ? 64 : 32);
+        const int block = level <= 1 ? 32 : (level == 2 ? 128 : (level == 3 ? 64 : 32)); // tile size
         const int64_t ntiles = (nslot + block - 1) / block;
         LV_TRY(lv_ensure(c, (void **)&c->d_tile_state, &c->cap_tiles, ntiles + 1, sizeof(unsigned long long)));
         LV_CUDA(c, cudaMemsetAsync(c->d_tile_state, 0, sizeof(unsigned long long) * (size_t)(ntiles + 1), c->stream));
@@ -332,10 +314,12 @@ int lv_clip_run(LvContext *c) {
         a.cap_nnz = c->cap_nnz;
         {
             LvProfScope prof(c, LV_PROF_CLIP);
-            if (level == 0) LV_TRY((launch_clip<16, 128>(c, a)));
-            else if (level == 1) LV_TRY((launch_clip<32, 64>(c, a)));
+            if (level <= 1) LV_TRY(lv_clip_launch_fast(c, a, level));
+            else if (level == 2) LV_TRY((launch_clip<16, 128>(c, a)));
+            else if (level == 3) LV_TRY((launch_clip<32, 64>(c, a)));
             else LV_TRY((launch_clip<128, 32>(c, a)));
         }
+        c->clip_last_level = level;
         LV_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
         LV_CUDA(c, cudaStreamSynchronize(c->stream));
         if (nslot == 0) { c->nnz = 0; return LV_OK; }
@@ -343,11 +327,15 @@ int lv_clip_run(LvContext *c) {
         if (c->h_flags[LVF_DESTROYED]) return lv_set_error(c, LV_EDESTROYED, "The Voronoi Mesh has been destroyed.");
         const int ov = c->h_flags[LVF_OVERFLOW];
         if (ov == 0) { c->nnz = c->h_flags[LVF_NNZ]; return LV_OK; }
-        if (ov & 1) { // a polygon outgrew the shared-memory edge list: rerun with the next capacity level
-            if (c->clip_level >= 2) return lv_set_error(c, LV_ECAPACITY, "polygon with more than 128 edges during clipping");
-            c->clip_level++;
+        if (ov & OVF_NNZ) need_nnz = (int64_t)c->h_flags[LVF_NNZ] + 1024;
+        if (ov & OVF_POLY) { // capacity: sticky
+            if (level >= 4) return lv_set_error(c, LV_ECAPACITY, "polygon with more than 128 edges during clipping");
+            level = level == 0 ? 1 : (level < 3 ? 3 : 4);
+            c->clip_level = level;
+        } else if (ov & OVF_ANOMALY) { // exactness: this remesh only
+            c->clip_anomalies++;
+            level = level == 0 ? 2 : 3;
         }
-        if (ov & 2) need_nnz = (int64_t)c->h_flags[LVF_NNZ] + 1024;
     }
     return lv_set_error(c, LV_ECAPACITY, "clip kernel did not fit after retries");
 }

@@ -1,0 +1,40 @@
+// lv_clip.cuh -- declarations shared by the two clipping kernels (lv_clip.cu: reference-order
+// edge-list kernel, lv_clip_fast.cu: linked-slot kernel).
+#pragma once
+#include "lv_internal.cuh"
+
+#define SIGNUM_EPS 4.440892098500626e-16 // 2*eps(Float64)  polygon.jl:2
+#define BD_UP (-1)                       // polygon.jl:4-7
+#define BD_RIGHT (-2)
+#define BD_DOWN (-3)
+#define BD_LEFT (-4)
+
+struct ClipArgs {
+    LvGridParams g;
+    const LvPathNode *path;
+    const int *cell_start;
+    const unsigned *ent_label;
+    const double2 *ent_xy;
+    const int *prim_of_label;
+    int nslot;
+    int *rowptr;
+    int *col;
+    double2 *v1, *v2;
+    double *area;
+    double2 *cen;
+    unsigned long long *tile_state;
+    int *flags;
+    long long cap_nnz;
+};
+
+
+#define TS_AGG (1ull << 62)
+#define TS_INC (2ull << 62)
+#define TS_MASK ((1ull << 62) - 1)
+
+// flags[LVF_OVERFLOW] bits
+#define OVF_POLY 1   // a polygon outgrew the kernel's edge capacity
+#define OVF_NNZ 2    // the CSR edge buffers are too small
+#define OVF_ANOMALY 4 // the fast kernel met a case it does not handle exactly (rerun with the edge-list kernel)
+
+int lv_clip_launch_fast(LvContext *c, const ClipArgs &a, int level); // lv_clip_fast.cu

@@ -71,7 +71,9 @@ struct LvContext {
     int64_t cap_tiles = 0;
     int *d_flags = nullptr; // [8] device status words, see LvFlag
     int *h_flags = nullptr; // pinned mirror
-    int clip_level = 0;     // polygon capacity level that last succeeded
+    int clip_level = 0;     // sticky polygon-capacity level (see lv_clip_run)
+    int clip_last_level = 0; // level that produced the current mesh
+    int64_t clip_anomalies = 0; // remeshes that had to be replayed by the edge-list kernel
     bool mesh_valid = false;
     // scratch for scans / label-order staging
     void *d_scratch = nullptr;

@@ -152,6 +152,12 @@ class VoronoiGrid:
         check(self._L.lv_prof_get(self._h, _capi.PROF_SLOTS[slot], C.byref(ms), C.byref(cnt)), self._h)
         return ms.value, cnt.value
 
+    def clip_info(self):
+        """(level, anomalies): which clipping kernel produced the current mesh (see lv_capi.h)."""
+        lvl, an = C.c_int32(), C.c_int64()
+        check(self._L.lv_clip_info(self._h, C.byref(lvl), C.byref(an)), self._h)
+        return lvl.value, an.value
+
     def launch_count(self) -> int:
         return int(self._L.lv_launch_count(self._h))
 

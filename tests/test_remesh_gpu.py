@@ -56,6 +56,26 @@ def test_remesh_matches_oracle(lv, oracle, kind, n_side, xper, yper, seed):
     _assert_mesh_equal(g, og, lv)
 
 
+def test_both_kernels_agree_and_fast_path_is_used(lv, oracle, monkeypatch):
+    """The linked-slot kernel (default) and the edge-list kernel (LV_CLIP_MODE=plain) must give the same
+    bytes; generic inputs must stay on the linked-slot kernel, degenerate lattices may be replayed."""
+    for kind, n_side, per in (("jitter", 128, True), ("poisson", 96, False), ("lattice", 48, True)):
+        xy, dr, bmin, bmax = make_points(kind, n_side, 11)
+        out = {}
+        for mode in ("fast", "plain"):
+            monkeypatch.setenv("LV_CLIP_MODE", mode)
+            g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=per, yperiodic=per)
+            g.set_points(xy); lv.remesh(g)
+            out[mode] = (g.rowptr.copy(), g.edges.copy(), lv.area(g).copy(), lv.centroid(g).copy(), g.clip_info())
+        monkeypatch.delenv("LV_CLIP_MODE")
+        f, p = out["fast"], out["plain"]
+        assert np.array_equal(f[0], p[0]) and f[1].tobytes() == p[1].tobytes()
+        assert f[2].tobytes() == p[2].tobytes() and f[3].tobytes() == p[3].tobytes()
+        assert p[4][0] >= 2
+        if kind != "lattice":
+            assert f[4] == (0, 0) or f[4] == (1, 0), f[4]     # no anomaly, linked-slot kernel
+
+
 def test_remesh_invariants_at_scale(lv):
     """1M cells: size-independent properties (no oracle needed): torus Euler count, tiling, symmetry."""
     M = 1024
