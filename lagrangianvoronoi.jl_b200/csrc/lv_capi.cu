@@ -188,7 +188,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
-                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
+                    c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
@@ -301,15 +301,15 @@ int32_t lv_mesh_nnz(LvHandle c, int64_t *nnz) {
 } // extern "C"
 
 // label-order view: degree gather, scan, copy.  40-byte Edge records with 1-based labels.
-__global__ void __launch_bounds__(256) k_label_deg(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(256) k_label_deg(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                    int *__restrict__ deg) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = prim[i];
-    deg[i] = rowptr[s + 1] - rowptr[s];
+    deg[i] = rdeg[s];
 }
 
-__global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                     const int *__restrict__ rowptr_l, const int *__restrict__ col,
                                                     const double2 *__restrict__ v1, const double2 *__restrict__ v2,
                                                     const unsigned *__restrict__ ent_label, const double *__restrict__ area,
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__rest
     if (i > n) return;
     if (i == n) { if (rowptr64) rowptr64[n] = rowptr_l[n]; return; }
     const int s = prim[i];
-    const int r0 = rowptr[s], r1 = rowptr[s + 1];
+    const int r0 = rowptr[s], r1 = r0 + rdeg[s];
     const int o = rowptr_l[i];
     if (rowptr64) rowptr64[i] = o;
     if (area_l) area_l[i] = area[s];
@@ -358,10 +358,10 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
     const int nb = (int)((n + 256) / 256);
     int st = LV_OK;
     do {
-        k_label_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, deg);
+        k_label_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, deg);
         c->launches++;
         if ((st = lv_exclusive_scan_i32(c, deg, rl, n)) != LV_OK) break;
-        k_label_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
+        k_label_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
                                                 c->d_area, c->d_cen, rowptr ? r64 : nullptr, edges ? e_l : nullptr,
                                                 area ? area_l : nullptr, centroid ? cen_l : nullptr);
         c->launches++;

@@ -251,10 +251,11 @@ int lv_cells_build(LvContext *c) {
         int64_t need = nslot + 1;
         if (need > cap) {
             int64_t ncap = need + need / 16 + 1024;
-            int64_t c1 = cap, c2 = cap, c3 = cap, c4 = cap, c5 = cap;
+            int64_t c1 = cap, c2 = cap, c3 = cap, c4 = cap, c5 = cap, c6 = cap;
             LV_TRY(lv_ensure(c, (void **)&c->d_ent_label, &c1, ncap, sizeof(unsigned)));
             LV_TRY(lv_ensure(c, (void **)&c->d_ent_xy, &c2, ncap, sizeof(double2)));
             LV_TRY(lv_ensure(c, (void **)&c->d_rowptr, &c3, ncap + 1, sizeof(int)));
+            LV_TRY(lv_ensure(c, (void **)&c->d_deg, &c6, ncap + 1, sizeof(unsigned char)));
             LV_TRY(lv_ensure(c, (void **)&c->d_area, &c4, ncap, sizeof(double)));
             LV_TRY(lv_ensure(c, (void **)&c->d_cen, &c5, ncap, sizeof(double2)));
             c->cap_slot = ncap;

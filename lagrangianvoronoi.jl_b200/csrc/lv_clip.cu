@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
     const long long off = s_prefix + local_off;
     if (slot < a.nslot) {
         a.rowptr[slot] = (int)off;
+        a.rdeg[slot] = (unsigned char)deg;
         a.area[slot] = area;
         a.cen[slot] = cen;
         if (off + deg > a.cap_nnz) {
@@ -304,6 +305,7 @@ int lv_clip_run(LvContext *c) {
         a.prim_of_label = c->d_prim_of_label;
         a.nslot = (int)nslot;
         a.rowptr = c->d_rowptr;
+        a.rdeg = c->d_deg;
         a.col = c->d_col;
         a.v1 = c->d_v1;
         a.v2 = c->d_v2;

@@ -17,7 +17,8 @@ struct ClipArgs {
     const double2 *ent_xy;
     const int *prim_of_label;
     int nslot;
-    int *rowptr;
+    int *rowptr;          // row start
+    unsigned char *rdeg;  // row degree
     int *col;
     double2 *v1, *v2;
     double *area;

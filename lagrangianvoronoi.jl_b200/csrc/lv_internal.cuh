@@ -61,7 +61,8 @@ struct LvContext {
     double2 *d_ent_xy = nullptr;     // [nslot] ORIGINAL position of the label (q.x)
     int *d_prim_of_label = nullptr;  // [n] label -> primary slot (-1: outside the cell list)
     // mesh (slot order)
-    int *d_rowptr = nullptr; // [nslot+1]
+    int *d_rowptr = nullptr; // [nslot] first edge of the row (rows are NOT stored in slot order, see lv_clip_fast.cu)
+    unsigned char *d_deg = nullptr; // [nslot] number of edges of the row
     int64_t nnz = 0, cap_nnz = 0;
     int *d_col = nullptr;    // [nnz] neighbour primary slot, or wall code -1..-4
     double2 *d_v1 = nullptr, *d_v2 = nullptr; // [nnz] edge end points (clockwise, polygon.jl:51-97)

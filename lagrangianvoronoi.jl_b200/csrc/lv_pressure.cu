@@ -87,7 +87,7 @@ int lv_pr_ensure(LvContext *c) {
 
 // ---- K3: operator assembly  pressure.jl:104-117 ------------------------------------------------
 __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned *__restrict__ ent_label,
-                                                       const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                       const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                        const int *__restrict__ col, const double2 *__restrict__ v1,
                                                        const double2 *__restrict__ v2, const double *__restrict__ mass,
                                                        const double *__restrict__ rho, const double *__restrict__ c2,
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
     const double ri = rho[i];
     diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
     const double2 x = ent_xy[i];
-    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) {
         const int j = col[k];
         if (j < 0) { w[k] = 0.0; continue; } // wall edge: not part of neighbors(p, grid)
@@ -116,7 +116,7 @@ int lv_pr_assemble(LvContext *c, double dt) {
     LvProfScope prof(c, LV_PROF_ASSEMBLE);
     const int ns = (int)c->nslot;
     if (ns > 0) {
-        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_ent_label, c->d_ent_xy, c->d_rowptr,
+        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                              c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
                                                                              c->d_diag, c->d_w);
         c->launches++;
@@ -145,7 +145,7 @@ __device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
 
 // ---- K4: matvec  pressure.jl:119-130, with optional fused dot(x, y) partial ----------------------
 template <bool DOT>
-__global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                      const double *__restrict__ w, const double *__restrict__ diag,
                                                      const double *__restrict__ x, double *__restrict__ y,
                                                      double *__restrict__ partial, const double *__restrict__ scal) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__res
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
         const double xi = x[i];
         double yi = diag[i] * xi;
-        const int r0 = rowptr[i], r1 = rowptr[i + 1];
+        const int r0 = rowptr[i], r1 = r0 + rdeg[i];
         for (int k = r0; k < r1; k++) {
             const int j = col[k];
             const double xj = j >= 0 ? x[j] : xi;
@@ -182,7 +182,7 @@ int lv_pr_matvec(LvContext *c, const double *x, double *y) {
     LvProfScope prof(c, LV_PROF_MATVEC);
     const int ns = (int)c->nslot;
     if (ns == 0) return LV_OK;
-    k_matvec<false><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, x, y, nullptr, c->d_red);
+    k_matvec<false><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, nullptr, c->d_red);
     c->launches++;
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
@@ -192,7 +192,7 @@ int lv_pr_matvec(LvContext *c, const double *x, double *y) {
 struct Vbc { double w[8]; };
 
 __global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned *__restrict__ ent_label,
-                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                    const int *__restrict__ col, const double2 *__restrict__ v1,
                                                    const double2 *__restrict__ v2, const double *__restrict__ area,
                                                    const double *__restrict__ mass, const double *__restrict__ rho,
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, do
     const double2 vi = v[i];
     double bi = (area[i] * Pi) / ((rho[i] * c2[i]) * (dt * dt)); // pressure.jl:171
     double gx = 0.0, gy = 0.0;
-    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) { // neighbors(p, grid)
         const int j = col[k];
         if (j < 0) continue;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, do
 }
 
 __global__ void __launch_bounds__(PR_BLOCK) k_rhs2(LvGridParams g, int nslot, const unsigned *__restrict__ ent_label,
-                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr,
+                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                    const int *__restrict__ col, const double2 *__restrict__ v1,
                                                    const double2 *__restrict__ v2, const double2 *__restrict__ GP,
                                                    double *__restrict__ b) {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs2(LvGridParams g, int nslot, co
     const double2 x = ent_xy[i];
     const double2 gi = GP[i];
     double bi = b[i];
-    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) {
         const int j = col[k];
         if (j < 0) continue;
@@ -271,11 +271,11 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
     Vbc vbc;
     for (int k = 0; k < 8; k++) vbc.w[k] = vbc_wall ? vbc_wall[k] : 0.0;
     const int nb = (ns + PR_BLOCK - 1) / PR_BLOCK;
-    k_rhs1<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_col, c->d_v1, c->d_v2,
+    k_rhs1<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2,
                                            c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b, c->d_GP);
     c->launches++;
     if (gp_step) {
-        k_rhs2<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_GP,
+        k_rhs2<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2, c->d_GP,
                                                c->d_b);
         c->launches++;
     }
@@ -391,7 +391,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     const int nb = pr_grid(c, ns);
     auto matvec_plain = [&](const double *in, double *out) {
         LvProfScope prof(c, LV_PROF_MATVEC);
-        k_matvec<false><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, in, out, nullptr, scal);
+        k_matvec<false><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, in, out, nullptr, scal);
         c->launches++;
     };
     matvec_plain(x, Ap);
@@ -408,7 +408,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         for (int it = 0; it < todo; it++) {
             {
                 LvProfScope prof(c, LV_PROF_MATVEC);
-                k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
+                k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
                 c->launches++;
             }
             LvProfScope prof(c, LV_PROF_VECOPS);
@@ -540,7 +540,7 @@ int32_t lv_pressure_assemble(LvHandle c, double dt) {
     return lv_pr_assemble(c, dt);
 }
 
-__global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                  const int *__restrict__ rowptr_l, const int *__restrict__ col, const double *__restrict__ w,
                                                  const double *__restrict__ diag, const unsigned *__restrict__ ent_label,
                                                  long long *__restrict__ col_l, double *__restrict__ w_l, double *__restrict__ diag_l) {
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restric
     const int s = prim[i];
     diag_l[i] = diag[s];
     int o = rowptr_l[i];
-    for (int k = rowptr[s]; k < rowptr[s + 1]; k++) {
+    for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) {
         const int j = col[k];
         if (j < 0) continue;
         col_l[o] = (long long)(ent_label[j] & ~LV_IMAGE_BIT) + 1;
@@ -557,13 +557,13 @@ __global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restric
         o++;
     }
 }
-__global__ void __launch_bounds__(256) k_op_deg(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(256) k_op_deg(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                 const int *__restrict__ col, int *__restrict__ deg) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = prim[i];
     int d = 0;
-    for (int k = rowptr[s]; k < rowptr[s + 1]; k++) d += col[k] >= 0;
+    for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) d += col[k] >= 0;
     deg[i] = d;
 }
 
@@ -585,10 +585,10 @@ int32_t lv_pressure_operator(LvHandle c, int64_t *rowptr, int64_t *col, double *
     int st = LV_OK;
     std::string msg;
     do {
-        k_op_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_col, deg);
+        k_op_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, c->d_col, deg);
         c->launches++;
         if ((st = lv_exclusive_scan_i32(c, deg, rl, n)) != LV_OK) break;
-        k_op_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, rl, c->d_col, c->d_w, c->d_diag, c->d_ent_label, col_l, w_l, d_l);
+        k_op_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_w, c->d_diag, c->d_ent_label, col_l, w_l, d_l);
         c->launches++;
         int *h_rl = (int *)malloc(sizeof(int) * (size_t)(n + 1));
         cudaError_t e = cudaMemcpyAsync(h_rl, rl, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
