@@ -91,6 +91,7 @@ struct LvContext {
     double *d_red = nullptr;      // reduction partials + scalars
     double *h_red = nullptr;      // pinned
     bool assembled = false;
+    int cg_hint = 0; // iterations of the previous solve (sizes the first launch batch)
     // instrumentation
     bool prof_on = false;
     LvProfSlot prof[LV_PROF_COUNT];
