@@ -150,6 +150,7 @@ __device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
 // keeps the reference's order: diagonal first, then the neighbours in edge order.
 // (A variant that staged each warp tile's col / w through shared memory measured 1.7x slower on
 // B200 -- three dependent memory round trips per tile instead of one -- and was dropped.)
+#define MV_U 8
 template <bool DOT>
 __global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                      const int *__restrict__ col, const double *__restrict__ w,
@@ -162,11 +163,25 @@ __global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__res
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
         const double xi = x[i];
         double yi = diag[i] * xi;
-        const int r0 = rowptr[i], r1 = r0 + rdeg[i];
-        for (int k = r0; k < r1; k++) {
-            const int j = col[k];
-            const double xj = j >= 0 ? x[j] : xi;
-            yi += w[k] * (xi - xj);
+        const int r0 = rowptr[i], d = rdeg[i];
+        // all loads of the first MV_U edges are issued before the first use (memory-level parallelism:
+        // the kernel is latency bound, not bandwidth bound, when the loads of a row are chained)
+        int cj[MV_U];
+        double wk[MV_U], xj[MV_U];
+#pragma unroll
+        for (int k = 0; k < MV_U; k++) {
+            cj[k] = k < d ? col[r0 + k] : -1;
+            wk[k] = k < d ? w[r0 + k] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MV_U; k++) xj[k] = cj[k] >= 0 ? x[cj[k]] : xi;
+#pragma unroll
+        for (int k = 0; k < MV_U; k++)
+            if (k < d) yi += wk[k] * (xi - xj[k]);
+        for (int k = MV_U; k < d; k++) {
+            const int j = col[r0 + k];
+            const double xv = j >= 0 ? x[j] : xi;
+            yi += w[r0 + k] * (xi - xv);
         }
         y[i] = yi;
         if (DOT) acc += xi * yi;
