@@ -85,6 +85,12 @@ struct LvContext {
     double *d_mass = nullptr, *d_rho = nullptr, *d_c2 = nullptr, *d_P = nullptr;
     double2 *d_v = nullptr, *d_GP = nullptr;
     double *d_diag = nullptr, *d_w = nullptr; // operator: diagonal [nslot], weights [nnz]
+    double *d_lrr = nullptr;                  // [nnz] lr_ratio of the edge (polygon.jl:228)
+    double2 *d_mx = nullptr, *d_mz = nullptr; // [nnz] m - p.x and m - z (pressure.jl:178,198)
+    double *d_bvel = nullptr;                 // [nslot] P-independent part of the right-hand side
+    bool bvel_valid = false;
+    double asm_dt = 0.0;
+    double last_vbc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t cap_w = 0;
     double *d_b = nullptr;
     double *d_vec[8] = {nullptr}; // Krylov workspace vectors

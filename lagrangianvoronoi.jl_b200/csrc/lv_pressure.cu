@@ -63,7 +63,7 @@ int lv_pr_ensure(LvContext *c) {
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     const int64_t need = c->cap_slot;
     if (c->pr_cap < need || !c->d_mass) {
-        double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_vec[0], &c->d_vec[1],
+        double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
                           &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
         for (double **p : one) {
             int64_t cap = *p ? c->pr_cap : 0;
@@ -80,18 +80,31 @@ int lv_pr_ensure(LvContext *c) {
         LV_CUDA(c, cudaMemsetAsync(c->d_v, 0, sizeof(double2) * (size_t)need, c->stream));
         c->pr_valid = false;
     }
-    if (c->cap_w < c->cap_nnz || !c->d_w) LV_TRY(lv_ensure(c, (void **)&c->d_w, &c->cap_w, c->cap_nnz, sizeof(double)));
+    if (c->cap_w < c->cap_nnz || !c->d_w) {
+        int64_t c1 = c->cap_w, c2 = c->cap_w, c3 = c->cap_w, c4 = c->cap_w;
+        LV_TRY(lv_ensure(c, (void **)&c->d_w, &c1, c->cap_nnz, sizeof(double)));
+        LV_TRY(lv_ensure(c, (void **)&c->d_lrr, &c2, c->cap_nnz, sizeof(double)));
+        LV_TRY(lv_ensure(c, (void **)&c->d_mx, &c3, c->cap_nnz, sizeof(double2)));
+        LV_TRY(lv_ensure(c, (void **)&c->d_mz, &c4, c->cap_nnz, sizeof(double2)));
+        c->cap_w = c->cap_nnz;
+        c->assembled = false;
+    }
     if (!c->d_red) LV_TRY(lv_alloc(c, (void **)&c->d_red, sizeof(double) * (SC_COUNT + 2 * 4096)));
     return LV_OK;
 }
 
 // ---- K3: operator assembly  pressure.jl:104-117 ------------------------------------------------
+// Besides A.diagonal and the weights w = lrr*(0.5/rho_i + 0.5/rho_j) the kernel keeps, per edge, the three
+// geometric factors every later sweep of find_pressure! needs -- lrr = lr_ratio(p.x - y, e) (polygon.jl:228),
+// m - p.x and m - z (pressure.jl:176,178,196,198) -- so that the 10 fixed-point passes neither repeat the
+// FP64 divide/sqrt nor re-gather the neighbour positions.  Values are the reference's expressions.
 __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned *__restrict__ ent_label,
                                                        const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                        const int *__restrict__ col, const double2 *__restrict__ v1,
                                                        const double2 *__restrict__ v2, const double *__restrict__ mass,
                                                        const double *__restrict__ rho, const double *__restrict__ c2,
-                                                       double *__restrict__ diag, double *__restrict__ w) {
+                                                       double *__restrict__ diag, double *__restrict__ w, double *__restrict__ lrr_out,
+                                                       double2 *__restrict__ mx_out, double2 *__restrict__ mz_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
     if (ent_label[i] & LV_IMAGE_BIT) { diag[i] = 0.0; return; }
@@ -101,12 +114,17 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
     const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) {
         const int j = col[k];
-        if (j < 0) { w[k] = 0.0; continue; } // wall edge: not part of neighbors(p, grid)
-        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
         const double2 a = v1[k], b = v2[k];
+        const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y); // midpoint(e)  geometry.jl:145-147
+        mx_out[k] = make_double2(mx - x.x, my - x.y);
+        if (j < 0) { w[k] = 0.0; lrr_out[k] = 0.0; mz_out[k] = make_double2(0.0, 0.0); continue; } // wall edge: not in neighbors(p, grid)
+        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
         const double ex = a.x - b.x, ey = a.y - b.y, dx = x.x - y.x, dy = x.y - y.y;
         const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy)); // lr_ratio  polygon.jl:228-232
+        lrr_out[k] = lrr;
         w[k] = lrr * (0.5 / ri + 0.5 / rho[j]);                             // pressure.jl:113
+        const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);        // midpoint(p.x, y)  pressure.jl:196
+        mz_out[k] = make_double2(mx - zx, my - zy);
     }
 }
 
@@ -118,11 +136,13 @@ int lv_pr_assemble(LvContext *c, double dt) {
     if (ns > 0) {
         k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                              c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
-                                                                             c->d_diag, c->d_w);
+                                                                             c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz);
         c->launches++;
         LV_CUDA(c, cudaGetLastError());
     }
     c->assembled = true;
+    c->bvel_valid = false;
+    c->asm_dt = dt;
     return LV_OK;
 }
 
@@ -213,35 +233,43 @@ int lv_pr_matvec(LvContext *c, const double *x, double *y) {
 // ---- right-hand side  pressure.jl:162-203 ---------------------------------------------------------
 struct Vbc { double w[8]; };
 
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned *__restrict__ ent_label,
-                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
-                                                   const int *__restrict__ col, const double2 *__restrict__ v1,
-                                                   const double2 *__restrict__ v2, const double *__restrict__ area,
-                                                   const double *__restrict__ mass, const double *__restrict__ rho,
-                                                   const double *__restrict__ c2, const double *__restrict__ P,
-                                                   const double2 *__restrict__ v, double *__restrict__ b, double2 *__restrict__ GP) {
+// First pass of find_pressure! (gp_step = false): b, the initial GP and -- kept for the later passes --
+// bvel, the part of b that does not depend on P (velocity divergence + wall terms, pressure.jl:177,180-184).
+// b itself is accumulated in the reference's order.
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned *__restrict__ ent_label,
+                                                        const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
+                                                        const int *__restrict__ col, const double2 *__restrict__ v1,
+                                                        const double2 *__restrict__ v2, const double *__restrict__ lrr_in,
+                                                        const double2 *__restrict__ mx_in, const double *__restrict__ area,
+                                                        const double *__restrict__ mass, const double *__restrict__ rho,
+                                                        const double *__restrict__ c2, const double *__restrict__ P,
+                                                        const double2 *__restrict__ v, double *__restrict__ b, double *__restrict__ bvel,
+                                                        double2 *__restrict__ GP) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
+    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
     const double2 x = ent_xy[i];
     const double Pi = P[i];
     const double2 vi = v[i];
     double bi = (area[i] * Pi) / ((rho[i] * c2[i]) * (dt * dt)); // pressure.jl:171
+    double bv = 0.0;
     double gx = 0.0, gy = 0.0;
     const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) { // neighbors(p, grid)
         const int j = col[k];
         if (j < 0) continue;
         const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
+        const double2 m = mx_in[k]; // m - p.x
+        const double lrr = lrr_in[k];
         const double2 a = v1[k], c = v2[k];
-        const double ex = a.x - c.x, ey = a.y - c.y, dx = x.x - y.x, dy = x.y - y.y;
-        const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy));
         const double mx = 0.5 * (a.x + c.x), my = 0.5 * (a.y + c.y);
         const double2 vj = v[j];
-        bi -= (lrr / dt) * ((vi.x - vj.x) * (mx - y.x) + (vi.y - vj.y) * (my - y.y)); // :177
+        const double t = (lrr / dt) * ((vi.x - vj.x) * (mx - y.x) + (vi.y - vj.y) * (my - y.y)); // :177
+        bi -= t;
+        bv -= t;
         const double s = lrr * (Pi - P[j]);
-        gx -= s * (mx - x.x); // :178
-        gy -= s * (my - x.y);
+        gx -= s * m.x; // :178
+        gy -= s * m.y;
     }
     for (int k = r0; k < r1; k++) { // boundaries(p)
         const int j = col[k];
@@ -250,36 +278,93 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs1(LvGridParams g, int nslot, do
         const double sx = a.y - c.y, sy = c.x - a.x; // dS  :181
         const int wl = -j - 1;
         const double bx = wl < 4 ? vbc.w[2 * wl] : 0.0, by = wl < 4 ? vbc.w[2 * wl + 1] : 0.0;
-        bi -= (sx * (bx - vi.x) + sy * (by - vi.y)) / dt; // :183
+        const double t = (sx * (bx - vi.x) + sy * (by - vi.y)) / dt; // :183
+        bi -= t;
+        bv -= t;
     }
-    const double m = mass[i];
-    GP[i] = make_double2(gx / m, gy / m); // :185
+    const double mi = mass[i];
+    GP[i] = make_double2(gx / mi, gy / mi); // :185
     b[i] = bi;
+    bvel[i] = bv;
 }
 
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs2(LvGridParams g, int nslot, const unsigned *__restrict__ ent_label,
-                                                   const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
-                                                   const int *__restrict__ col, const double2 *__restrict__ v1,
-                                                   const double2 *__restrict__ v2, const double2 *__restrict__ GP,
-                                                   double *__restrict__ b) {
+#define RH_U 8 // edges whose loads are issued before first use (same latency argument as k_matvec)
+
+// Later passes, sweep 1: GP_i = -sum lrr (P_i - P_j)(m - p.x) / mass_i   pressure.jl:178,185
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned *__restrict__ ent_label, const int *__restrict__ rowptr,
+                                                     const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                     const double *__restrict__ lrr_in, const double2 *__restrict__ mx_in,
+                                                     const double *__restrict__ mass, const double *__restrict__ P,
+                                                     double2 *__restrict__ GP) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) return;
-    const double2 x = ent_xy[i];
-    const double2 gi = GP[i];
-    double bi = b[i];
-    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
-    for (int k = r0; k < r1; k++) {
-        const int j = col[k];
+    if (ent_label[i] & LV_IMAGE_BIT) { GP[i] = make_double2(0.0, 0.0); return; }
+    const double Pi = P[i];
+    const int r0 = rowptr[i], d = rdeg[i];
+    int cj[RH_U];
+    double lr[RH_U], pj[RH_U];
+    double2 mm[RH_U];
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) {
+        cj[k] = k < d ? col[r0 + k] : -1;
+        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+        mm[k] = k < d ? mx_in[r0 + k] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) pj[k] = cj[k] >= 0 ? P[cj[k]] : Pi;
+    double gx = 0.0, gy = 0.0;
+#pragma unroll
+    for (int k = 0; k < RH_U; k++)
+        if (k < d && cj[k] >= 0) {
+            const double s = lr[k] * (Pi - pj[k]);
+            gx -= s * mm[k].x;
+            gy -= s * mm[k].y;
+        }
+    for (int k = RH_U; k < d; k++) {
+        const int j = col[r0 + k];
         if (j < 0) continue;
-        const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
-        const double2 a = v1[k], c = v2[k];
-        const double ex = a.x - c.x, ey = a.y - c.y, dx = x.x - y.x, dy = x.y - y.y;
-        const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy));
-        const double mx = 0.5 * (a.x + c.x), my = 0.5 * (a.y + c.y);
-        const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);
-        const double2 gj = GP[j];
-        bi += lrr * ((gi.x - gj.x) * (mx - zx) + (gi.y - gj.y) * (my - zy)); // :198
+        const double s = lrr_in[r0 + k] * (Pi - P[j]);
+        const double2 m = mx_in[r0 + k];
+        gx -= s * m.x;
+        gy -= s * m.y;
+    }
+    const double mi = mass[i];
+    GP[i] = make_double2(gx / mi, gy / mi);
+}
+
+// Later passes, sweep 2: b_i = A_i P_i/(rho c2 dt^2) + bvel_i + sum lrr (GP_i - GP_j).(m - z)   pressure.jl:171,189-202
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_corr(int nslot, double dt, const unsigned *__restrict__ ent_label, const int *__restrict__ rowptr,
+                                                       const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                       const double *__restrict__ lrr_in, const double2 *__restrict__ mz_in,
+                                                       const double *__restrict__ area, const double *__restrict__ rho,
+                                                       const double *__restrict__ c2, const double *__restrict__ P,
+                                                       const double *__restrict__ bvel, const double2 *__restrict__ GP,
+                                                       double *__restrict__ b) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; return; }
+    const double2 gi = GP[i];
+    double bi = (area[i] * P[i]) / ((rho[i] * c2[i]) * (dt * dt)) + bvel[i];
+    const int r0 = rowptr[i], d = rdeg[i];
+    int cj[RH_U];
+    double lr[RH_U];
+    double2 mm[RH_U], gj[RH_U];
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) {
+        cj[k] = k < d ? col[r0 + k] : -1;
+        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+        mm[k] = k < d ? mz_in[r0 + k] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) gj[k] = cj[k] >= 0 ? GP[cj[k]] : gi;
+#pragma unroll
+    for (int k = 0; k < RH_U; k++)
+        if (k < d && cj[k] >= 0) bi += lr[k] * ((gi.x - gj[k].x) * mm[k].x + (gi.y - gj[k].y) * mm[k].y); // :198
+    for (int k = RH_U; k < d; k++) {
+        const int j = col[r0 + k];
+        if (j < 0) continue;
+        const double2 g2 = GP[j], m = mz_in[r0 + k];
+        bi += lrr_in[r0 + k] * ((gi.x - g2.x) * m.x + (gi.y - g2.y) * m.y);
     }
     b[i] = bi;
 }
@@ -287,18 +372,31 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs2(LvGridParams g, int nslot, co
 int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
     LV_TRY(lv_pr_ensure(c));
     if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
+    if (!c->assembled || c->asm_dt != dt) LV_TRY(lv_pr_assemble(c, dt)); // the per-edge factors come from the assembly
     LvProfScope prof(c, LV_PROF_ASSEMBLE);
     const int ns = (int)c->nslot;
     if (ns == 0) return LV_OK;
     Vbc vbc;
-    for (int k = 0; k < 8; k++) vbc.w[k] = vbc_wall ? vbc_wall[k] : 0.0;
+    bool same_vbc = true;
+    for (int k = 0; k < 8; k++) { vbc.w[k] = vbc_wall ? vbc_wall[k] : 0.0; same_vbc &= (vbc.w[k] == c->last_vbc[k]); }
     const int nb = (ns + PR_BLOCK - 1) / PR_BLOCK;
-    k_rhs1<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2,
-                                           c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b, c->d_GP);
-    c->launches++;
+    const bool first = !gp_step || !c->bvel_valid || !same_vbc;
+    if (first) {
+        k_rhs_first<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1,
+                                                    c->d_v2, c->d_lrr, c->d_mx, c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b,
+                                                    c->d_bvel, c->d_GP);
+        c->launches++;
+        for (int k = 0; k < 8; k++) c->last_vbc[k] = vbc.w[k];
+        c->bvel_valid = true;
+    }
     if (gp_step) {
-        k_rhs2<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2, c->d_GP,
-                                               c->d_b);
+        if (!first) {
+            k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_ent_label, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
+                                                     c->d_GP);
+            c->launches++;
+        }
+        k_rhs_corr<<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_ent_label, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
+                                                   c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b);
         c->launches++;
     }
     LV_CUDA(c, cudaGetLastError());
@@ -491,9 +589,12 @@ int32_t lv_pressure_destroy(LvHandle c) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
-    double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_vec[0], &c->d_vec[1],
+    double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
                       &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
     for (double **p : one) { lv_free(c, *p, sizeof(double) * (size_t)c->pr_cap); *p = nullptr; }
+    lv_free(c, c->d_lrr, sizeof(double) * (size_t)c->cap_w); c->d_lrr = nullptr;
+    lv_free(c, c->d_mx, sizeof(double2) * (size_t)c->cap_w); c->d_mx = nullptr;
+    lv_free(c, c->d_mz, sizeof(double2) * (size_t)c->cap_w); c->d_mz = nullptr;
     lv_free(c, c->d_v, sizeof(double2) * (size_t)c->pr_cap); c->d_v = nullptr;
     lv_free(c, c->d_GP, sizeof(double2) * (size_t)c->pr_cap); c->d_GP = nullptr;
     lv_free(c, c->d_w, sizeof(double) * (size_t)c->cap_w); c->d_w = nullptr; c->cap_w = 0;
@@ -523,6 +624,7 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
     if (!dev) { cudaStreamSynchronize(c->stream); lv_free(c, stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)); }
     if (st == LV_OK && mass && rho && c2) c->pr_valid = true;
     if (mass || rho || c2) c->assembled = false;
+    if (v) c->bvel_valid = false;
     return st;
 }
 
