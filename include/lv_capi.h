@@ -136,6 +136,24 @@ int32_t lv_find_pressure_dev(LvHandle h, double dt, int32_t niter, double rtol, 
 int32_t lv_pressure_solve(LvHandle h, int32_t solver, const double *b, double *x, double rtol,
                           double atol, int32_t itmax, int32_t *iters, double *relres);
 
+/* ---- multi-GPU: y-strips, one process per GPU ------------------------------ */
+/* The reference is shared-memory only; these entry points have no counterpart there.  The host
+ * (lagrangianvoronoi.jl_b200/distributed.py) moves ghost generators between neighbouring strips with
+ * torch.distributed and hands the library the NCCL id, the ownership mask and the halo plan. */
+int32_t lv_comm_unique_id(uint8_t *out128);                       /* ncclGetUniqueId on rank 0 */
+int32_t lv_comm_init(LvHandle h, int32_t rank, int32_t nranks, const uint8_t *id128);
+/* remesh!(grid) on the generators present on this rank (owned + ghosts, ordered by global label);
+ * only polygons with owned_mask_dev[i] != 0 are clipped, ghosts are candidates only */
+int32_t lv_remesh_owned_dev(LvHandle h, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev);
+/* device pointers into the slot-ordered cell list (0 ent_label u32, 1 prim_of_label i32, 2 own u8,
+ * 3 ent_xy f64x2, 4 P f64, 5 area f64) for building the halo plan on the host */
+int32_t lv_device_array(LvHandle h, int32_t which, void **ptr, int64_t *count);
+/* per peer rank: how many values this rank sends / receives and the (device) slot lists, concatenated */
+int32_t lv_halo_plan(LvHandle h, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count,
+                     const int32_t *send_slots_dev, const int64_t *recv_count, const int32_t *recv_slots_dev);
+/* fill the ghost slots of a slot-ordered device vector (ncomp 1 or 2) from their owners */
+int32_t lv_halo_exchange_dev(LvHandle h, double *vec_dev, int32_t ncomp);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 int32_t lv_prof_enable(LvHandle h, int32_t on);
 int32_t lv_prof_reset(LvHandle h);

@@ -9,6 +9,7 @@ from ._capi import LvError, build_library, library_path, load_library, EDGE_DTYP
 from .host import (Rectangle, VoronoiGrid, PressureSolver, remesh, find_pressure, area, centroid,  # noqa: F401
                    neighbors_csr, mul)
 from . import synthetic  # noqa: F401
+from . import distributed  # noqa: F401
 
 __all__ = ["LvError", "build_library", "library_path", "load_library", "EDGE_DTYPE", "Rectangle", "VoronoiGrid",
-           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "synthetic"]
+           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "synthetic", "distributed"]

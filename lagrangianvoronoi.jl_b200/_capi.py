@@ -24,7 +24,8 @@ SYMBOLS = [
     "lv_pressure_create", "lv_pressure_destroy", "lv_fields_upload", "lv_fields_upload_dev", "lv_pressure_download",
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
-    "lv_launch_count", "lv_device_bytes",
+    "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
+    "lv_halo_plan", "lv_halo_exchange_dev",
 ]
 
 
@@ -100,6 +101,12 @@ def load_library() -> C.CDLL:
     L.lv_find_pressure_dev.argtypes = [vp, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                        vp, i32p, dp]
     L.lv_pressure_solve.argtypes = [vp, C.c_int32, vp, vp, C.c_double, C.c_double, C.c_int32, i32p, dp]
+    L.lv_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.lv_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
+    L.lv_remesh_owned_dev.argtypes = [vp, C.c_int64, vp, vp]
+    L.lv_device_array.argtypes = [vp, C.c_int32, C.POINTER(vp), ip]
+    L.lv_halo_plan.argtypes = [vp, C.c_int32, i32p, ip, vp, ip, vp]
+    L.lv_halo_exchange_dev.argtypes = [vp, vp, C.c_int32]
     L.lv_prof_enable.argtypes = [vp, C.c_int32]
     L.lv_prof_reset.argtypes = [vp]
     L.lv_prof_get.argtypes = [vp, C.c_int32, dp, ip]

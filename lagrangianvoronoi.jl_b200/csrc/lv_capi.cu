@@ -189,11 +189,12 @@ int32_t lv_destroy(LvHandle c) {
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
                     c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
-                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg};
+                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_red) cudaFreeHost(c->h_red);
+    lv_dist_destroy(c);
     lv_prof_resolve(c);
     for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -281,7 +282,9 @@ int32_t lv_remesh_dev(LvHandle c, int64_t n, const double *xy_dev) {
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(ensure_generators(c, n, false));
     c->xy = (const double2 *)xy_dev; // used in place: positions are only read
-    return remesh_common(c, n);
+    int st = remesh_common(c, n);
+    c->owned_mask = nullptr; // one-shot: set by lv_remesh_owned_dev
+    return st;
 }
 
 int32_t lv_clip_info(LvHandle c, int32_t *level, int64_t *anomalies) {
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(256) k_label_deg(int64_t n, const int *__restr
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = prim[i];
-    deg[i] = rdeg[s];
+    deg[i] = s >= 0 ? rdeg[s] : 0; // ghost generators (multi-GPU) have no row here
 }
 
 __global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
@@ -320,9 +323,14 @@ __global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__rest
     if (i > n) return;
     if (i == n) { if (rowptr64) rowptr64[n] = rowptr_l[n]; return; }
     const int s = prim[i];
-    const int r0 = rowptr[s], r1 = r0 + rdeg[s];
     const int o = rowptr_l[i];
     if (rowptr64) rowptr64[i] = o;
+    if (s < 0) {
+        if (area_l) area_l[i] = 0.0;
+        if (cen_l) cen_l[i] = make_double2(0.0, 0.0);
+        return;
+    }
+    const int r0 = rowptr[s], r1 = r0 + rdeg[s];
     if (area_l) area_l[i] = area[s];
     if (cen_l) cen_l[i] = cen[s];
     if (edges)
@@ -393,6 +401,7 @@ int32_t lv_remesh(LvHandle c, int64_t n, const double *xy, int64_t *rowptr, LvEd
     LV_TRY(ensure_generators(c, n, true));
     if (n > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_xy, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     c->xy = c->d_xy;
+    c->owned_mask = nullptr;
     LV_TRY(remesh_common(c, n));
     if (nnz) *nnz = c->nnz;
     if (rowptr || edges || area || centroid) LV_TRY(lv_mesh_to_labels(c, rowptr, edges, cap, area, centroid));

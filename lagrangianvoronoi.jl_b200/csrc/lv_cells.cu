@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) k_cells_count_fill(LvGridParams g, int64_
 // copy of the generator positions and the label -> primary-slot map.
 __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *__restrict__ start,
                                                      unsigned *__restrict__ ent_label, double2 *__restrict__ ent_xy,
-                                                     const double2 *__restrict__ xy, int *__restrict__ prim_of_label) {
+                                                     const double2 *__restrict__ xy, int *__restrict__ prim_of_label,
+                                                     const unsigned char *__restrict__ owned_mask, unsigned char *__restrict__ own) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= ncell_ext) return;
     const int s0 = start[b], s1 = start[b + 1];
@@ -120,7 +121,9 @@ __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *_
         unsigned e = ent_label[s0 + a];
         unsigned lab = e & M;
         ent_xy[s0 + a] = xy[lab];
-        if (!(e & LV_IMAGE_BIT)) prim_of_label[lab] = s0 + a;
+        const bool prim = !(e & LV_IMAGE_BIT);
+        if (prim) prim_of_label[lab] = s0 + a;
+        own[s0 + a] = prim && (owned_mask == nullptr || owned_mask[lab]);
     }
 }
 
@@ -251,22 +254,24 @@ int lv_cells_build(LvContext *c) {
         int64_t need = nslot + 1;
         if (need > cap) {
             int64_t ncap = need + need / 16 + 1024;
-            int64_t c1 = cap, c2 = cap, c3 = cap, c4 = cap, c5 = cap, c6 = cap;
+            int64_t c1 = cap, c2 = cap, c3 = cap, c4 = cap, c5 = cap, c6 = cap, c7 = cap;
             LV_TRY(lv_ensure(c, (void **)&c->d_ent_label, &c1, ncap, sizeof(unsigned)));
             LV_TRY(lv_ensure(c, (void **)&c->d_ent_xy, &c2, ncap, sizeof(double2)));
             LV_TRY(lv_ensure(c, (void **)&c->d_rowptr, &c3, ncap + 1, sizeof(int)));
             LV_TRY(lv_ensure(c, (void **)&c->d_deg, &c6, ncap + 1, sizeof(unsigned char)));
+            LV_TRY(lv_ensure(c, (void **)&c->d_own, &c7, ncap + 1, sizeof(unsigned char)));
             LV_TRY(lv_ensure(c, (void **)&c->d_area, &c4, ncap, sizeof(double)));
             LV_TRY(lv_ensure(c, (void **)&c->d_cen, &c5, ncap, sizeof(double2)));
             c->cap_slot = ncap;
         }
     }
     LV_CUDA(c, cudaMemsetAsync(c->d_cell_cnt, 0, sizeof(int) * (size_t)(ncell_ext + 1), st));
+    if (n > 0) LV_CUDA(c, cudaMemsetAsync(c->d_prim_of_label, 0xff, sizeof(int) * (size_t)n, st)); // -1: no primary slot here
     if (n > 0) {
         k_cells_count_fill<true><<<nb, 256, 0, st>>>(c->gp, n, c->xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label,
                                                      c->d_flags);
         k_cells_order<<<(int)((ncell_ext + 127) / 128), 128, 0, st>>>((int)ncell_ext, c->d_cell_start, c->d_ent_label,
-                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label);
+                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label, c->owned_mask, c->d_own);
         c->launches += 2;
     }
     LV_CUDA(c, cudaGetLastError());

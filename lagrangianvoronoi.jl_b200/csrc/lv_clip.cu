@@ -119,8 +119,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
     bool active = false;
     double2 x = make_double2(0.0, 0.0);
     if (slot < a.nslot) {
-        const unsigned e = a.ent_label[slot];
-        active = !(e & LV_IMAGE_BIT);
+        active = a.own[slot] != 0;
         x = a.ent_xy[slot];
     }
     double area = 0.0;
@@ -242,10 +241,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
             for (int k = 0; k < deg; k++) {
                 const int l = p.L(k);
                 int cc = l;
-                if (l >= 0) {
-                    const unsigned e = a.ent_label[l];
-                    cc = (e & LV_IMAGE_BIT) ? a.prim_of_label[e & ~LV_IMAGE_BIT] : l;
-                }
+                if (l >= 0) cc = lv_col_of(a, l);
                 a.col[off + k] = cc;
                 a.v1[off + k] = p.V1(k);
                 a.v2[off + k] = p.V2(k);
@@ -303,6 +299,7 @@ int lv_clip_run(LvContext *c) {
         a.ent_label = c->d_ent_label;
         a.ent_xy = c->d_ent_xy;
         a.prim_of_label = c->d_prim_of_label;
+        a.own = c->d_own;
         a.nslot = (int)nslot;
         a.rowptr = c->d_rowptr;
         a.rdeg = c->d_deg;

@@ -16,6 +16,7 @@ struct ClipArgs {
     const unsigned *ent_label;
     const double2 *ent_xy;
     const int *prim_of_label;
+    const unsigned char *own; // [nslot] slot is the primary slot of an owned generator
     int nslot;
     int *rowptr;          // row start
     unsigned char *rdeg;  // row degree
@@ -37,5 +38,14 @@ struct ClipArgs {
 #define OVF_POLY 1   // a polygon outgrew the kernel's edge capacity
 #define OVF_NNZ 2    // the CSR edge buffers are too small
 #define OVF_ANOMALY 4 // the fast kernel met a case it does not handle exactly (rerun with the edge-list kernel)
+
+// CSR column of a candidate slot l: the primary slot of its generator when this rank owns it, the
+// candidate slot itself for ghost generators (their values arrive by halo exchange at that slot)
+__device__ __forceinline__ int lv_col_of(const ClipArgs &a, int l) {
+    const unsigned e = a.ent_label[l];
+    if (!(e & LV_IMAGE_BIT)) return l;
+    const int p = a.prim_of_label[e & ~LV_IMAGE_BIT];
+    return (p >= 0 && a.own[p]) ? p : l;
+}
 
 int lv_clip_launch_fast(LvContext *c, const ClipArgs &a, int level); // lv_clip_fast.cu

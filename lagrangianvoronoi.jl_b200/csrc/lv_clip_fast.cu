@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         bool alive = false;
         double2 x = make_double2(0.0, 0.0);
         if (slot < a.nslot) {
-            alive = !(a.ent_label[slot] & LV_IMAGE_BIT);
+            alive = a.own[slot] != 0;
             x = a.ent_xy[slot];
         }
         const bool active = alive;
@@ -316,10 +316,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
                     if (fits) {
                         const int l = p.L(cur);
                         int cc = l;
-                        if (l >= 0) {
-                            const unsigned e = a.ent_label[l];
-                            cc = (e & LV_IMAGE_BIT) ? a.prim_of_label[e & ~LV_IMAGE_BIT] : l;
-                        }
+                        if (l >= 0) cc = lv_col_of(a, l);
                         a.col[off + k] = cc;
                         a.v1[off + k] = u;
                         a.v2[off + k] = w;

@@ -1,0 +1,207 @@
+// lv_dist.cu -- multi-GPU plumbing of the strip decomposition: one process per GPU, NCCL over NVLink.
+//
+// The rectangle is cut into y-strips of cell-list bucket rows.  Each rank clips the polygons of the
+// generators it owns; generators of the neighbouring strips that can influence them are present as
+// ghost entries of the local cell list (the Python host exchanges them with torch.distributed after
+// every move, lagrangianvoronoi.jl_b200/distributed.py).  This file holds what runs inside the
+// Krylov loop and therefore must not bounce through Python:
+//   * the halo exchange that fills the ghost slots of a slot-ordered vector from their owners
+//     (pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel), and
+//   * the 2-scalar ncclAllReduce behind every CG dot product.
+// NCCL is bound at run time (dlopen of the libnccl.so.2 PyTorch already loaded), the communicator is
+// created from a unique id that the host broadcasts with torch.distributed.
+#include "lv_internal.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool load_nccl(std::string &err) {
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD); if (lib) break; } // the copy torch loaded
+    if (!lib) for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define LOAD(sym) *(void **)(&g_nccl.sym) = dlsym(lib, "nccl" #sym); if (!g_nccl.sym) { err = "libnccl lacks nccl" #sym; return false; }
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(Send) LOAD(Recv) LOAD(AllReduce) LOAD(GroupStart) LOAD(GroupEnd) LOAD(GetErrorString)
+#undef LOAD
+    g_nccl.lib = lib;
+    return true;
+}
+} // namespace
+
+#define LV_NCCL(c, expr)                                                                                          \
+    do {                                                                                                          \
+        ncclResult_t _r = (expr);                                                                                 \
+        if (_r != ncclSuccess) return lv_set_error((c), LV_ECUDA, "%s failed: %s", #expr, g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_halo_pack(int64_t n, const int *__restrict__ slots, const double *__restrict__ vec, double *__restrict__ buf) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slots[i];
+#pragma unroll
+    for (int k = 0; k < NC; k++) buf[(size_t)NC * i + k] = vec[(size_t)NC * s + k];
+}
+template <int NC>
+__global__ void __launch_bounds__(256) k_halo_unpack(int64_t n, const int *__restrict__ slots, const double *__restrict__ buf, double *__restrict__ vec) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slots[i];
+#pragma unroll
+    for (int k = 0; k < NC; k++) vec[(size_t)NC * s + k] = buf[(size_t)NC * i + k];
+}
+
+int lv_halo_exchange(LvContext *c, double *vec, int ncomp) {
+    if (!c->comm || c->peers.empty()) return LV_OK;
+    ncclComm_t comm = (ncclComm_t)c->comm;
+    cudaStream_t st = c->stream;
+    if (c->halo_send_total > 0) {
+        const int nb = (int)((c->halo_send_total + 255) / 256);
+        if (ncomp == 1) k_halo_pack<1><<<nb, 256, 0, st>>>(c->halo_send_total, c->d_send_slots, vec, c->d_send_buf);
+        else k_halo_pack<2><<<nb, 256, 0, st>>>(c->halo_send_total, c->d_send_slots, vec, c->d_send_buf);
+        c->launches++;
+    }
+    LV_NCCL(c, g_nccl.GroupStart());
+    for (const auto &p : c->peers) {
+        if (p.nsend > 0) LV_NCCL(c, g_nccl.Send(c->d_send_buf + (size_t)ncomp * p.send_off, (size_t)ncomp * p.nsend, ncclDouble, p.rank, comm, st));
+        if (p.nrecv > 0) LV_NCCL(c, g_nccl.Recv(c->d_recv_buf + (size_t)ncomp * p.recv_off, (size_t)ncomp * p.nrecv, ncclDouble, p.rank, comm, st));
+    }
+    LV_NCCL(c, g_nccl.GroupEnd());
+    if (c->halo_recv_total > 0) {
+        const int nb = (int)((c->halo_recv_total + 255) / 256);
+        if (ncomp == 1) k_halo_unpack<1><<<nb, 256, 0, st>>>(c->halo_recv_total, c->d_recv_slots, c->d_recv_buf, vec);
+        else k_halo_unpack<2><<<nb, 256, 0, st>>>(c->halo_recv_total, c->d_recv_slots, c->d_recv_buf, vec);
+        c->launches++;
+    }
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+int lv_allreduce_sum(LvContext *c, double *dev, int count) {
+    if (!c->comm) return LV_OK;
+    LV_NCCL(c, g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return LV_OK;
+}
+
+void lv_dist_destroy(LvContext *c) {
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr;
+    cudaFree(c->d_send_slots); cudaFree(c->d_recv_slots); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
+    c->d_send_slots = c->d_recv_slots = nullptr;
+    c->d_send_buf = c->d_recv_buf = nullptr;
+}
+
+extern "C" {
+
+int32_t lv_comm_unique_id(uint8_t *out128) {
+    std::string err;
+    if (!out128) return LV_EINVAL;
+    if (!load_nccl(err)) return lv_set_error(nullptr, LV_ECUDA, "%s", err.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return lv_set_error(nullptr, LV_ECUDA, "ncclGetUniqueId failed");
+    memcpy(out128, &id, 128);
+    return LV_OK;
+}
+
+int32_t lv_comm_init(LvHandle c, int32_t rank, int32_t nranks, const uint8_t *id128) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return lv_set_error(c, LV_EINVAL, "bad communicator arguments");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    std::string err;
+    if (!load_nccl(err)) return lv_set_error(c, LV_ECUDA, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    LV_NCCL(c, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->comm = comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    return LV_OK;
+}
+
+// Halo plan of the current mesh: for every peer rank, the slots whose values this rank sends (its own
+// primary slots that are ghosts over there) and the ghost slots it receives into, both in the order the
+// two sides agreed on (the receiver's request order).  Slot lists are device arrays.
+int32_t lv_halo_plan(LvHandle c, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count, const int32_t *send_slots_dev,
+                     const int64_t *recv_count, const int32_t *recv_slots_dev) {
+    if (!c || npeers < 0) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    c->peers.clear();
+    int64_t so = 0, ro = 0;
+    for (int k = 0; k < npeers; k++) {
+        LvContext::HaloPeer p{peer_rank[k], send_count[k], recv_count[k], so, ro};
+        so += send_count[k];
+        ro += recv_count[k];
+        c->peers.push_back(p);
+    }
+    c->halo_send_total = so;
+    c->halo_recv_total = ro;
+    if (so > c->cap_halo_send) {
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_send_slots); cudaFree(c->d_send_buf);
+        c->cap_halo_send = so + so / 8 + 1024;
+        LV_CUDA(c, cudaMalloc((void **)&c->d_send_slots, sizeof(int) * (size_t)c->cap_halo_send));
+        LV_CUDA(c, cudaMalloc((void **)&c->d_send_buf, sizeof(double) * 2 * (size_t)c->cap_halo_send));
+    }
+    if (ro > c->cap_halo_recv) {
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_recv_slots); cudaFree(c->d_recv_buf);
+        c->cap_halo_recv = ro + ro / 8 + 1024;
+        LV_CUDA(c, cudaMalloc((void **)&c->d_recv_slots, sizeof(int) * (size_t)c->cap_halo_recv));
+        LV_CUDA(c, cudaMalloc((void **)&c->d_recv_buf, sizeof(double) * 2 * (size_t)c->cap_halo_recv));
+    }
+    if (so > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_send_slots, send_slots_dev, sizeof(int) * (size_t)so, cudaMemcpyDeviceToDevice, c->stream));
+    if (ro > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_recv_slots, recv_slots_dev, sizeof(int) * (size_t)ro, cudaMemcpyDeviceToDevice, c->stream));
+    return LV_OK;
+}
+
+// exchange a caller's slot-ordered device vector (tests; the solver calls lv_halo_exchange directly)
+int32_t lv_halo_exchange_dev(LvHandle c, double *vec_dev, int32_t ncomp) {
+    if (!c || !vec_dev || (ncomp != 1 && ncomp != 2)) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return lv_halo_exchange(c, vec_dev, ncomp);
+}
+
+// device pointers of the slot-ordered cell list, for the host to build the halo plan
+// which: 0 ent_label (uint32[nslot]), 1 prim_of_label (int32[n]), 2 own (uint8[nslot]), 3 ent_xy (double2[nslot]),
+//        4 P (double[nslot]), 5 area (double[nslot])
+int32_t lv_device_array(LvHandle c, int32_t which, void **ptr, int64_t *count) {
+    if (!c || !ptr || !count) return LV_EINVAL;
+    switch (which) {
+    case 0: *ptr = c->d_ent_label; *count = c->nslot; break;
+    case 1: *ptr = c->d_prim_of_label; *count = c->n; break;
+    case 2: *ptr = c->d_own; *count = c->nslot; break;
+    case 3: *ptr = c->d_ent_xy; *count = c->nslot; break;
+    case 4: *ptr = c->d_P; *count = c->nslot; break;
+    case 5: *ptr = c->d_area; *count = c->nslot; break;
+    default: return lv_set_error(c, LV_EINVAL, "unknown device array %d", which);
+    }
+    return LV_OK;
+}
+
+// remesh on the generators present on this rank (owned + ghosts, sorted by global label so that the
+// local index order is the global label order); only polygons with owned_mask != 0 are clipped
+int32_t lv_remesh_owned_dev(LvHandle c, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev) {
+    if (!c) return LV_EINVAL;
+    c->owned_mask = owned_mask_dev;
+    int32_t st = lv_remesh_dev(c, n_local, xy_dev);
+    return st;
+}
+
+} // extern "C"

@@ -59,7 +59,9 @@ struct LvContext {
     int64_t nslot = 0, cap_slot = 0;
     unsigned *d_ent_label = nullptr; // [nslot] 0-based label | LV_IMAGE_BIT
     double2 *d_ent_xy = nullptr;     // [nslot] ORIGINAL position of the label (q.x)
-    int *d_prim_of_label = nullptr;  // [n] label -> primary slot (-1: outside the cell list)
+    int *d_prim_of_label = nullptr;  // [n] label -> primary slot (-1: no primary slot in the local cell list)
+    unsigned char *d_own = nullptr;  // [nslot] 1 = primary slot of a generator this rank owns (a real row)
+    const unsigned char *owned_mask = nullptr; // [n] caller's device mask of owned generators (NULL: all)
     // mesh (slot order)
     int *d_rowptr = nullptr; // [nslot] first edge of the row (rows are NOT stored in slot order, see lv_clip_fast.cu)
     unsigned char *d_deg = nullptr; // [nslot] number of edges of the row
@@ -98,6 +100,14 @@ struct LvContext {
     double *h_red = nullptr;      // pinned
     bool assembled = false;
     int cg_hint = 0; // iterations of the previous solve (sizes the first launch batch)
+    // multi-GPU: NCCL communicator + halo plan (lv_dist.cu)
+    void *comm = nullptr; // ncclComm_t
+    int rank = 0, nranks = 1;
+    struct HaloPeer { int rank; int64_t nsend, nrecv; int64_t send_off, recv_off; };
+    std::vector<HaloPeer> peers;
+    int *d_send_slots = nullptr, *d_recv_slots = nullptr; // concatenated per peer
+    double *d_send_buf = nullptr, *d_recv_buf = nullptr;  // 2 components per entry
+    int64_t halo_send_total = 0, halo_recv_total = 0, cap_halo_send = 0, cap_halo_recv = 0;
     // instrumentation
     bool prof_on = false;
     LvProfSlot prof[LV_PROF_COUNT];
@@ -156,6 +166,11 @@ int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double 
                         const double *vbc_wall, int32_t *iters_out, double *relres_out);
 int lv_gather_to_slots(LvContext *c, const double *src_label_dev, double *dst_slot, int ncomp, double fill);
 int lv_scatter_to_labels(LvContext *c, const double *src_slot, double *dst_label_dev, int ncomp);
+
+// multi-GPU (lv_dist.cu): both are no-ops when the handle has no communicator
+int lv_halo_exchange(LvContext *c, double *vec_slot, int ncomp); // fill ghost slots from their owners
+int lv_allreduce_sum(LvContext *c, double *dev_scalars, int count);
+void lv_dist_destroy(LvContext *c);
 
 // ---- device helpers shared by kernels ---------------------------------------------------------
 __device__ __forceinline__ double lv_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }

@@ -11,7 +11,7 @@
 #define PR_BLOCK 256
 
 // scalars kept on the device between kernels (doubles in c->d_red[0..15])
-enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_COUNT = 16 };
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_COUNT = 16 };
 
 // ---- label <-> slot permutation --------------------------------------------------------------
 template <int NC>
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_scatter_labels(int64_t n, const in
     if (i >= n) return;
     const int s = prim[i];
 #pragma unroll
-    for (int k = 0; k < NC; k++) dst[(size_t)NC * i + k] = src[(size_t)NC * s + k];
+    for (int k = 0; k < NC; k++) dst[(size_t)NC * i + k] = s >= 0 ? src[(size_t)NC * s + k] : 0.0;
 }
 
 int lv_gather_to_slots(LvContext *c, const double *src, double *dst, int ncomp, double fill) {
@@ -98,7 +98,7 @@ int lv_pr_ensure(LvContext *c) {
 // geometric factors every later sweep of find_pressure! needs -- lrr = lr_ratio(p.x - y, e) (polygon.jl:228),
 // m - p.x and m - z (pressure.jl:176,178,196,198) -- so that the 10 fixed-point passes neither repeat the
 // FP64 divide/sqrt nor re-gather the neighbour positions.  Values are the reference's expressions.
-__global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned *__restrict__ ent_label,
+__global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned char *__restrict__ own,
                                                        const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                        const int *__restrict__ col, const double2 *__restrict__ v1,
                                                        const double2 *__restrict__ v2, const double *__restrict__ mass,
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
                                                        double2 *__restrict__ mx_out, double2 *__restrict__ mz_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) { diag[i] = 0.0; return; }
+    if (!own[i]) { diag[i] = 0.0; return; }
     const double ri = rho[i];
     diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
     const double2 x = ent_xy[i];
@@ -134,7 +134,7 @@ int lv_pr_assemble(LvContext *c, double dt) {
     LvProfScope prof(c, LV_PROF_ASSEMBLE);
     const int ns = (int)c->nslot;
     if (ns > 0) {
-        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg,
+        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                              c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
                                                                              c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz);
         c->launches++;
@@ -236,7 +236,7 @@ struct Vbc { double w[8]; };
 // First pass of find_pressure! (gp_step = false): b, the initial GP and -- kept for the later passes --
 // bvel, the part of b that does not depend on P (velocity divergence + wall terms, pressure.jl:177,180-184).
 // b itself is accumulated in the reference's order.
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned *__restrict__ ent_label,
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned char *__restrict__ own,
                                                         const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                         const int *__restrict__ col, const double2 *__restrict__ v1,
                                                         const double2 *__restrict__ v2, const double *__restrict__ lrr_in,
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
                                                         double2 *__restrict__ GP) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
+    if (!own[i]) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
     const double2 x = ent_xy[i];
     const double Pi = P[i];
     const double2 vi = v[i];
@@ -291,14 +291,14 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
 #define RH_U 8 // edges whose loads are issued before first use (same latency argument as k_matvec)
 
 // Later passes, sweep 1: GP_i = -sum lrr (P_i - P_j)(m - p.x) / mass_i   pressure.jl:178,185
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned *__restrict__ ent_label, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
                                                      const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                      const double *__restrict__ lrr_in, const double2 *__restrict__ mx_in,
                                                      const double *__restrict__ mass, const double *__restrict__ P,
                                                      double2 *__restrict__ GP) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) { GP[i] = make_double2(0.0, 0.0); return; }
+    if (!own[i]) { GP[i] = make_double2(0.0, 0.0); return; }
     const double Pi = P[i];
     const int r0 = rowptr[i], d = rdeg[i];
     int cj[RH_U];
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned *
 }
 
 // Later passes, sweep 2: b_i = A_i P_i/(rho c2 dt^2) + bvel_i + sum lrr (GP_i - GP_j).(m - z)   pressure.jl:171,189-202
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs_corr(int nslot, double dt, const unsigned *__restrict__ ent_label, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
                                                        const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mz_in,
                                                        const double *__restrict__ area, const double *__restrict__ rho,
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_corr(int nslot, double dt, con
                                                        double *__restrict__ b) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (ent_label[i] & LV_IMAGE_BIT) { b[i] = 0.0; return; }
+    if (!own[i]) { b[i] = 0.0; return; }
     const double2 gi = GP[i];
     double bi = (area[i] * P[i]) / ((rho[i] * c2[i]) * (dt * dt)) + bvel[i];
     const int r0 = rowptr[i], d = rdeg[i];
@@ -381,8 +381,9 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
     for (int k = 0; k < 8; k++) { vbc.w[k] = vbc_wall ? vbc_wall[k] : 0.0; same_vbc &= (vbc.w[k] == c->last_vbc[k]); }
     const int nb = (ns + PR_BLOCK - 1) / PR_BLOCK;
     const bool first = !gp_step || !c->bvel_valid || !same_vbc;
+    LV_TRY(lv_halo_exchange(c, c->d_P, 1)); // neighbours' pressures across the strip edges (no-op on one GPU)
     if (first) {
-        k_rhs_first<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_ent_label, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1,
+        k_rhs_first<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1,
                                                     c->d_v2, c->d_lrr, c->d_mx, c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b,
                                                     c->d_bvel, c->d_GP);
         c->launches++;
@@ -391,11 +392,12 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
     }
     if (gp_step) {
         if (!first) {
-            k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_ent_label, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
+            k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
                                                      c->d_GP);
             c->launches++;
         }
-        k_rhs_corr<<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_ent_label, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
+        LV_TRY(lv_halo_exchange(c, (double *)c->d_GP, 2));
+        k_rhs_corr<<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
                                                    c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b);
         c->launches++;
     }
@@ -424,14 +426,23 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_init(int nslot, const double *_
 }
 
 // one block: finish reductions and update the scalars.  mode 0: init, 1: alpha, 2: beta, 3: residual check
-__global__ void __launch_bounds__(256) k_cg_scalars(int mode, int nblk, int nblk_max, const double *__restrict__ partial,
+// stage 0: reduce the partials and update (single GPU); stage 1: reduce only, leaving the two local sums in
+// scal[SC_TMP0..1] for the NCCL allreduce; stage 2: update from the (now global) sums in scal[SC_TMP0..1].
+__global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nblk, int nblk_max, const double *__restrict__ partial,
                                                     double *__restrict__ scal, double rtol, double atol) {
     __shared__ double sm[32];
-    if (mode != 0 && mode != 3 && scal[SC_CONV] != 0.0) return;
-    double a = 0.0, b2 = 0.0;
-    for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
-    const double s1 = block_sum(a, sm);
-    const double s2 = block_sum(b2, sm);
+    if (stage != 1 && mode != 0 && mode != 3 && scal[SC_CONV] != 0.0) return;
+    double s1, s2;
+    if (stage != 2) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
+        s1 = block_sum(a, sm);
+        s2 = block_sum(b2, sm);
+        if (stage == 1) {
+            if (threadIdx.x == 0) { scal[SC_TMP0] = s1; scal[SC_TMP1] = s2; }
+            return;
+        }
+    } else { s1 = scal[SC_TMP0]; s2 = scal[SC_TMP1]; }
     if (threadIdx.x != 0) return;
     if (mode == 0) {
         scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_BNORM2] = s2;
@@ -509,17 +520,27 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
     const int NBMAX = 4096;
     const int nb = pr_grid(c, ns);
+    // finish a reduction: locally, or through a 2-scalar NCCL allreduce when the grid is decomposed
+    auto finish = [&](int mode) -> int {
+        if (!c->comm) { k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol); c->launches++; return LV_OK; }
+        k_cg_scalars<<<1, 256, 0, st>>>(mode, 1, nb, NBMAX, partial, scal, rtol, atol);
+        LV_TRY(lv_allreduce_sum(c, scal + SC_TMP0, 2));
+        k_cg_scalars<<<1, 256, 0, st>>>(mode, 2, nb, NBMAX, partial, scal, rtol, atol);
+        c->launches += 2;
+        return LV_OK;
+    };
     auto matvec_plain = [&](const double *in, double *out) {
         LvProfScope prof(c, LV_PROF_MATVEC);
         k_matvec<false><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, in, out, nullptr, scal);
         c->launches++;
     };
+    LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
     matvec_plain(x, Ap);
     {
         LvProfScope prof(c, LV_PROF_VECOPS);
         k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
-        k_cg_scalars<<<1, 256, 0, st>>>(0, nb, NBMAX, partial, scal, rtol, atol);
-        c->launches += 2;
+        c->launches++;
+        LV_TRY(finish(0));
     }
     // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
     // flag is set, so the host only has to look at the flag between batches.  The first batch is
@@ -529,17 +550,18 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
         const int todo = itmax - done < batch ? itmax - done : batch;
         for (int it = 0; it < todo; it++) {
+            LV_TRY(lv_halo_exchange(c, p, 1)); // ghost columns of the search direction (no-op on one GPU)
             {
                 LvProfScope prof(c, LV_PROF_MATVEC);
                 k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
                 c->launches++;
             }
             LvProfScope prof(c, LV_PROF_VECOPS);
-            k_cg_scalars<<<1, 256, 0, st>>>(1, nb, NBMAX, partial, scal, rtol, atol);
+            LV_TRY(finish(1));
             k_cg_update_xr<<<nb, PR_BLOCK, 0, st>>>(ns, scal, p, Ap, x, r, partial);
-            k_cg_scalars<<<1, 256, 0, st>>>(2, nb, NBMAX, partial, scal, rtol, atol);
+            LV_TRY(finish(2));
             k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
-            c->launches += 4;
+            c->launches += 2;
         }
         done += todo;
         LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
@@ -550,10 +572,11 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     c->cg_hint = (int)c->h_red[SC_ITER];
     if (iters) *iters = (int)c->h_red[SC_ITER];
     if (relres) { // true residual ||b - A x|| / ||b||
+        LV_TRY(lv_halo_exchange(c, x, 1));
         matvec_plain(x, Ap);
         k_resid<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, partial, NBMAX);
-        k_cg_scalars<<<1, 256, 0, st>>>(3, nb, NBMAX, partial, scal, rtol, atol);
-        c->launches += 2;
+        c->launches++;
+        LV_TRY(finish(3));
         LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
         LV_CUDA(c, cudaStreamSynchronize(st));
         const double bn = c->h_red[SC_BNORM2], rn = c->h_red[SC_RES2];
@@ -622,6 +645,10 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
         if ((st = lv_gather_to_slots(c, src_dev, it.dst, it.nc, it.fill)) != LV_OK) break;
     }
     if (!dev) { cudaStreamSynchronize(c->stream); lv_free(c, stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)); }
+    // neighbours' density, pressure and velocity across the strip edges
+    if (st == LV_OK && rho) st = lv_halo_exchange(c, c->d_rho, 1);
+    if (st == LV_OK && P) st = lv_halo_exchange(c, c->d_P, 1);
+    if (st == LV_OK && v) st = lv_halo_exchange(c, (double *)c->d_v, 2);
     if (st == LV_OK && mass && rho && c2) c->pr_valid = true;
     if (mass || rho || c2) c->assembled = false;
     if (v) c->bvel_valid = false;
@@ -675,6 +702,7 @@ __global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restric
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int s = prim[i];
+    if (s < 0) { diag_l[i] = 0.0; return; }
     diag_l[i] = diag[s];
     int o = rowptr_l[i];
     for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) {
@@ -691,7 +719,8 @@ __global__ void __launch_bounds__(256) k_op_deg(int64_t n, const int *__restrict
     if (i >= n) return;
     const int s = prim[i];
     int d = 0;
-    for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) d += col[k] >= 0;
+    if (s >= 0)
+        for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) d += col[k] >= 0;
     deg[i] = d;
 }
 
@@ -751,6 +780,7 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
     cudaError_t e = cudaMemcpyAsync(stage, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "upload failed: %s", cudaGetErrorString(e));
     if (st == LV_OK) st = lv_gather_to_slots(c, (const double *)stage, c->d_vec[3], 1, 0.0);
+    if (st == LV_OK) st = lv_halo_exchange(c, c->d_vec[3], 1);
     if (st == LV_OK) st = lv_pr_matvec(c, c->d_vec[3], c->d_vec[4]);
     cudaStreamSynchronize(c->stream);
     lv_free(c, stage, sizeof(double) * (size_t)n);

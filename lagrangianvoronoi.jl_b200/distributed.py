@@ -1,0 +1,317 @@
+"""Multi-GPU host logic: y-strip decomposition of the rectangle, one process per GPU.
+
+The reference is shared-memory only; this is the decomposition of section 8(e):
+
+* the global cell list (same origin, same ``h``) is cut into strips of bucket rows; a generator is owned by
+  the rank whose rows contain its primary bucket; labels stay global;
+* before a remesh every rank sends the generators whose buckets (primary or periodic image) fall into a
+  neighbour's halo window -- ``H`` bucket rows either side, ``H`` = the largest row offset the reference's
+  neighbour walk can reach before it throws (voronoigrid.jl:63-65) -- with ``torch.distributed`` send/recv;
+* owned and ghost generators are merged in global-label order, so the local cell list finds labels in the
+  same order as the single-GPU (= ``julia -t 1``) run and connectivity does not depend on the GPU count;
+* after the remesh the ranks agree on a halo plan (which of my slots a neighbour needs, in its order); the
+  library then exchanges ghost values with NCCL send/recv inside the Krylov loop and allreduces the dots.
+
+Everything in this module is plain ``torch`` + ``torch.distributed`` and works on CPU tensors with the
+``gloo`` backend (tests) as well as on CUDA tensors with ``nccl``; the compute calls go to liblvb200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import check, load_library, ptr
+from .host import PressureSolver, Rectangle, VoronoiGrid
+
+
+# ---------------------------------------------------------------------------------------------------
+# pure planning helpers (device agnostic, unit-tested on CPU)
+# ---------------------------------------------------------------------------------------------------
+def halo_rows(i2: np.ndarray, rr: np.ndarray, rr_max: float) -> int:
+    """Largest |row offset| of a path node the walk can actually visit (rr <= rr_max)."""
+    vis = rr <= rr_max
+    return int(np.abs(i2[vis]).max()) if vis.any() else 0
+
+
+def partition_rows(n2: int, row_lo: int, row_hi: int, world: int) -> np.ndarray:
+    """Row boundaries R[0..world]: rank r owns bucket rows [R[r], R[r+1]).  The rows [row_lo, row_hi] that
+    hold the primary buckets of the domain are split evenly; rank 0 also owns the padding rows below,
+    the last rank the padding rows above (they only ever hold periodic images)."""
+    inner = row_hi - row_lo + 1
+    cuts = [row_lo + (inner * r) // world for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n2
+    return np.asarray(cuts, dtype=np.int64)
+
+
+def bucket_row(y: torch.Tensor, oy: float, h: float) -> torch.Tensor:
+    """0-based bucket row of a y coordinate: floor((y - oy)/h), the arithmetic of findkey (neighborlist.jl:47-52)."""
+    return torch.floor((y - oy) / h).to(torch.int64)
+
+
+def owner_of_rows(rows: torch.Tensor, R: np.ndarray) -> torch.Tensor:
+    """Rank owning each bucket row (rows outside [0, n2) are clamped to the first / last rank)."""
+    cuts = torch.as_tensor(R[1:-1], dtype=torch.int64, device=rows.device)
+    return torch.searchsorted(cuts, rows, right=True)
+
+
+def ghost_mask_for(y: torch.Tensor, oy: float, h: float, yperiodic: bool, yperiod: float, lo: int, hi: int) -> torch.Tensor:
+    """Generators with a primary or y-image bucket row inside [lo, hi) (a neighbour's halo window).
+    x-images keep the row, so only the three y-images of insert_periodic! matter (voronoigrid.jl:130-147)."""
+    m = torch.zeros_like(y, dtype=torch.bool)
+    shifts = (0.0, yperiod, -yperiod) if yperiodic else (0.0,)
+    for s in shifts:
+        r = bucket_row(y + s * 1.0 if s else y, oy, h)
+        m |= (r >= lo) & (r < hi)
+    return m
+
+
+def exchange_variable(send: dict, world: int, rank: int, device, dtype, width: int, group=None) -> dict:
+    """Send ``send[q]`` (a [k, width] tensor, possibly empty) to every peer q in ``send`` and return what the
+    peers sent to us.  Counts travel first (all_gather), payloads with batched isend/irecv."""
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    for q, t in send.items():
+        counts[q] = t.shape[0]
+    all_counts = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    ops, recv = [], {}
+    for q in range(world):
+        if q == rank:
+            continue
+        k_in = int(all_counts[q][rank])
+        if k_in > 0:
+            recv[q] = torch.empty((k_in, width), dtype=dtype, device=device)
+            ops.append(dist.P2POp(dist.irecv, recv[q], q, group=group))
+        k_out = int(counts[q])
+        if k_out > 0:
+            ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
+
+
+class StripPlan:
+    """Geometry of the decomposition: who owns which bucket rows and which peers exist."""
+
+    def __init__(self, info: dict, path, h: float, rr_max: float, bmin, bmax, xperiodic: bool, yperiodic: bool, world: int, rank: int):
+        self.world, self.rank = world, rank
+        self.n1, self.n2 = int(info["n1"]), int(info["n2"])
+        self.oy = float(info["origin"][1])
+        self.h = float(h)
+        self.yperiodic = bool(yperiodic)
+        self.yperiod = float(bmax[1] - bmin[1])
+        i1, i2, rr = path
+        self.H = halo_rows(np.asarray(i2), np.asarray(rr), rr_max)
+        row_lo = int(math.floor((bmin[1] - self.oy) / self.h))
+        row_hi = int(math.floor((bmax[1] - self.oy) / self.h))
+        self.R = partition_rows(self.n2, row_lo, min(row_hi, self.n2 - 1), world)
+        if world > 1 and np.diff(self.R)[1:-1].min(initial=10 ** 9) < self.H:
+            raise ValueError(f"strips thinner than the halo ({self.H} bucket rows): use fewer ranks for this grid")
+        if world > 1 and min(self.R[1] - row_lo, row_hi + 1 - self.R[-2]) < self.H:
+            raise ValueError(f"strips thinner than the halo ({self.H} bucket rows): use fewer ranks for this grid")
+
+    def window(self, q: int):
+        """Bucket rows whose entries rank q needs: its own rows plus H rows either side."""
+        return int(self.R[q]) - self.H, int(self.R[q + 1]) + self.H
+
+    def peers(self):
+        """Ranks whose windows can overlap my rows: the strip neighbours, wrapping when y is periodic."""
+        if self.world == 1:
+            return []
+        cand = {self.rank - 1, self.rank + 1}
+        if self.yperiodic:
+            cand = {q % self.world for q in cand}
+            # images of the top strip land in the bottom padding rows and vice versa
+            if self.rank == 0:
+                cand.add(self.world - 1)
+            if self.rank == self.world - 1:
+                cand.add(0)
+        return sorted(q for q in cand if 0 <= q < self.world and q != self.rank)
+
+    def owner(self, y: torch.Tensor) -> torch.Tensor:
+        return owner_of_rows(bucket_row(y, self.oy, self.h), self.R)
+
+    def select_ghosts(self, xy: torch.Tensor, labels: torch.Tensor) -> dict:
+        """Per peer: the rows [x, y, label] of my generators that fall into its halo window."""
+        out = {}
+        for q in self.peers():
+            lo, hi = self.window(q)
+            m = ghost_mask_for(xy[:, 1], self.oy, self.h, self.yperiodic, self.yperiod, lo, hi)
+            sel = torch.nonzero(m, as_tuple=False).squeeze(1)
+            payload = torch.empty((sel.numel(), 3), dtype=torch.float64, device=xy.device)
+            payload[:, :2] = xy[sel]
+            payload[:, 2] = labels[sel].to(torch.float64)  # labels < 2^53 travel exactly in a double
+            out[q] = payload
+        return out
+
+
+def merge_owned_and_ghosts(xy_own, lab_own, recv: dict, rank: int):
+    """Local generator set in global-label order.  Returns (xy, labels, owner_rank) tensors."""
+    xs, ls, os_ = [xy_own], [lab_own], [torch.full_like(lab_own, rank)]
+    for q, t in sorted(recv.items()):
+        xs.append(t[:, :2])
+        lq = t[:, 2].to(torch.int64)
+        ls.append(lq)
+        os_.append(torch.full_like(lq, q))
+    xy, lab, own = torch.cat(xs), torch.cat(ls), torch.cat(os_)
+    order = torch.argsort(lab, stable=True)
+    return xy[order].contiguous(), lab[order].contiguous(), own[order].contiguous()
+
+
+def exchange_ghosts(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor, group=None):
+    """One ghost-generator exchange (collective).  Returns the local generator set in global-label order:
+    (xy, labels, owner_rank)."""
+    if plan.world > 1:
+        send = plan.select_ghosts(xy_own, lab_own)
+        recv = exchange_variable(send, plan.world, plan.rank, xy_own.device, torch.float64, 3, group)
+    else:
+        recv = {}
+    return merge_owned_and_ghosts(xy_own, lab_own, recv, plan.rank)
+
+
+def migrate_generators(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor, group=None):
+    """After a move: hand generators that left the strip to their new owner (collective).  Returns the new
+    owned set (xy, labels) in global-label order."""
+    if plan.world == 1:
+        return xy_own, lab_own
+    own = plan.owner(xy_own[:, 1])
+    send = {}
+    for q in range(plan.world):
+        if q == plan.rank:
+            continue
+        sel = torch.nonzero(own == q, as_tuple=False).squeeze(1)
+        pay = torch.empty((sel.numel(), 3), dtype=torch.float64, device=xy_own.device)
+        pay[:, :2] = xy_own[sel]
+        pay[:, 2] = lab_own[sel].to(torch.float64)
+        send[q] = pay
+    recv = exchange_variable(send, plan.world, plan.rank, xy_own.device, torch.float64, 3, group)
+    keep = own == plan.rank
+    xy, lab, _ = merge_owned_and_ghosts(xy_own[keep], lab_own[keep], recv, plan.rank)
+    return xy, lab
+
+
+# ---------------------------------------------------------------------------------------------------
+# the distributed grid / solver (GPU)
+# ---------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, p: int, n: int, typestr: str, shape=None):
+        self.__cuda_array_interface__ = {"shape": shape or (n,), "typestr": typestr, "data": (p, False), "version": 3}
+
+
+class StripGrid:
+    """A VoronoiGrid decomposed into y-strips over the ranks of a torch.distributed process group."""
+
+    def __init__(self, boundary_rect: Rectangle, dr: float, h=None, r_max=None, xperiodic=False, yperiodic=False,
+                 device: int = 0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.grid = VoronoiGrid(boundary_rect, dr, h=h, r_max=r_max, xperiodic=xperiodic, yperiodic=yperiodic, device=device)
+        g = self.grid
+        self.dev = torch.device("cuda", device)
+        self.plan = StripPlan(g.info(), g.magic_path(), g.h, g.rr_max, boundary_rect.xmin, boundary_rect.xmax, xperiodic,
+                              yperiodic, self.world, self.rank)
+        self._L = g._L
+        if self.world > 1:
+            idbuf = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                arr = (C.c_uint8 * 128)()
+                check(self._L.lv_comm_unique_id(arr), None)
+                idbuf = torch.tensor(list(arr), dtype=torch.uint8)
+            idbuf = idbuf.to(self.dev)
+            dist.broadcast(idbuf, 0, group=group)
+            raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
+            check(self._L.lv_comm_init(g._h, self.rank, self.world, raw), g._h)
+        self.xy_own = torch.zeros((0, 2), dtype=torch.float64, device=self.dev)
+        self.lab_own = torch.zeros(0, dtype=torch.int64, device=self.dev)
+
+    # -- generators -----------------------------------------------------------------------------------
+    def set_owned(self, xy, labels) -> None:
+        """Generators this rank owns (they must lie in its strip), global labels ascending."""
+        self.xy_own = torch.as_tensor(xy, dtype=torch.float64, device=self.dev).contiguous()
+        self.lab_own = torch.as_tensor(labels, dtype=torch.int64, device=self.dev).contiguous()
+
+    def migrate(self) -> None:
+        """After a move: hand generators that left the strip to their new owner."""
+        self.xy_own, self.lab_own = migrate_generators(self.plan, self.xy_own, self.lab_own, self.group)
+
+    # -- remesh!(grid) --------------------------------------------------------------------------------
+    def remesh(self) -> None:
+        g, L = self.grid, self._L
+        self.xy_loc, self.lab_loc, self.owner_loc = exchange_ghosts(self.plan, self.xy_own, self.lab_own, self.group)
+        self.mask_loc = (self.owner_loc == self.rank).to(torch.uint8).contiguous()
+        self.n_loc = int(self.xy_loc.shape[0])
+        stream = torch.cuda.current_stream(self.dev)
+        g.set_stream(stream.cuda_stream)
+        check(L.lv_remesh_owned_dev(g._h, self.n_loc, ptr(self.xy_loc), ptr(self.mask_loc)), g._h)
+        g._dev_n = self.n_loc
+        if self.world > 1:
+            self._build_halo_plan()
+
+    def _dev_tensor(self, which: int, typestr: str, torch_dtype):
+        p, n = C.c_void_p(), C.c_int64()
+        check(self._L.lv_device_array(self.grid._h, which, C.byref(p), C.byref(n)), self.grid._h)
+        if n.value == 0:
+            return torch.zeros(0, dtype=torch_dtype, device=self.dev)
+        return torch.as_tensor(_DevArray(p.value, n.value, typestr), device=self.dev)
+
+    def _build_halo_plan(self) -> None:
+        g, L = self.grid, self._L
+        ent = self._dev_tensor(0, "<i4", torch.int32)                             # label | image bit (bit 31 = sign)
+        prim = self._dev_tensor(1, "<i4", torch.int32)
+        lab_local = (ent & 0x7FFFFFFF).to(torch.int64)
+        slot_owner = self.owner_loc[lab_local]
+        recv_slots, requests = {}, {}
+        for q in self.plan.peers():
+            sl = torch.nonzero(slot_owner == q, as_tuple=False).squeeze(1)
+            recv_slots[q] = sl.to(torch.int32)
+            requests[q] = self.lab_loc[lab_local[sl]].unsqueeze(1)                 # global labels, in my slot order
+        asked = exchange_variable(requests, self.world, self.rank, self.dev, torch.int64, 1, self.group)
+        peers, send_slots = [], {}
+        for q in self.plan.peers():
+            want = asked.get(q, torch.zeros((0, 1), dtype=torch.int64, device=self.dev)).squeeze(1)
+            idx = torch.searchsorted(self.lab_loc, want)                           # global label -> local index
+            if want.numel() and not bool((self.lab_loc[idx.clamp(max=self.n_loc - 1)] == want).all()):
+                raise RuntimeError("halo plan: a peer asked for a generator this rank does not hold")
+            ss = prim[idx]
+            if ss.numel() and int(ss.min()) < 0:
+                raise RuntimeError("halo plan: requested generator has no primary slot here")
+            send_slots[q] = ss.to(torch.int32)
+            peers.append(q)
+        npeer = len(peers)
+        pr = (C.c_int32 * max(npeer, 1))(*peers)
+        sc = (C.c_int64 * max(npeer, 1))(*[int(send_slots[q].numel()) for q in peers])
+        rc = (C.c_int64 * max(npeer, 1))(*[int(recv_slots[q].numel()) for q in peers])
+        s_all = torch.cat([send_slots[q] for q in peers]) if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
+        r_all = torch.cat([recv_slots[q] for q in peers]) if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
+        self._halo_keep = (s_all.contiguous(), r_all.contiguous())
+        torch.cuda.current_stream(self.dev).synchronize()
+        check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(self._halo_keep[0]) if s_all.numel() else None, rc,
+                             ptr(self._halo_keep[1]) if r_all.numel() else None), g._h)
+        self.halo_counts = {q: (int(send_slots[q].numel()), int(recv_slots[q].numel())) for q in peers}
+
+    # -- results --------------------------------------------------------------------------------------
+    def owned_index(self) -> torch.Tensor:
+        """Positions of the owned generators inside the local (label-ordered) arrays."""
+        return torch.nonzero(self.mask_loc, as_tuple=False).squeeze(1)
+
+    def mesh_download(self, edges: bool = True):
+        """(rowptr, edges, area, centroid) of the LOCAL generator list; ghost rows are empty.  Edge labels are
+        1-based local indices; ``self.lab_loc[label-1]`` is the global label."""
+        return self.grid.mesh_download(self.n_loc, edges=edges)
+
+
+class StripSolver(PressureSolver):
+    """PressureSolver on a StripGrid: fields are given for the local generator list (ghost entries are
+    overwritten by the halo exchange), the solve runs collectively on all ranks."""
+
+    def __init__(self, sgrid: StripGrid, **kw):
+        self.sgrid = sgrid
+        super().__init__(sgrid.grid, **kw)
