@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-side", type=int, default=1024, help="lattice side of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = M^2 cells per GPU (box [0,1]x[0,N]); strong = one M x M box split N ways")
     return ap.parse_args()
 
 
@@ -172,31 +174,65 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     M = args.side
-    n = M * M
     dr = 1.0 / M
     dt = 0.1 * dr
-    # every rank owns an independent periodic box (replicas) until the strip decomposition lands
-    xy = lv.synthetic.jittered_lattice(M, args.seed + rank)
-    g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), dr, xperiodic=True, yperiodic=True, device=local)
     stream = torch.cuda.current_stream()
-    g.set_stream(stream.cuda_stream)
-    g.set_points(xy)
-    xy_dev = torch.from_numpy(xy).to(dev)
-    g.remesh_dev(xy_dev)
-    solver = lv.PressureSolver(g)
-    _, _, area, _ = g.mesh_download(n, edges=False)
-    v, P = lv.synthetic.taylor_green_fields(xy)
-    f_host = {"mass": area.copy(), "rho": np.ones(n), "c2": np.full(n, args.c0 ** 2), "P": P, "v": v}
-    f_dev = {k: torch.from_numpy(np.ascontiguousarray(a)).to(dev) for k, a in f_host.items()}
-    for k, a in f_host.items():
-        getattr(g, k)[...] = a
+    if world == 1:
+        # ---- one GPU: the whole periodic unit box
+        n = M * M
+        xy = lv.synthetic.jittered_lattice(M, args.seed)
+        g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), dr, xperiodic=True, yperiodic=True, device=local)
+        g.set_stream(stream.cuda_stream)
+        g.set_points(xy)
+        xy_dev = torch.from_numpy(xy).to(dev)
+        g.remesh_dev(xy_dev)
+        solver = lv.PressureSolver(g)
+        _, _, area, _ = g.mesh_download(n, edges=False)
+        v, P = lv.synthetic.taylor_green_fields(xy)
+        f_host = {"mass": area.copy(), "rho": np.ones(n), "c2": np.full(n, args.c0 ** 2), "P": P, "v": v}
+        f_dev = {k: torch.from_numpy(np.ascontiguousarray(a)).to(dev) for k, a in f_host.items()}
+        for k, a in f_host.items():
+            getattr(g, k)[...] = a
+        n_total = n
+        parallelism = "single GPU"
 
-    def step_dev():
-        g.remesh_dev(xy_dev)
-        g.remesh_dev(xy_dev)
-        solver.upload_fields(f_dev["mass"], f_dev["rho"], f_dev["c2"], f_dev["P"], f_dev["v"], device=True)
-        iters, _ = solver.find_pressure_dev(dt, args.niter)
-        return int(iters.sum())
+        def step_dev():
+            g.remesh_dev(xy_dev)
+            g.remesh_dev(xy_dev)
+            solver.upload_fields(f_dev["mass"], f_dev["rho"], f_dev["c2"], f_dev["P"], f_dev["v"], device=True)
+            iters, _ = solver.find_pressure_dev(dt, args.niter)
+            return int(iters.sum())
+    else:
+        # ---- N GPUs: y-strips of one periodic box, ghost-generator exchange per remesh, NCCL halo + allreduce in CG.
+        # weak: the box grows to [0,1] x [0,N] (one unit square of M^2 cells per GPU); strong: a fixed M x M box.
+        from lvb200.distributed import StripGrid, StripSolver
+        My = M * world if args.scaling == "weak" else M
+        n_total = M * My
+        j0, j1 = (My * rank) // world, (My * (rank + 1)) // world
+        xy, k = lv.synthetic.jittered_lattice(M, args.seed, rows=(j0, j1), My=My, return_index=True)
+        sg = StripGrid(lv.Rectangle((0.0, 0.0), (1.0, My / M)), dr, xperiodic=True, yperiodic=True, device=local)
+        g = sg.grid
+        sg.set_owned(xy, k + 1)
+        sg.migrate()  # lattice strips and bucket-row strips agree up to a row: settle ownership once
+        sg.remesh()
+        solver = StripSolver(sg)
+        _, _, area, _ = sg.mesh_download(edges=False)
+        xy_loc = sg.xy_loc.cpu().numpy()
+        v, P = lv.synthetic.taylor_green_fields(xy_loc)
+        nl = xy_loc.shape[0]
+        f_dev = {k2: torch.from_numpy(np.ascontiguousarray(a)).to(dev) for k2, a in
+                 {"mass": np.where(area > 0, area, 1.0), "rho": np.ones(nl), "c2": np.full(nl, args.c0 ** 2), "P": P, "v": v}.items()}
+        n = int(sg.mask_loc.sum().item())
+        parallelism = (f"{world} y-strips ({args.scaling} scaling), ghost generators by torch.distributed send/recv per remesh, "
+                       f"NCCL halo + 2-scalar allreduce per CG iteration; halo (send, recv) per peer = {sg.halo_counts}")
+        args.no_e2e = True  # the host-buffer drop-in API is single-GPU (one Julia process, one GPU)
+
+        def step_dev():
+            sg.remesh()
+            sg.remesh()
+            solver.upload_fields(f_dev["mass"], f_dev["rho"], f_dev["c2"], f_dev["P"], f_dev["v"], device=True)
+            iters, _ = solver.find_pressure_dev(dt, args.niter)
+            return int(iters.sum())
 
     def step_e2e():
         g.P[...] = P
@@ -251,7 +287,7 @@ def run_ours(args):
         nnz = int(g.rowptr[-1])
         h2d = 2 * n * 16 + n * 8 * 6                     # 2 x positions + mass, rho, c2, P, v(2)
         d2h = 2 * ((n + 1) * 8 + nnz * 40 + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
-        e2e = {"value": world * n * args.steps / (float(te.item()) / 1e3) / 1e6, "unit": UNIT,
+        e2e = {"value": n_total * args.steps / (float(te.item()) / 1e3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / args.steps}
 
     if rank != 0:
@@ -268,18 +304,19 @@ def run_ours(args):
     rem_ms = prof["cells"][0] + prof["clip"][0]
     pr_ms = prof["assemble"][0] + prof["matvec"][0] + prof["vecops"][0]
     line = {
-        "metric": METRIC, "value": world * n * args.steps / (ms_max / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": n_total * args.steps / (ms_max / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic periodic random-jittered box, {n} cells per GPU (M={M}), dr=1/{M}, h=2dr, r_max=10dr, "
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic periodic random-jittered box, {n_total} cells over {world} GPU(s) (lattice side M={M}), dr=1/{M}, h=2dr, r_max=10dr, "
                                f"Taylor-Green v/P, rho=1, c0={args.c0}, dt=0.1dr; step = 2 x remesh + find_pressure(niter={args.niter}, "
                                f"CG rtol=atol=1e-6, itmax=1000)",
-                   "cells_per_gpu": n, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "cells_total": n_total, "cells_rank0": n, "parallelism": parallelism,
                    "l2": "inputs larger than L2 (no flush needed)", "krylov_iters_per_step": iters_total // args.steps},
-        "submetrics": {"remesh_mcells_s": 2 * n * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
-                       "cg_mcell_iters_s": n * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
+        "submetrics": {"remesh_mcells_s": 2 * n_total * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
+                       "cg_mcell_iters_s": n_total * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
                        "s_per_step": ms_max / args.steps / 1e3,
-                       "phase_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}},
+                       "phase_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()},
+                                                 host_and_exchange=(ms_max - sum(v[0] for v in prof.values())) / args.steps)},
         "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
                      "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if hbm else None, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "avg_launch_ms": mv_avg, "launches": mv_cnt, "launches_queued": mv_launched,

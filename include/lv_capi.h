@@ -73,8 +73,9 @@ int32_t lv_set_rects(LvHandle h, const double bmin[2], const double bmax[2], con
 /* cell-list geometry (neighborlist.jl:23-25) and the length of the truncated magic_path */
 int32_t lv_grid_info(LvHandle h, int64_t *n1, int64_t *n2, double origin[2], int64_t *npath);
 int32_t lv_magic_path(LvHandle h, int64_t cap, int64_t *i1, int64_t *i2, double *rr, int64_t *count);
-/* run on a caller-provided cudaStream_t (NULL restores the handle's own stream) */
-int32_t lv_set_stream(LvHandle h, void *cuda_stream);
+/* run on a caller-provided cudaStream_t (own = 0; NULL is the legacy default stream) or go back to the
+ * handle's own non-blocking stream (own = 1) */
+int32_t lv_set_stream(LvHandle h, void *cuda_stream, int32_t own);
 int32_t lv_sync(LvHandle h); /* stream-synchronise and report any pending device-side status */
 
 /* ---- remesh!(grid)  voronoigrid.jl:89-108 ----------------------------------------------- */

@@ -79,7 +79,7 @@ def load_library() -> C.CDLL:
     L.lv_set_rects.argtypes = [vp, dp, dp, dp, dp]
     L.lv_grid_info.argtypes = [vp, ip, ip, dp, ip]
     L.lv_magic_path.argtypes = [vp, C.c_int64, ip, ip, dp, ip]
-    L.lv_set_stream.argtypes = [vp, vp]
+    L.lv_set_stream.argtypes = [vp, vp, C.c_int32]
     L.lv_sync.argtypes = [vp]
     L.lv_remesh.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int64, ip, vp, vp]
     L.lv_remesh_dev.argtypes = [vp, C.c_int64, vp]

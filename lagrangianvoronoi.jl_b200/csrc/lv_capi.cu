@@ -237,11 +237,13 @@ int32_t lv_magic_path(LvHandle c, int64_t cap, int64_t *i1, int64_t *i2, double 
     return LV_OK;
 }
 
-int32_t lv_set_stream(LvHandle c, void *stream) {
+int32_t lv_set_stream(LvHandle c, void *stream, int32_t own) {
     if (!c) return LV_EINVAL;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    // a NULL stream is a real stream (the legacy default stream torch uses): it must not fall back to the
+    // handle's non-blocking stream, which does not order against it
+    c->stream = own ? c->own_stream : (cudaStream_t)stream;
     return LV_OK;
 }
 

@@ -168,7 +168,11 @@ class VoronoiGrid:
         check(self._L.lv_sync(self._h), self._h)
 
     def set_stream(self, stream_ptr: int | None):
-        check(self._L.lv_set_stream(self._h, C.c_void_p(stream_ptr or 0)), self._h)
+        """Run on the given cudaStream_t (0 = the legacy default stream torch uses); None = the handle's own stream."""
+        if stream_ptr is None:
+            check(self._L.lv_set_stream(self._h, None, 1), self._h)
+        else:
+            check(self._L.lv_set_stream(self._h, C.c_void_p(int(stream_ptr)), 0), self._h)
 
     # -- device-resident entry points (inputs already in HBM; used by bench.py `value`) ---------------
     def remesh_dev(self, xy_dev, n: int | None = None) -> None:

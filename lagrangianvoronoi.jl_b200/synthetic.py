@@ -30,21 +30,25 @@ def uniform(seed: int, counter: np.ndarray) -> np.ndarray:
     return (mix64(z) >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
 
 
-def jittered_lattice(M: int, seed: int = 0, jitter: float = 0.8, rows: tuple | None = None) -> np.ndarray:
-    """Generator k = i*M + j at ((i+0.5+J(u1-0.5))dr, (j+0.5+J(u2-0.5))dr), dr = 1/M.
+def jittered_lattice(M: int, seed: int = 0, jitter: float = 0.8, rows: tuple | None = None, My: int | None = None,
+                     return_index: bool = False):
+    """Generator k = i*My + j at ((i+0.5+J(u1-0.5))dr, (j+0.5+J(u2-0.5))dr), dr = 1/M, i < M, j < My (= M).
 
-    ``rows=(j0, j1)`` returns only the generators with lattice column index j in [j0, j1) -- the
-    y-strip a rank owns in the multi-GPU decomposition -- in the same global order."""
+    ``rows=(j0, j1)`` returns only the generators with lattice index j in [j0, j1) -- the y-strip a rank owns in
+    the multi-GPU decomposition -- in the same global order.  ``My`` stretches the box to [0,1] x [0, My/M]
+    (weak scaling: one unit square per GPU).  ``return_index`` also returns the 0-based global index k."""
     dr = 1.0 / M
+    My = M if My is None else My
     i = np.arange(M, dtype=np.int64)
-    j = np.arange(M, dtype=np.int64) if rows is None else np.arange(rows[0], rows[1], dtype=np.int64)
+    j = np.arange(My, dtype=np.int64) if rows is None else np.arange(rows[0], rows[1], dtype=np.int64)
     I, J = np.meshgrid(i, j, indexing="ij")
-    k = (I * M + J).reshape(-1)
+    k = (I * My + J).reshape(-1)
     u1 = uniform(seed, 2 * k)
     u2 = uniform(seed, 2 * k + 1)
     x = (I.reshape(-1) + 0.5 + jitter * (u1 - 0.5)) * dr
     y = (J.reshape(-1) + 0.5 + jitter * (u2 - 0.5)) * dr
-    return np.stack([x, y], axis=1)
+    xy = np.stack([x, y], axis=1)
+    return (xy, k) if return_index else xy
 
 
 def taylor_green_fields(xy: np.ndarray, t: float = 0.0, Re: float = 400.0):
