@@ -301,6 +301,13 @@ def run_ours(args):
     mv_cnt = iters_total + args.niter * args.steps
     mv_avg = mv_ms / max(mv_cnt, 1)
     achieved = MATVEC_BYTES_PER_CELL * n / (mv_avg * 1e-3) / 1e9 if mv_avg > 0 else 0.0
+    traffic = None
+    try:  # DRAM bytes per launch measured once with ncu --set full (profiles/), scaled to this run's cell count
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_matvec"]
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["cells"]
+    except Exception:
+        pass
     rem_ms = prof["cells"][0] + prof["clip"][0]
     pr_ms = prof["assemble"][0] + prof["matvec"][0] + prof["vecops"][0]
     line = {
@@ -320,7 +327,7 @@ def run_ours(args):
         "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
                      "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if hbm else None, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "avg_launch_ms": mv_avg, "launches": mv_cnt, "launches_queued": mv_launched,
-                     "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_CELL * n, "traffic": None},
+                     "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_CELL * n, "traffic": traffic},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu:
