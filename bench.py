@@ -176,7 +176,9 @@ def run_ours(args):
     M = args.side
     dr = 1.0 / M
     dt = 0.1 * dr
-    stream = torch.cuda.current_stream()
+    # everything (torch ops, NCCL waits, the library's kernels and copies) runs on ONE explicit non-default stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     if world == 1:
         # ---- one GPU: the whole periodic unit box
         n = M * M

@@ -189,7 +189,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
                     c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
-                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own};
+                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -357,9 +357,8 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
     size_t off_cen = off_area + sizeof(double) * (size_t)n;
     size_t off_e = (off_cen + sizeof(double2) * (size_t)n + 15) & ~(size_t)15;
     size_t total = off_e + (edges ? sizeof(LvEdge) * (size_t)nnz : 0) + 64;
-    void *stage = nullptr;
-    LV_TRY(lv_alloc(c, &stage, total));
-    char *base = (char *)stage;
+    LV_TRY(lv_ensure(c, &c->d_stage, &c->cap_stage, (int64_t)total, 1)); // grow-only: no cudaMalloc/cudaFree per remesh
+    char *base = (char *)c->d_stage;
     int *deg = (int *)(base + off_deg), *rl = (int *)(base + off_rl);
     long long *r64 = (long long *)(base + off_r64);
     double *area_l = (double *)(base + off_area);
@@ -384,7 +383,6 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
         if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "mesh download failed: %s", cudaGetErrorString(e));
     } while (0);
     cudaStreamSynchronize(c->stream);
-    lv_free(c, stage, total);
     return st;
 }
 

@@ -81,6 +81,8 @@ struct LvContext {
     // scratch for scans / label-order staging
     void *d_scratch = nullptr;
     int64_t cap_scratch = 0;
+    void *d_stage = nullptr; // label-order staging of the mesh for the device->host copy
+    int64_t cap_stage = 0;
     // pressure (slot order)
     bool pr_valid = false;
     int64_t pr_cap = 0;

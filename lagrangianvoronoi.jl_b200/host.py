@@ -217,10 +217,9 @@ def remesh(grid: VoronoiGrid, edges: bool = True) -> None:
                           ptr(grid._centroid)), grid._h)
         grid.edges = None
         return
-    cap = 0 if grid.edges is None else grid.edges.shape[0]
-    guess = max(cap, 7 * n + 64)
-    if grid.edges is None or cap < guess:
-        grid._edge_buf = _host_empty((guess,), EDGE_DTYPE)
+    buf = getattr(grid, "_edge_buf", None)
+    if buf is None or buf.shape[0] < 6 * n + 64:  # grow-only pinned buffer: page-locking GBs per call would dominate
+        grid._edge_buf = _host_empty((7 * n + 64,), EDGE_DTYPE)
     st = L.lv_remesh(grid._h, n, ptr(grid.x), ptr(grid.rowptr), ptr(grid._edge_buf), grid._edge_buf.shape[0],
                      C.byref(nnz), ptr(grid._area), ptr(grid._centroid))
     if st == _capi.LV_ECAPACITY and nnz.value > grid._edge_buf.shape[0]:  # pragma: no cover - 7n is generous
