@@ -143,9 +143,12 @@ int32_t lv_pressure_solve(LvHandle h, int32_t solver, const double *b, double *x
  * torch.distributed and hands the library the NCCL id, the ownership mask and the halo plan. */
 int32_t lv_comm_unique_id(uint8_t *out128);                       /* ncclGetUniqueId on rank 0 */
 int32_t lv_comm_init(LvHandle h, int32_t rank, int32_t nranks, const uint8_t *id128);
-/* remesh!(grid) on the generators present on this rank (owned + ghosts, ordered by global label);
- * only polygons with owned_mask_dev[i] != 0 are clipped, ghosts are candidates only */
-int32_t lv_remesh_owned_dev(LvHandle h, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev);
+/* remesh!(grid) on the generators present on this rank (owned + ghosts).  Only polygons with
+ * owned_mask_dev[i] != 0 are clipped, ghosts are candidates only.  order_key_dev[i] (the global label,
+ * < 2^31) orders the labels inside a bucket so that the candidate order -- hence every vertex bit -- is
+ * the single-GPU order (`julia -t 1` order) regardless of how generators are laid out locally. */
+int32_t lv_remesh_owned_dev(LvHandle h, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev,
+                            const int32_t *order_key_dev);
 /* device pointers into the slot-ordered cell list (0 ent_label u32, 1 prim_of_label i32, 2 own u8,
  * 3 ent_xy f64x2, 4 P f64, 5 area f64) for building the halo plan on the host */
 int32_t lv_device_array(LvHandle h, int32_t which, void **ptr, int64_t *count);

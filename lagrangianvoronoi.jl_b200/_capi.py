@@ -103,7 +103,7 @@ def load_library() -> C.CDLL:
     L.lv_pressure_solve.argtypes = [vp, C.c_int32, vp, vp, C.c_double, C.c_double, C.c_int32, i32p, dp]
     L.lv_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.lv_comm_init.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
-    L.lv_remesh_owned_dev.argtypes = [vp, C.c_int64, vp, vp]
+    L.lv_remesh_owned_dev.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.lv_device_array.argtypes = [vp, C.c_int32, C.POINTER(vp), ip]
     L.lv_halo_plan.argtypes = [vp, C.c_int32, i32p, ip, vp, ip, vp]
     L.lv_halo_exchange_dev.argtypes = [vp, vp, C.c_int32]

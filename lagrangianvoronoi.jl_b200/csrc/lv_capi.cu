@@ -286,6 +286,7 @@ int32_t lv_remesh_dev(LvHandle c, int64_t n, const double *xy_dev) {
     c->xy = (const double2 *)xy_dev; // used in place: positions are only read
     int st = remesh_common(c, n);
     c->owned_mask = nullptr; // one-shot: set by lv_remesh_owned_dev
+    c->order_key = nullptr;
     return st;
 }
 
@@ -402,6 +403,7 @@ int32_t lv_remesh(LvHandle c, int64_t n, const double *xy, int64_t *rowptr, LvEd
     if (n > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_xy, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     c->xy = c->d_xy;
     c->owned_mask = nullptr;
+    c->order_key = nullptr;
     LV_TRY(remesh_common(c, n));
     if (nnz) *nnz = c->nnz;
     if (rowptr || edges || area || centroid) LV_TRY(lv_mesh_to_labels(c, rowptr, edges, cap, area, centroid));

@@ -66,29 +66,38 @@ __global__ void __launch_bounds__(256) k_cells_count_fill(LvGridParams g, int64_
 __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *__restrict__ start,
                                                      unsigned *__restrict__ ent_label, double2 *__restrict__ ent_xy,
                                                      const double2 *__restrict__ xy, int *__restrict__ prim_of_label,
-                                                     const unsigned char *__restrict__ owned_mask, unsigned char *__restrict__ own) {
+                                                     const unsigned char *__restrict__ owned_mask, unsigned char *__restrict__ own,
+                                                     const int *__restrict__ order_key) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= ncell_ext) return;
     const int s0 = start[b], s1 = start[b + 1];
     const int k = s1 - s0;
     if (k <= 0) return;
     const unsigned M = ~LV_IMAGE_BIT;
+    // sort key: (label, image bit); in the multi-GPU decomposition the label is replaced by the generator's
+    // GLOBAL label (order_key) so that every rank orders a bucket exactly like the single-GPU run does
+    auto key_of = [order_key](unsigned e) -> unsigned {
+        const unsigned lab = e & ~LV_IMAGE_BIT;
+        const unsigned base = order_key ? (unsigned)order_key[lab] : lab;
+        return (base << 1) | (e >> 31);
+    };
     if (k <= 16) {
-        unsigned v[16];
+        unsigned v[16], kk[16];
 #pragma unroll
-        for (int a = 0; a < 16; a++) v[a] = a < k ? ent_label[s0 + a] : 0xffffffffu;
-        // odd-even transposition network on the key (label, image-bit): branch-free, registers only
+        for (int a = 0; a < 16; a++) {
+            v[a] = a < k ? ent_label[s0 + a] : 0xffffffffu;
+            kk[a] = a < k ? key_of(v[a]) : 0xffffffffu;
+        }
+        // odd-even transposition network: branch-free, registers only
 #pragma unroll
         for (int r = 0; r < 16; r++) {
 #pragma unroll
             for (int a = (r & 1); a + 1 < 16; a += 2) {
-                unsigned ka = (v[a] << 1) | (v[a] >> 31), kb = (v[a + 1] << 1) | (v[a + 1] >> 31);
-                if (v[a] == 0xffffffffu) ka = 0xffffffffu;
-                if (v[a + 1] == 0xffffffffu) kb = 0xffffffffu;
-                bool sw = kb < ka;
-                unsigned lo = sw ? v[a + 1] : v[a], hi = sw ? v[a] : v[a + 1];
-                v[a] = lo;
-                v[a + 1] = hi;
+                const bool sw = kk[a + 1] < kk[a];
+                const unsigned lo = sw ? v[a + 1] : v[a], hi = sw ? v[a] : v[a + 1];
+                const unsigned klo = sw ? kk[a + 1] : kk[a], khi = sw ? kk[a] : kk[a + 1];
+                v[a] = lo; v[a + 1] = hi;
+                kk[a] = klo; kk[a + 1] = khi;
             }
         }
 #pragma unroll
@@ -96,7 +105,7 @@ __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *_
             if (a < k) ent_label[s0 + a] = v[a];
     } else { // heap sort in place (crowded bucket)
         unsigned *A = ent_label + s0;
-        auto key = [](unsigned v) { return ((unsigned long long)(v & ~LV_IMAGE_BIT) << 1) | (v >> 31); };
+        auto key = [&](unsigned v) { return key_of(v); };
         for (int st = k / 2 - 1; st >= 0; st--) {
             int r = st;
             for (;;) {
@@ -271,7 +280,7 @@ int lv_cells_build(LvContext *c) {
         k_cells_count_fill<true><<<nb, 256, 0, st>>>(c->gp, n, c->xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label,
                                                      c->d_flags);
         k_cells_order<<<(int)((ncell_ext + 127) / 128), 128, 0, st>>>((int)ncell_ext, c->d_cell_start, c->d_ent_label,
-                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label, c->owned_mask, c->d_own);
+                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label, c->owned_mask, c->d_own, c->order_key);
         c->launches += 2;
     }
     LV_CUDA(c, cudaGetLastError());

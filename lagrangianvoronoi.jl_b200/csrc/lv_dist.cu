@@ -195,11 +195,14 @@ int32_t lv_device_array(LvHandle c, int32_t which, void **ptr, int64_t *count) {
     return LV_OK;
 }
 
-// remesh on the generators present on this rank (owned + ghosts, sorted by global label so that the
-// local index order is the global label order); only polygons with owned_mask != 0 are clipped
-int32_t lv_remesh_owned_dev(LvHandle c, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev) {
+// remesh on the generators present on this rank (owned + ghosts); buckets are ordered by order_key (the
+// global labels) so that the candidate order equals the single-GPU order; only polygons with
+// owned_mask != 0 are clipped
+int32_t lv_remesh_owned_dev(LvHandle c, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev,
+                            const int32_t *order_key_dev) {
     if (!c) return LV_EINVAL;
     c->owned_mask = owned_mask_dev;
+    c->order_key = order_key_dev;
     int32_t st = lv_remesh_dev(c, n_local, xy_dev);
     return st;
 }

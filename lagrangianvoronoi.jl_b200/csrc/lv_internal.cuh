@@ -62,6 +62,7 @@ struct LvContext {
     int *d_prim_of_label = nullptr;  // [n] label -> primary slot (-1: no primary slot in the local cell list)
     unsigned char *d_own = nullptr;  // [nslot] 1 = primary slot of a generator this rank owns (a real row)
     const unsigned char *owned_mask = nullptr; // [n] caller's device mask of owned generators (NULL: all)
+    const int *order_key = nullptr;            // [n] caller's device ordering key (global labels) or NULL = the label itself
     // mesh (slot order)
     int *d_rowptr = nullptr; // [nslot] first edge of the row (rows are NOT stored in slot order, see lv_clip_fast.cu)
     unsigned char *d_deg = nullptr; // [nslot] number of edges of the row

@@ -136,9 +136,10 @@ class StripPlan:
     def owner(self, y: torch.Tensor) -> torch.Tensor:
         return owner_of_rows(bucket_row(y, self.oy, self.h), self.R)
 
-    def select_ghosts(self, xy: torch.Tensor, labels: torch.Tensor) -> dict:
-        """Per peer: the rows [x, y, label] of my generators that fall into its halo window."""
-        out = {}
+    def select_ghosts(self, xy: torch.Tensor, labels: torch.Tensor):
+        """Per peer: the rows [x, y, label] of my generators that fall into its halo window, and their
+        indices in my owned arrays (the halo plan refers to ghosts by their position in this list)."""
+        out, sels = {}, {}
         for q in self.peers():
             lo, hi = self.window(q)
             m = ghost_mask_for(xy[:, 1], self.oy, self.h, self.yperiodic, self.yperiod, lo, hi)
@@ -147,7 +148,8 @@ class StripPlan:
             payload[:, :2] = xy[sel]
             payload[:, 2] = labels[sel].to(torch.float64)  # labels < 2^53 travel exactly in a double
             out[q] = payload
-        return out
+            sels[q] = sel
+        return out, sels
 
 
 def merge_owned_and_ghosts(xy_own, lab_own, recv: dict, rank: int):
@@ -163,15 +165,36 @@ def merge_owned_and_ghosts(xy_own, lab_own, recv: dict, rank: int):
     return xy[order].contiguous(), lab[order].contiguous(), own[order].contiguous()
 
 
-def exchange_ghosts(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor, group=None):
-    """One ghost-generator exchange (collective).  Returns the local generator set in global-label order:
-    (xy, labels, owner_rank)."""
+class LocalSet:
+    """Generators present on a rank after the ghost exchange: the owned ones first (in the order given), then
+    the ghosts grouped by the peer that sent them (in that peer's send order)."""
+
+    def __init__(self, xy, lab, owner, n_own, ghost_range, sent_sel):
+        self.xy, self.lab, self.owner, self.n_own = xy, lab, owner, n_own
+        self.ghost_range = ghost_range  # peer -> (start, stop) in the local arrays
+        self.sent_sel = sent_sel        # peer -> indices (into my owned arrays) of what I sent there
+
+
+def exchange_ghosts(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor, group=None) -> LocalSet:
+    """One ghost-generator exchange (collective).  No sorting or merging: the library orders every bucket by
+    the global label it is given as ordering key, so ghosts are simply appended."""
+    n_own = int(xy_own.shape[0])
     if plan.world > 1:
-        send = plan.select_ghosts(xy_own, lab_own)
+        send, sels = plan.select_ghosts(xy_own, lab_own)
         recv = exchange_variable(send, plan.world, plan.rank, xy_own.device, torch.float64, 3, group)
     else:
-        recv = {}
-    return merge_owned_and_ghosts(xy_own, lab_own, recv, plan.rank)
+        sels, recv = {}, {}
+    xs, ls, os_ = [xy_own], [lab_own], [torch.full_like(lab_own, plan.rank)]
+    ranges, pos = {}, n_own
+    for q in sorted(recv):
+        t = recv[q]
+        xs.append(t[:, :2])
+        lq = t[:, 2].to(torch.int64)
+        ls.append(lq)
+        os_.append(torch.full_like(lq, q))
+        ranges[q] = (pos, pos + int(t.shape[0]))
+        pos += int(t.shape[0])
+    return LocalSet(torch.cat(xs).contiguous(), torch.cat(ls).contiguous(), torch.cat(os_).contiguous(), n_own, ranges, sels)
 
 
 def migrate_generators(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor, group=None):
@@ -245,12 +268,18 @@ class StripGrid:
     # -- remesh!(grid) --------------------------------------------------------------------------------
     def remesh(self) -> None:
         g, L = self.grid, self._L
-        self.xy_loc, self.lab_loc, self.owner_loc = exchange_ghosts(self.plan, self.xy_own, self.lab_own, self.group)
-        self.mask_loc = (self.owner_loc == self.rank).to(torch.uint8).contiguous()
-        self.n_loc = int(self.xy_loc.shape[0])
+        loc = exchange_ghosts(self.plan, self.xy_own, self.lab_own, self.group)
+        self.local = loc
+        self.xy_loc, self.lab_loc, self.owner_loc = loc.xy, loc.lab, loc.owner
+        self.n_loc = int(loc.xy.shape[0])
+        if self.n_loc and int(loc.lab.max()) >= 2 ** 31:
+            raise ValueError("global labels must stay below 2^31")
+        self.key_loc = loc.lab.to(torch.int32).contiguous()
+        self.mask_loc = torch.zeros(self.n_loc, dtype=torch.uint8, device=self.dev)
+        self.mask_loc[: loc.n_own] = 1
         stream = torch.cuda.current_stream(self.dev)
         g.set_stream(stream.cuda_stream)
-        check(L.lv_remesh_owned_dev(g._h, self.n_loc, ptr(self.xy_loc), ptr(self.mask_loc)), g._h)
+        check(L.lv_remesh_owned_dev(g._h, self.n_loc, ptr(self.xy_loc), ptr(self.mask_loc), ptr(self.key_loc)), g._h)
         g._dev_n = self.n_loc
         if self.world > 1:
             self._build_halo_plan()
@@ -263,24 +292,28 @@ class StripGrid:
         return torch.as_tensor(_DevArray(p.value, n.value, typestr), device=self.dev)
 
     def _build_halo_plan(self) -> None:
-        g, L = self.grid, self._L
-        ent = self._dev_tensor(0, "<i4", torch.int32)                             # label | image bit (bit 31 = sign)
+        """Ghost slots are filled from their owners.  A ghost is named by its position in the list its owner
+        sent (no label search): I ask peer q for positions k, q answers with the primary slots of sent_sel[q][k]."""
+        g, L, loc = self.grid, self._L, self.local
+        ent = self._dev_tensor(0, "<i4", torch.int32)                              # label | image bit (bit 31 = sign)
         prim = self._dev_tensor(1, "<i4", torch.int32)
-        lab_local = (ent & 0x7FFFFFFF).to(torch.int64)
-        slot_owner = self.owner_loc[lab_local]
+        lab_local = ent & 0x7FFFFFFF
+        gs = torch.nonzero(lab_local >= loc.n_own, as_tuple=False).squeeze(1)       # slots of ghost entries
+        gl = lab_local[gs].to(torch.int64)
         recv_slots, requests = {}, {}
         for q in self.plan.peers():
-            sl = torch.nonzero(slot_owner == q, as_tuple=False).squeeze(1)
-            recv_slots[q] = sl.to(torch.int32)
-            requests[q] = self.lab_loc[lab_local[sl]].unsqueeze(1)                 # global labels, in my slot order
+            a, b = loc.ghost_range.get(q, (0, 0))
+            m = (gl >= a) & (gl < b)
+            recv_slots[q] = gs[m].to(torch.int32)
+            requests[q] = (gl[m] - a).unsqueeze(1)
         asked = exchange_variable(requests, self.world, self.rank, self.dev, torch.int64, 1, self.group)
         peers, send_slots = [], {}
         for q in self.plan.peers():
             want = asked.get(q, torch.zeros((0, 1), dtype=torch.int64, device=self.dev)).squeeze(1)
-            idx = torch.searchsorted(self.lab_loc, want)                           # global label -> local index
-            if want.numel() and not bool((self.lab_loc[idx.clamp(max=self.n_loc - 1)] == want).all()):
-                raise RuntimeError("halo plan: a peer asked for a generator this rank does not hold")
-            ss = prim[idx]
+            sel = loc.sent_sel.get(q, torch.zeros(0, dtype=torch.int64, device=self.dev))
+            if want.numel() and int(want.max()) >= sel.numel():
+                raise RuntimeError("halo plan: a peer asked for a generator this rank did not send")
+            ss = prim[sel[want]]
             if ss.numel() and int(ss.min()) < 0:
                 raise RuntimeError("halo plan: requested generator has no primary slot here")
             send_slots[q] = ss.to(torch.int32)

@@ -49,9 +49,13 @@ def _worker(rank, world, port, kind, n_side, xper, yper, q):
         dist.all_reduce(cnt)
         assert int(cnt) == len(xy)
         # -- ghost exchange: all Voronoi neighbours of owned generators are present locally
-        xy_loc, lab_loc, own_loc = exchange_ghosts(plan, X[mine], lab[mine])
-        assert bool((lab_loc[1:] > lab_loc[:-1]).all())                      # global-label order, no duplicates
+        loc = exchange_ghosts(plan, X[mine], lab[mine])
+        xy_loc, lab_loc, own_loc = loc.xy, loc.lab, loc.owner
+        assert loc.n_own == int(mine.sum()) and bool((own_loc[: loc.n_own] == rank).all())   # owned first
         have = set(lab_loc.tolist())
+        assert len(have) == lab_loc.numel()                                  # no generator twice
+        for qq, (a, b) in loc.ghost_range.items():
+            assert bool((own_loc[a:b] == qq).all())
         for i in torch.nonzero(mine).squeeze(1).tolist():
             nb = edges["label"][rowptr[i]:rowptr[i + 1]]
             assert all(int(j) in have for j in nb if j > 0), (rank, i)
