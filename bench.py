@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-side", type=int, default=1024, help="lattice side of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: CG halo by ncclSend/Recv instead of peer-memory loads")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = M^2 cells per GPU (box [0,1]x[0,N]); strong = one M x M box split N ways")
     return ap.parse_args()
@@ -212,7 +213,8 @@ def run_ours(args):
         n_total = M * My
         j0, j1 = (My * rank) // world, (My * (rank + 1)) // world
         xy, k = lv.synthetic.jittered_lattice(M, args.seed, rows=(j0, j1), My=My, return_index=True)
-        sg = StripGrid(lv.Rectangle((0.0, 0.0), (1.0, My / M)), dr, xperiodic=True, yperiodic=True, device=local)
+        sg = StripGrid(lv.Rectangle((0.0, 0.0), (1.0, My / M)), dr, xperiodic=True, yperiodic=True, device=local,
+                       use_peer_memory=not args.nccl_halo)
         g = sg.grid
         sg.set_owned(xy, k + 1)
         sg.migrate()  # lattice strips and bucket-row strips agree up to a row: settle ownership once
@@ -226,7 +228,8 @@ def run_ours(args):
                  {"mass": np.where(area > 0, area, 1.0), "rho": np.ones(nl), "c2": np.full(nl, args.c0 ** 2), "P": P, "v": v}.items()}
         n = int(sg.mask_loc.sum().item())
         parallelism = (f"{world} y-strips ({args.scaling} scaling), ghost generators by torch.distributed send/recv per remesh, "
-                       f"NCCL halo + 2-scalar allreduce per CG iteration; halo (send, recv) per peer = {sg.halo_counts}")
+                       f"CG halo = {'ncclSend/Recv' if args.nccl_halo else 'NVLink peer-memory loads (CUDA IPC)'} + 2-scalar ncclAllReduce per iteration; "
+                       f"halo (send, recv) per peer = {sg.halo_counts}")
         args.no_e2e = True  # the host-buffer drop-in API is single-GPU (one Julia process, one GPU)
 
         def step_dev():

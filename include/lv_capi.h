@@ -155,6 +155,17 @@ int32_t lv_device_array(LvHandle h, int32_t which, void **ptr, int64_t *count);
 /* per peer rank: how many values this rank sends / receives and the (device) slot lists, concatenated */
 int32_t lv_halo_plan(LvHandle h, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count,
                      const int32_t *send_slots_dev, const int64_t *recv_count, const int32_t *recv_slots_dev);
+/* Peer-memory halo of the CG search direction: lv_peer_export returns the CUDA IPC handles (64 + 64 bytes) of
+ * this rank's vector and version flag; the host gathers them and gives every rank the handles of its peers
+ * (order of lv_halo_plan) plus, per ghost value, its slot in the owner's numbering.  The CG loop then pulls
+ * ghost values with NVLink loads ordered by the flags instead of pack / ncclSend / ncclRecv / unpack. */
+int32_t lv_peer_export(LvHandle h, uint8_t *out128);
+int32_t lv_peer_plan(LvHandle h, int32_t npeers, const uint8_t *handles, const int32_t *remote_slots_dev);
+/* Peer-memory allreduce of the two CG scalars: every rank exports a mailbox (CUDA IPC handle, 64 bytes), maps the
+ * mailboxes of all ranks and from then on posts / collects partial sums with NVLink stores and flags; sums are
+ * taken in rank order, so the result is deterministic and identical on every rank. */
+int32_t lv_mailbox_export(LvHandle h, uint8_t *out64);
+int32_t lv_mailbox_plan(LvHandle h, int32_t nranks, const uint8_t *handles);
 /* fill the ghost slots of a slot-ordered device vector (ncomp 1 or 2) from their owners */
 int32_t lv_halo_exchange_dev(LvHandle h, double *vec_dev, int32_t ncomp);
 

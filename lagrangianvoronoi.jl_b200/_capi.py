@@ -25,7 +25,7 @@ SYMBOLS = [
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
     "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
-    "lv_halo_plan", "lv_halo_exchange_dev",
+    "lv_halo_plan", "lv_halo_exchange_dev", "lv_peer_export", "lv_peer_plan", "lv_mailbox_export", "lv_mailbox_plan",
 ]
 
 
@@ -107,6 +107,10 @@ def load_library() -> C.CDLL:
     L.lv_device_array.argtypes = [vp, C.c_int32, C.POINTER(vp), ip]
     L.lv_halo_plan.argtypes = [vp, C.c_int32, i32p, ip, vp, ip, vp]
     L.lv_halo_exchange_dev.argtypes = [vp, vp, C.c_int32]
+    L.lv_peer_export.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.lv_peer_plan.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint8), vp]
+    L.lv_mailbox_export.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.lv_mailbox_plan.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint8)]
     L.lv_prof_enable.argtypes = [vp, C.c_int32]
     L.lv_prof_reset.argtypes = [vp]
     L.lv_prof_get.argtypes = [vp, C.c_int32, dp, ip]

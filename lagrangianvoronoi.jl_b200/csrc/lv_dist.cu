@@ -13,6 +13,7 @@
 #include "lv_internal.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstring>
 
 namespace {
 struct NcclApi {
@@ -93,13 +94,116 @@ int lv_halo_exchange(LvContext *c, double *vec, int ncomp) {
     return LV_OK;
 }
 
+// ---- peer-memory halo (NVLink loads instead of pack / ncclSend / ncclRecv / unpack) -----------------------
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void k_halo_signal(int *flag, int version) {
+    __threadfence_system(); // everything this stream wrote before is visible to the peers first
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(version) : "memory");
+}
+// one launch per peer: wait until the peer has published `version`, then gather my ghost values from its vector
+__global__ void __launch_bounds__(256) k_halo_pull(int64_t n, const int *__restrict__ recv_slots, const int *__restrict__ remote_slots,
+                                                   const double *peer_vec, const int *peer_flag, int version, double *__restrict__ vec) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_sys(peer_flag) < version) { }
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vec[recv_slots[i]] = __ldcv(peer_vec + remote_slots[i]);
+}
+
+int lv_halo_signal(LvContext *c) {
+    if (!c->comm || !c->peer_ready) return LV_OK;
+    c->pver++;
+    k_halo_signal<<<1, 1, 0, c->stream>>>(c->d_peer_flag, c->pver);
+    c->launches++;
+    return LV_OK;
+}
+
+int lv_halo_pull_p(LvContext *c, double *p) {
+    if (!c->comm) return LV_OK;
+    if (!c->peer_ready || p != c->d_vec[1]) return lv_halo_exchange(c, p, 1);
+    for (size_t k = 0; k < c->peers.size(); k++) {
+        const auto &pr = c->peers[k];
+        if (pr.nrecv == 0) continue;
+        const auto &pm = c->peer_maps[k];
+        const int nb = (int)((pr.nrecv + 255) / 256);
+        k_halo_pull<<<nb, 256, 0, c->stream>>>(pr.nrecv, c->d_recv_slots + pr.recv_off, c->d_remote_slots + pr.recv_off,
+                                               (const double *)pm.vec_base, (const int *)pm.flag_base, c->pver, p);
+        c->launches++;
+    }
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// mailbox layout per rank: [parity 2][rank 64] of {double v[2]; int flag; int pad} = 24 -> 32 bytes
+typedef LvMailSlot MailSlot;
+#define MB_MAX_RANKS LV_MB_MAX_RANKS
+
+// one block, one thread per rank: post my two partial sums into everybody's mailbox (release), wait until
+// everybody's partials for this sequence number have arrived in mine (acquire), sum them in rank order
+__global__ void k_peer_allreduce(MailSlot *const *mailboxes, int nranks, int rank, int seq, double *vals) {
+    __shared__ double s0[MB_MAX_RANKS], s1[MB_MAX_RANKS];
+    const int q = threadIdx.x;
+    const int par = seq & 1;
+    if (q < nranks) {
+        MailSlot *dst = mailboxes[q] + par * MB_MAX_RANKS + rank;
+        dst->v[0] = vals[0];
+        dst->v[1] = vals[1];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(&dst->flag), "r"(seq) : "memory");
+        MailSlot *src = mailboxes[rank] + par * MB_MAX_RANKS + q;
+        while (ld_acquire_sys(&src->flag) < seq) { }
+        s0[q] = __ldcv(&src->v[0]);
+        s1[q] = __ldcv(&src->v[1]);
+    }
+    __syncthreads();
+    if (q == 0) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nranks; k++) { a += s0[k]; b += s1[k]; }
+        vals[0] = a;
+        vals[1] = b;
+    }
+}
+
 int lv_allreduce_sum(LvContext *c, double *dev, int count) {
     if (!c->comm) return LV_OK;
+    if (c->mailbox_ready && count == 2) {
+        c->ar_seq++;
+        k_peer_allreduce<<<1, MB_MAX_RANKS, 0, c->stream>>>((MailSlot *const *)c->d_mailbox_ptrs, c->nranks, c->rank, c->ar_seq, dev);
+        c->launches++;
+        return LV_OK;
+    }
     LV_NCCL(c, g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
     return LV_OK;
 }
 
+static void close_mailboxes(LvContext *c) {
+    for (size_t q = 0; q < c->mailbox_of.size(); q++)
+        if ((int)q != c->rank && c->mailbox_of[q]) cudaIpcCloseMemHandle(c->mailbox_of[q]);
+    c->mailbox_of.clear();
+    c->mailbox_ready = false;
+}
+
+static void close_peer_maps(LvContext *c) {
+    for (auto &pm : c->peer_maps) {
+        if (pm.vec_base) cudaIpcCloseMemHandle(pm.vec_base);
+        if (pm.flag_base) cudaIpcCloseMemHandle(pm.flag_base);
+    }
+    c->peer_maps.clear();
+    c->peer_ready = false;
+}
+
 void lv_dist_destroy(LvContext *c) {
+    close_peer_maps(c);
+    close_mailboxes(c);
+    cudaFree(c->d_mailbox); c->d_mailbox = nullptr;
+    cudaFree(c->d_mailbox_ptrs); c->d_mailbox_ptrs = nullptr;
+    cudaFree(c->d_remote_slots); c->d_remote_slots = nullptr;
+    cudaFree(c->d_peer_flag); c->d_peer_flag = nullptr;
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
     cudaFree(c->d_send_slots); cudaFree(c->d_recv_slots); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
@@ -168,6 +272,105 @@ int32_t lv_halo_plan(LvHandle c, int32_t npeers, const int32_t *peer_rank, const
     }
     if (so > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_send_slots, send_slots_dev, sizeof(int) * (size_t)so, cudaMemcpyDeviceToDevice, c->stream));
     if (ro > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_recv_slots, recv_slots_dev, sizeof(int) * (size_t)ro, cudaMemcpyDeviceToDevice, c->stream));
+    return LV_OK;
+}
+
+// CUDA IPC handles of this rank's search-direction vector (64 B) and version flag (64 B); the host gathers
+// them from all ranks and hands every rank its peers' handles through lv_peer_plan
+int32_t lv_peer_export(LvHandle c, uint8_t *out128) {
+    if (!c || !out128) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(lv_pr_ensure(c));
+    if (!c->d_peer_flag) {
+        LV_CUDA(c, cudaMalloc((void **)&c->d_peer_flag, 256));
+        LV_CUDA(c, cudaMemset(c->d_peer_flag, 0, 256));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hv, hf;
+    LV_CUDA(c, cudaIpcGetMemHandle(&hv, c->d_vec[1]));
+    LV_CUDA(c, cudaIpcGetMemHandle(&hf, c->d_peer_flag));
+    memcpy(out128, &hv, 64);
+    memcpy(out128 + 64, &hf, 64);
+    return LV_OK;
+}
+
+// CUDA IPC handle (64 B) of this rank's allreduce mailbox; lv_mailbox_plan maps the mailboxes of all ranks
+int32_t lv_mailbox_export(LvHandle c, uint8_t *out64) {
+    if (!c || !out64) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_mailbox) {
+        LV_CUDA(c, cudaMalloc(&c->d_mailbox, sizeof(MailSlot) * 2 * MB_MAX_RANKS));
+        LV_CUDA(c, cudaMemset(c->d_mailbox, 0, sizeof(MailSlot) * 2 * MB_MAX_RANKS));
+    }
+    cudaIpcMemHandle_t hm;
+    LV_CUDA(c, cudaIpcGetMemHandle(&hm, c->d_mailbox));
+    memcpy(out64, &hm, 64);
+    return LV_OK;
+}
+
+int32_t lv_mailbox_plan(LvHandle c, int32_t nranks, const uint8_t *handles /* nranks x 64 */) {
+    if (!c || !c->comm || nranks != c->nranks || nranks > MB_MAX_RANKS) return lv_set_error(c, LV_EINVAL, "lv_mailbox_plan: bad arguments");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (c->mailbox_ready && !memcmp(c->mailbox_handles, handles, 64 * (size_t)nranks)) return LV_OK;
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    close_mailboxes(c);
+    c->mailbox_of.assign((size_t)nranks, nullptr);
+    for (int q = 0; q < nranks; q++) {
+        if (q == c->rank) { c->mailbox_of[q] = c->d_mailbox; continue; }
+        cudaIpcMemHandle_t hm;
+        memcpy(&hm, handles + 64 * q, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&c->mailbox_of[q], hm, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            c->mailbox_of[q] = nullptr;
+            close_mailboxes(c);
+            return lv_set_error(c, LV_ECUDA, "cudaIpcOpenMemHandle(mailbox of rank %d) failed: %s", q, cudaGetErrorString(e));
+        }
+    }
+    if (!c->d_mailbox_ptrs) LV_CUDA(c, cudaMalloc((void **)&c->d_mailbox_ptrs, sizeof(void *) * MB_MAX_RANKS));
+    LV_CUDA(c, cudaMemcpy(c->d_mailbox_ptrs, c->mailbox_of.data(), sizeof(void *) * (size_t)nranks, cudaMemcpyHostToDevice));
+    memcpy(c->mailbox_handles, handles, 64 * (size_t)nranks);
+    c->mailbox_ready = true;
+    return LV_OK;
+}
+
+// peers in the order of lv_halo_plan; handles[k] = what peer k exported; remote_slots_dev[i] = slot, in its
+// owner's numbering, of the value that lands in recv slot i (same concatenated order as recv_slots)
+int32_t lv_peer_plan(LvHandle c, int32_t npeers, const uint8_t *handles, const int32_t *remote_slots_dev) {
+    if (!c || npeers != (int32_t)c->peers.size()) return lv_set_error(c, LV_EINVAL, "lv_peer_plan: call lv_halo_plan first");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    // reopen only what changed (opening an IPC handle is expensive; the vector is reallocated rarely)
+    bool same = c->peer_maps.size() == (size_t)npeers;
+    for (int k = 0; same && k < npeers; k++)
+        same = c->peer_maps[k].rank == c->peers[k].rank && !memcmp(c->peer_maps[k].handle, handles + 128 * k, 128);
+    if (!same) {
+        close_peer_maps(c);
+        for (int k = 0; k < npeers; k++) {
+            LvContext::PeerMap pm;
+            pm.rank = c->peers[k].rank;
+            memcpy(pm.handle, handles + 128 * k, 128);
+            cudaIpcMemHandle_t hv, hf;
+            memcpy(&hv, handles + 128 * k, 64);
+            memcpy(&hf, handles + 128 * k + 64, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&pm.vec_base, hv, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pm.flag_base, hf, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                close_peer_maps(c);
+                return lv_set_error(c, LV_ECUDA, "cudaIpcOpenMemHandle(peer %d) failed: %s", pm.rank, cudaGetErrorString(e));
+            }
+            c->peer_maps.push_back(pm);
+        }
+    }
+    const int64_t ro = c->halo_recv_total;
+    if (ro > c->cap_remote) {
+        cudaFree(c->d_remote_slots);
+        c->cap_remote = ro + ro / 8 + 1024;
+        LV_CUDA(c, cudaMalloc((void **)&c->d_remote_slots, sizeof(int) * (size_t)c->cap_remote));
+    }
+    if (ro > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_remote_slots, remote_slots_dev, sizeof(int) * (size_t)ro, cudaMemcpyDeviceToDevice, c->stream));
+    c->peer_ready = true;
     return LV_OK;
 }
 

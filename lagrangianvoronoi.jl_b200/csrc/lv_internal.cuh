@@ -111,6 +111,23 @@ struct LvContext {
     int *d_send_slots = nullptr, *d_recv_slots = nullptr; // concatenated per peer
     double *d_send_buf = nullptr, *d_recv_buf = nullptr;  // 2 components per entry
     int64_t halo_send_total = 0, halo_recv_total = 0, cap_halo_send = 0, cap_halo_recv = 0;
+    // peer-memory halo of the CG search direction: ghost values are pulled straight out of the neighbours'
+    // vectors over NVLink (CUDA IPC mappings), ordered by a per-rank version flag (lv_dist.cu)
+    struct PeerMap { int rank; unsigned char handle[128]; void *vec_base = nullptr; void *flag_base = nullptr; };
+    std::vector<PeerMap> peer_maps;
+    int *d_remote_slots = nullptr; // [halo_recv_total] slot of each ghost value in its owner's vector
+    int64_t cap_remote = 0;
+    int *d_peer_flag = nullptr;    // this rank's version flag (exported to the peers)
+    int pver = 0;                  // version of the search direction last published
+    bool peer_ready = false;
+    // peer-memory allreduce of the CG scalars: every rank owns a mailbox (2 parities x nranks x {2 doubles, flag})
+    // that all other ranks write into over NVLink; sums are taken in rank order (deterministic)
+    void *d_mailbox = nullptr;             // this rank's mailbox (exported)
+    std::vector<void *> mailbox_of;        // [nranks] mapped mailboxes (own entry = d_mailbox)
+    void **d_mailbox_ptrs = nullptr;       // device copy of mailbox_of
+    unsigned char mailbox_handles[64 * 64];
+    int ar_seq = 0;                        // reductions done so far (same on every rank)
+    bool mailbox_ready = false;
     // instrumentation
     bool prof_on = false;
     LvProfSlot prof[LV_PROF_COUNT];
@@ -170,9 +187,15 @@ int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double 
 int lv_gather_to_slots(LvContext *c, const double *src_label_dev, double *dst_slot, int ncomp, double fill);
 int lv_scatter_to_labels(LvContext *c, const double *src_slot, double *dst_label_dev, int ncomp);
 
+// allreduce mailbox slot: what one rank posts into another rank's mailbox (lv_dist.cu, lv_pressure.cu)
+struct __align__(16) LvMailSlot { double v[2]; int flag; int pad[3]; };
+#define LV_MB_MAX_RANKS 64
+
 // multi-GPU (lv_dist.cu): both are no-ops when the handle has no communicator
 int lv_halo_exchange(LvContext *c, double *vec_slot, int ncomp); // fill ghost slots from their owners
 int lv_allreduce_sum(LvContext *c, double *dev_scalars, int count);
+int lv_halo_signal(LvContext *c);               // publish "my search direction is ready" (after it was written)
+int lv_halo_pull_p(LvContext *c, double *p);    // ghost slots of p from the peers' memory, or NCCL exchange as fallback
 void lv_dist_destroy(LvContext *c);
 
 // ---- device helpers shared by kernels ---------------------------------------------------------

@@ -428,9 +428,44 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_init(int nslot, const double *_
 // one block: finish reductions and update the scalars.  mode 0: init, 1: alpha, 2: beta, 3: residual check
 // stage 0: reduce the partials and update (single GPU); stage 1: reduce only, leaving the two local sums in
 // scal[SC_TMP0..1] for the NCCL allreduce; stage 2: update from the (now global) sums in scal[SC_TMP0..1].
+// stage 3 (multi-GPU with mapped mailboxes): reduce, exchange the two local sums with every rank through the
+// NVLink mailboxes (rank-ordered, deterministic sum) and update -- one launch, no NCCL in the Krylov loop.
+// The mailbox exchange always runs, also after convergence, so that all ranks keep the same sequence numbers.
+struct MailArgs { LvMailSlot *const *boxes; int nranks, rank, seq; };
 __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nblk, int nblk_max, const double *__restrict__ partial,
-                                                    double *__restrict__ scal, double rtol, double atol) {
+                                                    double *__restrict__ scal, double rtol, double atol, MailArgs mail) {
     __shared__ double sm[32];
+    __shared__ double sh[2], m0[LV_MB_MAX_RANKS], m1[LV_MB_MAX_RANKS];
+    if (stage == 3) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
+        const double t1 = block_sum(a, sm);
+        const double t2 = block_sum(b2, sm);
+        if (threadIdx.x == 0) { sh[0] = t1; sh[1] = t2; }
+        __syncthreads();
+        const int q = threadIdx.x, par = mail.seq & 1;
+        if (q < mail.nranks) {
+            LvMailSlot *dst = mail.boxes[q] + par * LV_MB_MAX_RANKS + mail.rank;
+            dst->v[0] = sh[0];
+            dst->v[1] = sh[1];
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(&dst->flag), "r"(mail.seq) : "memory");
+            LvMailSlot *src = mail.boxes[mail.rank] + par * LV_MB_MAX_RANKS + q;
+            int f;
+            do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory"); } while (f < mail.seq);
+            m0[q] = __ldcv(&src->v[0]);
+            m1[q] = __ldcv(&src->v[1]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double g1 = 0.0, g2 = 0.0;
+            for (int k = 0; k < mail.nranks; k++) { g1 += m0[k]; g2 += m1[k]; }
+            scal[SC_TMP0] = g1;
+            scal[SC_TMP1] = g2;
+        }
+        __syncthreads();
+        stage = 2; // fall through to the update from scal[SC_TMP0..1]
+    }
     if (stage != 1 && mode != 0 && mode != 3 && scal[SC_CONV] != 0.0) return;
     double s1, s2;
     if (stage != 2) {
@@ -522,10 +557,17 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     const int nb = pr_grid(c, ns);
     // finish a reduction: locally, or through a 2-scalar NCCL allreduce when the grid is decomposed
     auto finish = [&](int mode) -> int {
-        if (!c->comm) { k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol); c->launches++; return LV_OK; }
-        k_cg_scalars<<<1, 256, 0, st>>>(mode, 1, nb, NBMAX, partial, scal, rtol, atol);
+        MailArgs mail{nullptr, 1, 0, 0};
+        if (!c->comm) { k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol, mail); c->launches++; return LV_OK; }
+        if (c->mailbox_ready) {
+            mail = MailArgs{(LvMailSlot *const *)c->d_mailbox_ptrs, c->nranks, c->rank, ++c->ar_seq};
+            k_cg_scalars<<<1, 256, 0, st>>>(mode, 3, nb, NBMAX, partial, scal, rtol, atol, mail);
+            c->launches++;
+            return LV_OK;
+        }
+        k_cg_scalars<<<1, 256, 0, st>>>(mode, 1, nb, NBMAX, partial, scal, rtol, atol, mail);
         LV_TRY(lv_allreduce_sum(c, scal + SC_TMP0, 2));
-        k_cg_scalars<<<1, 256, 0, st>>>(mode, 2, nb, NBMAX, partial, scal, rtol, atol);
+        k_cg_scalars<<<1, 256, 0, st>>>(mode, 2, nb, NBMAX, partial, scal, rtol, atol, mail);
         c->launches += 2;
         return LV_OK;
     };
@@ -540,6 +582,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         LvProfScope prof(c, LV_PROF_VECOPS);
         k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
         c->launches++;
+        LV_TRY(lv_halo_signal(c)); // p = r is ready for the neighbours
         LV_TRY(finish(0));
     }
     // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
@@ -550,7 +593,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
         const int todo = itmax - done < batch ? itmax - done : batch;
         for (int it = 0; it < todo; it++) {
-            LV_TRY(lv_halo_exchange(c, p, 1)); // ghost columns of the search direction (no-op on one GPU)
+            LV_TRY(lv_halo_pull_p(c, p)); // ghost columns of the search direction, read from the neighbours' memory
             {
                 LvProfScope prof(c, LV_PROF_MATVEC);
                 k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
@@ -562,6 +605,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
             LV_TRY(finish(2));
             k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
             c->launches += 2;
+            LV_TRY(lv_halo_signal(c));
         }
         done += todo;
         LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));

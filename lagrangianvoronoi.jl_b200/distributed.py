@@ -232,8 +232,9 @@ class StripGrid:
     """A VoronoiGrid decomposed into y-strips over the ranks of a torch.distributed process group."""
 
     def __init__(self, boundary_rect: Rectangle, dr: float, h=None, r_max=None, xperiodic=False, yperiodic=False,
-                 device: int = 0, group=None):
+                 device: int = 0, group=None, use_peer_memory: bool = True):
         self.group = group
+        self.use_peer_memory = use_peer_memory  # False: NCCL send/recv for every halo (baseline path)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.grid = VoronoiGrid(boundary_rect, dr, h=h, r_max=r_max, xperiodic=xperiodic, yperiodic=yperiodic, device=device)
@@ -252,6 +253,16 @@ class StripGrid:
             dist.broadcast(idbuf, 0, group=group)
             raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
             check(self._L.lv_comm_init(g._h, self.rank, self.world, raw), g._h)
+            if use_peer_memory:  # allreduce mailboxes: every rank maps every other rank's mailbox once
+                mine = (C.c_uint8 * 64)()
+                check(self._L.lv_mailbox_export(g._h, mine), g._h)
+                hb = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+                allm = [torch.zeros(64, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+                dist.all_gather(allm, hb, group=group)
+                flat = []
+                for t in allm:
+                    flat += t.cpu().tolist()
+                check(self._L.lv_mailbox_plan(g._h, self.world, (C.c_uint8 * (64 * self.world))(*flat)), g._h)
         self.xy_own = torch.zeros((0, 2), dtype=torch.float64, device=self.dev)
         self.lab_own = torch.zeros(0, dtype=torch.int64, device=self.dev)
 
@@ -329,6 +340,25 @@ class StripGrid:
         check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(self._halo_keep[0]) if s_all.numel() else None, rc,
                              ptr(self._halo_keep[1]) if r_all.numel() else None), g._h)
         self.halo_counts = {q: (int(send_slots[q].numel()), int(recv_slots[q].numel())) for q in peers}
+        if self.use_peer_memory and npeer:
+            # peer-memory halo: tell every peer where (in my numbering) the values it receives live, and map
+            # each other's vectors with CUDA IPC so the CG loop can read them over NVLink
+            reply = exchange_variable({q: send_slots[q].to(torch.int64).unsqueeze(1) for q in peers}, self.world, self.rank,
+                                      self.dev, torch.int64, 1, self.group)
+            remote = torch.cat([reply[q].squeeze(1) if q in reply else torch.zeros(0, dtype=torch.int64, device=self.dev)
+                                for q in peers]).to(torch.int32).contiguous()
+            mine = (C.c_uint8 * 128)()
+            check(L.lv_peer_export(g._h, mine), g._h)
+            hbuf = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+            allh = [torch.zeros(128, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+            dist.all_gather(allh, hbuf, group=self.group)
+            flat = []
+            for q in peers:
+                flat += allh[q].cpu().tolist()
+            harr = (C.c_uint8 * (128 * npeer))(*flat)
+            self._remote_keep = remote
+            torch.cuda.current_stream(self.dev).synchronize()
+            check(L.lv_peer_plan(g._h, npeer, harr, ptr(remote) if remote.numel() else None), g._h)
 
     # -- results --------------------------------------------------------------------------------------
     def owned_index(self) -> torch.Tensor:
