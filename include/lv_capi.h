@@ -137,6 +137,26 @@ int32_t lv_find_pressure_dev(LvHandle h, double dt, int32_t niter, double rtol, 
 int32_t lv_pressure_solve(LvHandle h, int32_t solver, const double *b, double *x, double rtol,
                           double atol, int32_t itmax, int32_t *iters, double *relres);
 
+/* ---- device-resident time step: the callers either side of the hot path ------------ */
+/* Polygon fields of @Euler_vars (celldefs.jl:7-27) kept in HBM in label order so that a whole step! runs without
+ * PCIe round trips.  Field names: x v dv momentum (2 doubles per polygon), rho e P c2 mass energy quality mu phase
+ * (1), D (4, column-major).  Set "x" first (it fixes n); every other field defaults to zero. */
+int32_t lv_state_set(LvHandle h, const char *name, const double *host, int64_t n);
+int32_t lv_state_get(LvHandle h, const char *name, double *host);
+int32_t lv_state_ptr(LvHandle h, const char *name, void **dev_ptr, int64_t *n);
+int32_t lv_state_remesh(LvHandle h);                                   /* remesh!(grid)            voronoigrid.jl:89-108 */
+int32_t lv_step_move(LvHandle h, double dt);                           /* move!(grid, dt)          move.jl:9-33 (remeshes) */
+int32_t lv_step_eos(LvHandle h, double gamma, double p0, int32_t stiffened); /* stiffened_eos!(grid, gamma, P0) pressure.jl:64-70 /
+                                                                          ideal_eos!(grid, gamma; Pmin = p0) pressure.jl:49-55 */
+int32_t lv_step_find_pressure(LvHandle h, double dt, int32_t niter, double rtol, double atol, int32_t itmax,
+                              int32_t solver, const double *vbc_wall, int32_t *iters_out, double *relres_out);
+int32_t lv_step_pressure_step(LvHandle h, double dt);                  /* pressure_step!           pressure.jl:10-25 */
+int32_t lv_step_gravity(LvHandle h, double gx, double gy, double dt);  /* gravity_step!            pressure.jl:77-82 */
+int32_t lv_step_find_D(LvHandle h);                                    /* find_D!                  diffusion.jl:8-19 */
+int32_t lv_step_viscous_step(LvHandle h, double dt, int32_t artificial_viscosity); /* viscous_step! diffusion.jl:39-53 */
+int32_t lv_step_find_dv(LvHandle h, double dt, double alpha);          /* find_dv!                 relaxation.jl:10-25 */
+int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* relaxation_step!       relaxation.jl:36-73 (remeshes) */
+
 /* ---- multi-GPU: y-strips, one process per GPU ------------------------------ */
 /* The reference is shared-memory only; these entry points have no counterpart there.  The host
  * (lagrangianvoronoi.jl_b200/distributed.py) moves ghost generators between neighbouring strips with

@@ -192,6 +192,8 @@ int32_t lv_destroy(LvHandle c) {
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
+    for (double *v : c->st_field) if (v) cudaFree(v);
+    if (c->st_tmp) cudaFree(c->st_tmp);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->h_red) cudaFreeHost(c->h_red);
     lv_dist_destroy(c);

@@ -103,6 +103,10 @@ struct LvContext {
     double *h_red = nullptr;      // pinned
     bool assembled = false;
     int cg_hint = 0; // iterations of the previous solve (sizes the first launch batch)
+    // device-resident polygon fields in label order (lv_step.cu)
+    double *st_field[16] = {nullptr};
+    double *st_tmp = nullptr;
+    int64_t st_n = 0, st_cap = 0;
     // multi-GPU: NCCL communicator + halo plan (lv_dist.cu)
     void *comm = nullptr; // ncclComm_t
     int rank = 0, nranks = 1;

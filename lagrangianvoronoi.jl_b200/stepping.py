@@ -1,0 +1,116 @@
+"""Device-resident time stepping: the callers either side of the hot path.
+
+Same names and argument meaning as the reference's explicit operators (Julia's ``f!`` becomes ``f``); the
+polygon fields live in HBM in label order between calls, so a canonical ``step!`` (examples/gresho.jl:100-114,
+tests/taylorgreen.jl:61-71) runs without PCIe round trips:
+
+    to_device(grid)                      upload grid.x and every field
+    move(grid, dt)                       move!            move.jl:9-33        (remeshes)
+    stiffened_eos(grid, gamma, P0)       stiffened_eos!   pressure.jl:64-70
+    ideal_eos(grid, gamma, Pmin=0)       ideal_eos!       pressure.jl:49-55
+    find_pressure_resident(solver, dt)   find_pressure!   pressure.jl:215-225
+    pressure_step(grid, dt)              pressure_step!   pressure.jl:10-25
+    gravity_step(grid, g, dt)            gravity_step!    pressure.jl:77-82
+    find_D(grid)                         find_D!          diffusion.jl:8-19
+    viscous_step(grid, dt, artificial_viscosity=True)     diffusion.jl:39-53
+    find_dv(grid, dt, alpha=1.0)         find_dv!         relaxation.jl:10-25
+    relaxation_step(grid, dt, rusanov=True)               relaxation.jl:36-73 (remeshes)
+    from_device(grid)                    download x and every field (e.g. before export / postproc!)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._capi import LV_SOLVER_CG, LV_SOLVER_MINRES, check, ptr
+from .host import PressureSolver, VoronoiGrid, _FIELDS, _host_empty, _wall_velocities
+
+_STATE_FIELDS = ["v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu"]
+
+
+def state_set(grid: VoronoiGrid, name: str, arr) -> None:
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    n = grid.n
+    check(grid._L.lv_state_set(grid._h, name.encode(), ptr(a), n), grid._h)
+
+
+def state_get(grid: VoronoiGrid, name: str, out=None) -> np.ndarray:
+    nc = {"x": 2, "D": 4, "phase": 1}.get(name, _FIELDS.get(name, 1))
+    n = grid.n
+    if out is None:
+        out = _host_empty((n, nc) if nc > 1 else (n,), np.float64)
+    check(grid._L.lv_state_get(grid._h, name.encode(), ptr(out)), grid._h)
+    return out
+
+
+def to_device(grid: VoronoiGrid, remesh: bool = True) -> None:
+    """Upload the generators and every polygon field; optionally build the mesh of the resident positions."""
+    state_set(grid, "x", grid.x)
+    for name in _STATE_FIELDS:
+        state_set(grid, name, getattr(grid, name))
+    if remesh:
+        check(grid._L.lv_state_remesh(grid._h), grid._h)
+    grid._resident = True
+
+
+def from_device(grid: VoronoiGrid, mesh: bool = False) -> None:
+    """Download positions and fields into the grid's host arrays (and, on request, the edge view)."""
+    state_get(grid, "x", grid.x)
+    for name in _STATE_FIELDS:
+        state_get(grid, name, getattr(grid, name))
+    if mesh:
+        grid.rowptr, e, grid._area, grid._centroid = grid.mesh_download(grid.n)
+        grid.edges = e
+
+
+def remesh_resident(grid: VoronoiGrid) -> None:
+    check(grid._L.lv_state_remesh(grid._h), grid._h)
+
+
+def move(grid: VoronoiGrid, dt: float) -> None:
+    check(grid._L.lv_step_move(grid._h, float(dt)), grid._h)
+
+
+def stiffened_eos(grid: VoronoiGrid, gamma: float = 1.4, P0: float = 0.0) -> None:
+    check(grid._L.lv_step_eos(grid._h, float(gamma), float(P0), 1), grid._h)
+
+
+def ideal_eos(grid: VoronoiGrid, gamma: float = 1.4, Pmin: float = 0.0) -> None:
+    check(grid._L.lv_step_eos(grid._h, float(gamma), float(Pmin), 0), grid._h)
+
+
+def find_pressure_resident(solver: PressureSolver, dt: float, niter: int = 10, boundary_velocity=None) -> None:
+    g = solver.grid
+    iters = np.zeros(niter, np.int32)
+    relres = np.zeros(niter) if solver.verbose else None
+    vw = _wall_velocities(g, boundary_velocity)
+    kind = LV_SOLVER_MINRES if solver.solver == "minres" else LV_SOLVER_CG
+    check(g._L.lv_step_find_pressure(g._h, float(dt), int(niter), solver.rtol, solver.atol, int(solver.itmax), kind, ptr(vw),
+                                     iters.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     None if relres is None else relres.ctypes.data_as(C.POINTER(C.c_double))), g._h)
+    solver.iters, solver.relres = iters, relres
+
+
+def pressure_step(grid: VoronoiGrid, dt: float) -> None:
+    check(grid._L.lv_step_pressure_step(grid._h, float(dt)), grid._h)
+
+
+def gravity_step(grid: VoronoiGrid, g, dt: float) -> None:
+    check(grid._L.lv_step_gravity(grid._h, float(g[0]), float(g[1]), float(dt)), grid._h)
+
+
+def find_D(grid: VoronoiGrid) -> None:
+    check(grid._L.lv_step_find_D(grid._h), grid._h)
+
+
+def viscous_step(grid: VoronoiGrid, dt: float, artificial_viscosity: bool = True) -> None:
+    check(grid._L.lv_step_viscous_step(grid._h, float(dt), int(artificial_viscosity)), grid._h)
+
+
+def find_dv(grid: VoronoiGrid, dt: float, alpha: float = 1.0) -> None:
+    check(grid._L.lv_step_find_dv(grid._h, float(dt), float(alpha)), grid._h)
+
+
+def relaxation_step(grid: VoronoiGrid, dt: float, rusanov: bool = True) -> None:
+    check(grid._L.lv_step_relaxation_step(grid._h, float(dt), int(rusanov)), grid._h)

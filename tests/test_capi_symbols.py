@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "lv_capi.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lv_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(lv_[A-Za-z_0-9]+)\s*\(", text)))
 
 
 def test_library_builds_and_exports_every_declared_symbol(lv):

@@ -1,0 +1,125 @@
+"""GPU parity tests of the device-resident explicit sweeps against the oracle, and the
+reference's own integration test (tests/taylorgreen.jl) run end to end on the GPU path."""
+import numpy as np
+import pytest
+
+from .conftest import make_points
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["x", "v", "rho", "e", "P", "c2", "mass", "dv", "quality", "momentum", "energy"]
+
+
+def _pair(lv, oracle, kind, n_side, xper, yper, seed):
+    xy, dr, bmin, bmax = make_points(kind, n_side, seed)
+    rng = np.random.default_rng(seed)
+    n = len(xy)
+    og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=xper, yperiodic=yper)
+    og.set_points(xy); assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper)
+    g.set_points(xy)
+    v, P = lv.synthetic.taylor_green_fields(xy)
+    v = v + 0.05 * rng.standard_normal((n, 2))
+    rho = 1.0 + 0.3 * rng.random(n)
+    mass = rho * og.area()
+    e = 0.5 * (v ** 2).sum(1) + (P + 50.0) / (rho * 0.4)
+    mu = np.full(n, 1.0 / 400)
+    for name, val in (("v", v), ("rho", rho), ("mass", mass), ("e", e), ("P", P), ("mu", mu), ("c2", 100.0 + 0 * rho)):
+        og.set(name, val)
+        getattr(g, name)[...] = val
+    lv.stepping.to_device(g)
+    return g, og, dr
+
+
+def _compare(lv, g, og, names, rtol=1e-12):
+    for nm in names:
+        a = lv.stepping.state_get(g, nm)
+        b = og.get(nm)
+        scale = np.abs(b).max() + 1e-300
+        assert np.abs(a - b).max() <= rtol * scale, (nm, np.abs(a - b).max() / scale)
+
+
+@pytest.mark.parametrize("kind,n_side,xper,yper", [("jitter", 48, True, True), ("poisson", 40, False, False), ("rect2x1", 32, True, False)])
+def test_explicit_sweeps_match_oracle(lv, oracle, kind, n_side, xper, yper):
+    S = lv.stepping
+    g, og, dr = _pair(lv, oracle, kind, n_side, xper, yper, 9)
+    dt = 0.1 * dr
+    S.stiffened_eos(g, 1.4, 30.0); og.stiffened_eos(1.4, 30.0)
+    _compare(lv, g, og, ["rho", "P", "c2"])
+    S.pressure_step(g, dt); og.pressure_step(dt)
+    _compare(lv, g, og, ["v", "e"])
+    S.find_D(g); og.find_D()
+    assert np.allclose(S.state_get(g, "D"), og.get("D"), rtol=1e-12, atol=1e-12 * np.abs(og.get("D")).max())
+    S.viscous_step(g, dt, True); og.viscous_step(dt, True)
+    _compare(lv, g, og, ["v", "e"])
+    S.find_dv(g, dt, 1.0); og.find_dv(dt, 1.0)
+    _compare(lv, g, og, ["dv", "quality"])
+    S.relaxation_step(g, dt, True); assert og.relaxation_step(dt, True) == 0
+    _compare(lv, g, og, ["x", "mass", "v", "e", "momentum", "energy"])
+    S.ideal_eos(g, 1.4, 0.1); og.ideal_eos(1.4, 0.1)
+    _compare(lv, g, og, ["rho", "P", "c2"])
+    S.move(g, dt); assert og.move(dt) == 0
+    _compare(lv, g, og, ["x", "v"])
+    # the mesh after the device-side moves is still the oracle's, bit for bit
+    rowptr, edges, area, cen = g.mesh_download(g.n)
+    r0, e0 = og.mesh()
+    assert np.array_equal(rowptr, r0) and edges.tobytes() == e0.tobytes()
+
+
+def test_walls_stop_escaping_generators(lv, oracle):
+    """move! projects the velocity of cells that would leave the box and zeroes it if that fails (move.jl:9-21)."""
+    S = lv.stepping
+    g, og, dr = _pair(lv, oracle, "poisson", 32, False, False, 4)
+    x0 = og.get("x")
+    vv = 0.2 * og.get("v")
+    near = (x0[:, 0] > 1.0 - 1.5 * dr) | (x0[:, 1] < 1.5 * dr)      # cells at the right / bottom wall run into it
+    vv[near] = np.array([3.0, -2.0])
+    og.set("v", vv); S.state_set(g, "v", vv)
+    dt = 0.6 * dr
+    S.move(g, dt); assert og.move(dt) == 0
+    _compare(lv, g, og, ["x", "v"])
+    x = S.state_get(g, "x")
+    assert x.min() >= 0.0 and x.max() <= 1.0
+    v1 = S.state_get(g, "v")
+    assert (np.abs(v1[near] - np.array([3.0, -2.0])).max(1) > 0).any()   # some velocities were projected or zeroed
+
+
+def test_taylor_green_on_the_gpu(lv, oracle):
+    """The reference's only test (tests/taylorgreen.jl): N = 80, Re = 400, 80 steps of the canonical step!, thresholds
+    E_err < 1e-8, v_err < 0.01, P_err < 0.01 (:112-114) -- every operator of the step on the GPU."""
+    S = lv.stepping
+    N = 80; Re = 400.0; rho0 = 1.0; dr = 1.0 / N; dt = 0.1 * dr; c0 = 50.0; gamma = 1.4; t_end = 0.1
+    P0 = rho0 * c0 ** 2 / gamma
+    og = oracle.OracleGrid((0, 0), (1, 1), dr, xperiodic=True, yperiodic=True)
+    assert og.populate_hex() == 0                                   # seeding only (populate.jl:149-174)
+    xy = og.get("x")
+    g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), dr, xperiodic=True, yperiodic=True)
+    g.set_points(xy)
+    lv.remesh(g, edges=False)
+    area = lv.area(g).copy()
+    v, P = lv.synthetic.taylor_green_fields(xy, 0.0, Re)
+    g.v[...] = v; g.rho[...] = rho0; g.mass[...] = rho0 * area; g.P[...] = P
+    g.e[...] = 0.5 * (v ** 2).sum(1) + P / (rho0 * (gamma - 1.0)); g.mu[...] = 1.0 / Re
+    S.to_device(g)
+    solver = lv.PressureSolver(g)
+    t = 0.0; k = 0; E0 = None; errs = None
+    k_frame = max(round(t_end / (20 * dt)), 1)
+    while t < t_end:
+        k += 1
+        S.move(g, dt)
+        S.stiffened_eos(g, gamma, P0)
+        S.find_pressure_resident(solver, dt)
+        S.pressure_step(g, dt); S.find_D(g); S.viscous_step(g, dt, False); S.find_dv(g, dt)
+        S.relaxation_step(g, dt)
+        if k % k_frame == 0:
+            S.from_device(g)
+            _, _, area, _ = g.mesh_download(g.n, edges=False)
+            p_avg = (area * g.P).sum()
+            E = (g.mass * g.e).sum()
+            E0 = E if E0 is None else E0
+            ve, Pe = lv.synthetic.taylor_green_fields(g.x, t, Re)
+            errs = (E - E0, np.sqrt((area * ((g.v - ve) ** 2).sum(1)).sum()), np.sqrt((area * (g.P - p_avg - Pe) ** 2).sum()))
+        t += dt
+    assert k == 80
+    E_err, v_err, P_err = errs
+    assert E_err < 1e-8 and v_err < 0.01 and P_err < 0.01, errs
