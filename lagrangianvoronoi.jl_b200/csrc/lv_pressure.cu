@@ -11,7 +11,11 @@
 #define PR_BLOCK 256
 
 // scalars kept on the device between kernels (doubles in c->d_red[0..15])
-enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_COUNT = 16 };
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11,
+       // MINRES (Paige-Saunders, in the formulation of Krylov.jl 0.9.8 minres!) scalar state
+       MR_BETA = 16, MR_OLDB = 17, MR_DBAR = 18, MR_EPS = 19, MR_CS = 20, MR_SN = 21, MR_PHIBAR = 22, MR_GAMMA = 23, MR_PHI = 24,
+       MR_DELTA = 25, MR_ANORM2 = 26, MR_GMAX = 27, MR_GMIN = 28, MR_XENORM2 = 29, MR_ROOT = 30, MR_BETA1 = 31, MR_ERRV = 32 /* ..36 */,
+       SC_COUNT = 64 };
 
 // ---- label <-> slot permutation --------------------------------------------------------------
 template <int NC>
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
         __syncthreads();
         stage = 2; // fall through to the update from scal[SC_TMP0..1]
     }
-    if (stage != 1 && mode != 0 && mode != 3 && scal[SC_CONV] != 0.0) return;
+    if (stage != 1 && mode != 0 && mode != 3 && mode != 4 && scal[SC_CONV] != 0.0) return;
     double s1, s2;
     if (stage != 2) {
         double a = 0.0, b2 = 0.0;
@@ -494,9 +498,133 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
         scal[SC_RR] = s1;
         scal[SC_ITER] += 1.0;
         if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
-    } else {
+    } else if (mode == 3) {
         scal[SC_RES2] = s1; scal[SC_BNORM2] = s2;
+    } else if (mode == 4) { // MINRES init: beta1 = ||r0||
+        const double beta1 = sqrt(s1);
+        scal[MR_BETA1] = beta1; scal[MR_BETA] = beta1; scal[MR_OLDB] = 0.0; scal[MR_DBAR] = 0.0; scal[MR_EPS] = 0.0;
+        scal[MR_CS] = -1.0; scal[MR_SN] = 0.0; scal[MR_PHIBAR] = beta1; scal[MR_ANORM2] = 0.0; scal[MR_GMAX] = 0.0;
+        scal[MR_GMIN] = __longlong_as_double(0x7ff0000000000000ll); scal[MR_XENORM2] = 0.0;
+        for (int k = 0; k < 5; k++) scal[MR_ERRV + k] = 0.0;
+        scal[SC_TOL] = atol + rtol * beta1;
+        scal[SC_ITER] = 0.0;
+        scal[SC_CONV] = (beta1 == 0.0 || beta1 <= scal[SC_TOL]) ? 1.0 : 0.0;
+    } else if (mode == 5) { // alpha = v.y / beta ; delta = cs*dbar + sn*alpha
+        const double alpha = s1 / scal[MR_BETA];
+        scal[SC_ALPHA] = alpha;
+        scal[MR_DELTA] = scal[MR_CS] * scal[MR_DBAR] + scal[MR_SN] * alpha;
+    } else if (mode == 6) { // new beta, plane rotation
+        const double alpha = scal[SC_ALPHA], oldb = scal[MR_BETA], cs = scal[MR_CS], sn = scal[MR_SN], dbar = scal[MR_DBAR];
+        const double beta = sqrt(s1);
+        scal[MR_OLDB] = oldb; scal[MR_BETA] = beta;
+        scal[MR_ANORM2] = scal[MR_ANORM2] + alpha * alpha + oldb * oldb + beta * beta;
+        const double gbar = sn * dbar - cs * alpha;
+        scal[MR_EPS] = sn * beta;
+        scal[MR_DBAR] = -cs * beta;
+        scal[MR_ROOT] = sqrt(gbar * gbar + scal[MR_DBAR] * scal[MR_DBAR]);
+        double gamma = sqrt(gbar * gbar + beta * beta);
+        gamma = gamma > 2.220446049250313e-16 ? gamma : 2.220446049250313e-16;
+        scal[MR_GAMMA] = gamma;
+        scal[MR_CS] = gbar / gamma; scal[MR_SN] = beta / gamma;
+        scal[MR_PHI] = scal[MR_CS] * scal[MR_PHIBAR];
+        scal[MR_PHIBAR] = scal[MR_SN] * scal[MR_PHIBAR];
+    } else if (mode == 7) { // stopping tests (s1 = ||x||^2)
+        const double epsM = 2.220446049250313e-16, etol = sqrt(epsM), ctol = sqrt(epsM);
+        const int iter = (int)scal[SC_ITER] + 1;
+        scal[SC_ITER] = (double)iter;
+        const double gamma = scal[MR_GAMMA], phi = scal[MR_PHI];
+        scal[MR_ERRV + (iter % 5)] = phi;
+        double err_lbnd = 0.0;
+        if (iter >= 5) { double e2 = 0.0; for (int k = 0; k < 5; k++) e2 += scal[MR_ERRV + k] * scal[MR_ERRV + k]; err_lbnd = sqrt(e2); }
+        scal[MR_GMAX] = scal[MR_GMAX] > gamma ? scal[MR_GMAX] : gamma;
+        scal[MR_GMIN] = scal[MR_GMIN] < gamma ? scal[MR_GMIN] : gamma;
+        const double ANorm = sqrt(scal[MR_ANORM2]), xNorm = sqrt(s1), Acond = scal[MR_GMAX] / scal[MR_GMIN], rNorm = scal[MR_PHIBAR];
+        const double test1 = rNorm / (ANorm * xNorm), test2 = scal[MR_ROOT] / ANorm, tol = scal[SC_TOL];
+        scal[MR_XENORM2] = scal[MR_XENORM2] + phi * phi;
+        const bool ill = (1.0 + 1.0 / Acond <= 1.0) || (1.0 / Acond <= ctol);
+        const bool solved = (1.0 + test2 <= 1.0) || (test2 <= tol) || (1.0 + test1 <= 1.0) || (test1 <= tol) ||
+                            (iter >= 5 && err_lbnd <= etol * sqrt(scal[MR_XENORM2])) || (rNorm + 1.0 <= 1.0) || (rNorm <= tol);
+        scal[SC_RR] = rNorm * rNorm;
+        if (solved || ill || !(rNorm == rNorm)) scal[SC_CONV] = 1.0;
     }
+}
+
+// ---- MINRES vector kernels (vectors: r1, r2 (= v, M = I), y, w1, w2, x; see lv_pr_solve_minres) ----------------
+__global__ void __launch_bounds__(PR_BLOCK) k_mr_init(int nslot, const double *__restrict__ b, const double *__restrict__ Ax0, double *__restrict__ r1,
+                                                      double *__restrict__ r2, double *__restrict__ w1, double *__restrict__ w2,
+                                                      double *__restrict__ x, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    double rr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double ri = b[i] - Ax0[i]; // warm start: r1 = b - A*x0
+        r1[i] = ri; r2[i] = ri; w1[i] = 0.0; w2[i] = 0.0; x[i] = 0.0;
+        rr += ri * ri;
+    }
+    const double s = block_sum(rr, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// y = y/beta - (beta/oldbeta) r1 (iter >= 2); partial(v.y)
+__global__ void __launch_bounds__(PR_BLOCK) k_mr_a(int nslot, int iter, const double *__restrict__ scal, const double *__restrict__ v,
+                                                   const double *__restrict__ r1, double *__restrict__ y, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    if (scal[SC_CONV] != 0.0) return;
+    const double beta = scal[MR_BETA], oldb = scal[MR_OLDB];
+    const double ib = 1.0 / beta, c1 = iter >= 2 ? -beta / oldb : 0.0;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        double yi = y[i] * ib;
+        if (iter >= 2) yi += c1 * r1[i];
+        y[i] = yi;
+        acc += v[i] * yi;
+    }
+    const double s = block_sum(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// y -= (alpha/beta) r2; w update; r1 = r2; r2 = y; partial(r2.r2)
+__global__ void __launch_bounds__(PR_BLOCK) k_mr_b(int nslot, int iter, const double *__restrict__ scal, double *__restrict__ r1,
+                                                   double *__restrict__ r2, const double *__restrict__ y, double *__restrict__ wa /* w1 */,
+                                                   double *__restrict__ wb /* w2 */, double *__restrict__ partial) {
+    __shared__ double sm[32];
+    if (scal[SC_CONV] != 0.0) return;
+    const double beta = scal[MR_BETA], alpha = scal[SC_ALPHA], eps_old = scal[MR_EPS], delta = scal[MR_DELTA];
+    const double c2 = -alpha / beta, ib = 1.0 / beta;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double vi = r2[i];
+        const double yi = y[i] + c2 * vi;
+        if (iter == 1) wb[i] = wb[i] + ib * vi;
+        else {
+            double w = wa[i];
+            if (iter >= 3) w = w * (-eps_old);
+            w = w + (-delta) * wb[i];
+            wa[i] = w + ib * vi;
+        }
+        r1[i] = vi;
+        r2[i] = yi;
+        acc += yi * yi;
+    }
+    const double s = block_sum(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// w /= gamma; x += phi w; partial(x.x)
+__global__ void __launch_bounds__(PR_BLOCK) k_mr_c(int nslot, const double *__restrict__ scal, double *__restrict__ w, double *__restrict__ x,
+                                                   double *__restrict__ partial) {
+    __shared__ double sm[32];
+    if (scal[SC_CONV] != 0.0) return;
+    const double ig = 1.0 / scal[MR_GAMMA], phi = scal[MR_PHI];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double wi = w[i] * ig;
+        w[i] = wi;
+        const double xi = x[i] + phi * wi;
+        x[i] = xi;
+        acc += xi * xi;
+    }
+    const double s = block_sum(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(PR_BLOCK) k_axpy1(int nslot, const double *__restrict__ x, double *__restrict__ y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) y[i] += x[i];
 }
 
 // x += alpha p ; r -= alpha Ap ; partial(r.r)
@@ -545,7 +673,8 @@ __global__ void __launch_bounds__(PR_BLOCK) k_resid(int nslot, const double *__r
 // A x = b with x = c->d_P (initial guess in, solution out), b = c->d_b
 int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres) {
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
-    if (solver != LV_SOLVER_CG) return lv_set_error(c, LV_EINVAL, "solver %d not available (LV_SOLVER_CG only)", solver);
+    if (solver != LV_SOLVER_CG && solver != LV_SOLVER_MINRES) return lv_set_error(c, LV_EINVAL, "unknown solver %d", solver);
+    const bool minres = solver == LV_SOLVER_MINRES;
     const int ns = (int)c->nslot;
     if (iters) *iters = 0;
     if (relres) *relres = 0.0;
@@ -578,39 +707,83 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     };
     LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
     matvec_plain(x, Ap);
-    {
-        LvProfScope prof(c, LV_PROF_VECOPS);
-        k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
-        c->launches++;
-        LV_TRY(lv_halo_signal(c)); // p = r is ready for the neighbours
-        LV_TRY(finish(0));
-    }
-    // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
-    // flag is set, so the host only has to look at the flag between batches.  The first batch is
-    // sized by the previous solve (the fixed-point passes of find_pressure! need similar counts).
-    int done = 0;
-    while (done < itmax) {
-        int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
-        const int todo = itmax - done < batch ? itmax - done : batch;
-        for (int it = 0; it < todo; it++) {
-            LV_TRY(lv_halo_pull_p(c, p)); // ghost columns of the search direction, read from the neighbours' memory
-            {
-                LvProfScope prof(c, LV_PROF_MATVEC);
-                k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
-                c->launches++;
-            }
+    if (!minres) {
+        {
             LvProfScope prof(c, LV_PROF_VECOPS);
-            LV_TRY(finish(1));
-            k_cg_update_xr<<<nb, PR_BLOCK, 0, st>>>(ns, scal, p, Ap, x, r, partial);
-            LV_TRY(finish(2));
-            k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
-            c->launches += 2;
-            LV_TRY(lv_halo_signal(c));
+            k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
+            c->launches++;
+            LV_TRY(lv_halo_signal(c)); // p = r is ready for the neighbours
+            LV_TRY(finish(0));
         }
-        done += todo;
-        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
-        LV_CUDA(c, cudaStreamSynchronize(st));
-        if (c->h_red[SC_CONV] != 0.0) break;
+        // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
+        // flag is set, so the host only has to look at the flag between batches.  The first batch is
+        // sized by the previous solve (the fixed-point passes of find_pressure! need similar counts).
+        int done = 0;
+        while (done < itmax) {
+            int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
+            const int todo = itmax - done < batch ? itmax - done : batch;
+            for (int it = 0; it < todo; it++) {
+                LV_TRY(lv_halo_pull_p(c, p)); // ghost columns of the search direction, read from the neighbours' memory
+                {
+                    LvProfScope prof(c, LV_PROF_MATVEC);
+                    k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
+                    c->launches++;
+                }
+                LvProfScope prof(c, LV_PROF_VECOPS);
+                LV_TRY(finish(1));
+                k_cg_update_xr<<<nb, PR_BLOCK, 0, st>>>(ns, scal, p, Ap, x, r, partial);
+                LV_TRY(finish(2));
+                k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
+                c->launches += 2;
+                LV_TRY(lv_halo_signal(c));
+            }
+            done += todo;
+            LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+            LV_CUDA(c, cudaStreamSynchronize(st));
+            if (c->h_red[SC_CONV] != 0.0) break;
+        }
+    } else {
+        // MINRES (the reference's Krylov method, pressure.jl:219), warm-started: solve A dx = b - A x0, x = x0 + dx.
+        // v = r2 lives in d_vec[1], the vector the neighbours map, so the peer-memory halo serves it as well.
+        double *r1 = c->d_vec[0], *r2 = c->d_vec[1], *y = c->d_vec[2], *w1 = c->d_vec[3], *w2 = c->d_vec[4], *dx = c->d_vec[5];
+        {
+            LvProfScope prof(c, LV_PROF_VECOPS);
+            k_mr_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap /* = A x0, same buffer as y */, r1, r2, w1, w2, dx, partial);
+            c->launches++;
+            LV_TRY(lv_halo_signal(c));
+            LV_TRY(finish(4));
+        }
+        int done = 0;
+        while (done < itmax) {
+            int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
+            const int todo = itmax - done < batch ? itmax - done : batch;
+            for (int it = 0; it < todo; it++) {
+                const int iter = done + it + 1;
+                LV_TRY(lv_halo_pull_p(c, r2));
+                {
+                    LvProfScope prof(c, LV_PROF_MATVEC);
+                    k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, r2, y, partial, scal);
+                    c->launches++;
+                }
+                LvProfScope prof(c, LV_PROF_VECOPS);
+                k_mr_a<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r2, r1, y, partial);
+                LV_TRY(finish(5));
+                double *wa = (iter == 1) ? w1 : w1, *wb = w2; // iter == 1 works on w2 in place, later iterations build w in w1
+                k_mr_b<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r1, r2, y, wa, wb, partial);
+                LV_TRY(lv_halo_signal(c)); // r2 (the next v) is final
+                LV_TRY(finish(6));
+                k_mr_c<<<nb, PR_BLOCK, 0, st>>>(ns, scal, iter == 1 ? w2 : w1, dx, partial);
+                LV_TRY(finish(7));
+                c->launches += 3;
+                if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
+            }
+            done += todo;
+            LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+            LV_CUDA(c, cudaStreamSynchronize(st));
+            if (c->h_red[SC_CONV] != 0.0) break;
+        }
+        k_axpy1<<<nb, PR_BLOCK, 0, st>>>(ns, dx, x); // x = x0 + dx
+        c->launches++;
     }
     LV_CUDA(c, cudaGetLastError());
     c->cg_hint = (int)c->h_red[SC_ITER];
