@@ -156,6 +156,7 @@ int32_t lv_step_find_D(LvHandle h);                                    /* find_D
 int32_t lv_step_viscous_step(LvHandle h, double dt, int32_t artificial_viscosity); /* viscous_step! diffusion.jl:39-53 */
 int32_t lv_step_find_dv(LvHandle h, double dt, double alpha);          /* find_dv!                 relaxation.jl:10-25 */
 int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* relaxation_step!       relaxation.jl:36-73 (remeshes) */
+int32_t lv_step_lloyd(LvHandle h, int32_t niter);                      /* populate_lloyd! loop     populate.jl:132-145 */
 
 /* ---- multi-GPU: y-strips, one process per GPU ------------------------------ */
 /* The reference is shared-memory only; these entry points have no counterpart there.  The host

@@ -11,6 +11,8 @@ from .host import (Rectangle, VoronoiGrid, PressureSolver, remesh, find_pressure
 from . import synthetic  # noqa: F401
 from . import distributed  # noqa: F401
 from . import stepping  # noqa: F401
+from . import populate  # noqa: F401
+from . import io  # noqa: F401
 
 __all__ = ["LvError", "build_library", "library_path", "load_library", "EDGE_DTYPE", "Rectangle", "VoronoiGrid",
-           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "synthetic", "distributed", "stepping"]
+           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "synthetic", "distributed", "stepping", "populate", "io"]

@@ -301,6 +301,13 @@ __global__ void __launch_bounds__(ST_BLOCK) k_relax_apply(StepView S, double dt,
     S.x[i] = make_double2(x.x + dt * dv.x, x.y + dt * dv.y);
 }
 
+__global__ void __launch_bounds__(ST_BLOCK) k_to_centroid(StepView S) { // p.x = centroid(p)  populate.jl:136-138
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const int s = S.prim[i];
+    if (s >= 0) S.x[i] = S.cen[s];
+}
+
 // ---- state management --------------------------------------------------------------------------------------------
 static const char *const FIELD_NAMES[] = {"x", "v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu", "phase", "D"};
 static const int FIELD_NC[] = {2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 4};
@@ -489,6 +496,19 @@ int32_t lv_step_relaxation_step(LvHandle c, double dt, int32_t rusanov) { // rel
         c->launches += 2;
     }
     LV_CUDA(c, cudaGetLastError());
+    return state_remesh(c);
+}
+
+// populate_lloyd!'s relaxation loop (populate.jl:132-145): niter x (remesh!; p.x = centroid(p)), then a final remesh!
+int32_t lv_step_lloyd(LvHandle c, int32_t niter) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->st_field[0]) return lv_set_error(c, LV_EINVAL, "no device state");
+    for (int it = 0; it < niter; it++) {
+        LV_TRY(state_remesh(c));
+        StepView S = make_view(c);
+        if (S.n > 0) { k_to_centroid<<<GRID(S.n)>>>(S); c->launches++; }
+    }
     return state_remesh(c);
 }
 
