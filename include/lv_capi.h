@@ -156,6 +156,10 @@ int32_t lv_step_find_D(LvHandle h);                                    /* find_D
 int32_t lv_step_viscous_step(LvHandle h, double dt, int32_t artificial_viscosity); /* viscous_step! diffusion.jl:39-53 */
 int32_t lv_step_find_dv(LvHandle h, double dt, double alpha);          /* find_dv!                 relaxation.jl:10-25 */
 int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* relaxation_step!       relaxation.jl:36-73 (remeshes) */
+/* multiphase_projection!(solver) (relaxation.jl:179-206; MultiphaseProjector mul! :91-123, refresh! :162-177).  Reference
+ * settings: quality_threshold 0.25, atol = rtol = 1e-4, itmax 200; *solved = 0 where the reference would @warn */
+int32_t lv_step_multiphase_projection(LvHandle h, double quality_threshold, double rtol, double atol, int32_t itmax,
+                                      int32_t *iters, int32_t *solved);
 int32_t lv_step_lloyd(LvHandle h, int32_t niter);                      /* populate_lloyd! loop     populate.jl:132-145 */
 
 /* ---- multi-GPU: y-strips, one process per GPU ------------------------------ */

@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../../include/lv_capi.h"
 
 #define LV_IMAGE_BIT 0x80000000u // set in ent_label[] for periodic-image slots
@@ -188,6 +189,8 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall);
 int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres);
 int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver,
                         const double *vbc_wall, int32_t *iters_out, double *relres_out);
+int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *, double *)> &apply, const double *b, double *x,
+                    double rtol, double atol, int itmax, int *iters, int *solved);
 int lv_gather_to_slots(LvContext *c, const double *src_label_dev, double *dst_slot, int ncomp, double fill);
 int lv_scatter_to_labels(LvContext *c, const double *src_slot, double *dst_label_dev, int ncomp);
 

@@ -802,6 +802,51 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     return LV_OK;
 }
 
+// Cold-started MINRES on an arbitrary symmetric operator given as a callback (single GPU): used by the multiphase
+// projector (relaxation.jl:182), which is matrix free and lives in label order.  Same iteration and stopping rules as
+// the pressure MINRES above (Krylov.jl minres!).  x receives the solution; *solved = 0 when itmax was hit.
+int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *, double *)> &apply, const double *b, double *x,
+                    double rtol, double atol, int itmax, int *iters, int *solved) {
+    if (iters) *iters = 0;
+    if (solved) *solved = 1;
+    if (n == 0) return LV_OK;
+    cudaStream_t st = c->stream;
+    double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
+    const int NBMAX = 4096;
+    const int nb = pr_grid(c, n);
+    const MailArgs nomail{nullptr, 1, 0, 0};
+    double *r1 = c->d_vec[0], *r2 = c->d_vec[1], *y = c->d_vec[2], *w1 = c->d_vec[3], *w2 = c->d_vec[4];
+    LV_CUDA(c, cudaMemsetAsync(y, 0, sizeof(double) * (size_t)n, st)); // A*x0 with x0 = 0
+    k_mr_init<<<nb, PR_BLOCK, 0, st>>>(n, b, y, r1, r2, w1, w2, x, partial);
+    k_cg_scalars<<<1, 256, 0, st>>>(4, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+    c->launches += 2;
+    int done = 0;
+    bool conv = false;
+    while (done < itmax) {
+        const int todo = itmax - done < 16 ? itmax - done : 16;
+        for (int it = 0; it < todo; it++) {
+            const int iter = done + it + 1;
+            LV_TRY(apply(r2, y));
+            k_mr_a<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r2, r1, y, partial);
+            k_cg_scalars<<<1, 256, 0, st>>>(5, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            k_mr_b<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r1, r2, y, w1, w2, partial);
+            k_cg_scalars<<<1, 256, 0, st>>>(6, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            k_mr_c<<<nb, PR_BLOCK, 0, st>>>(n, scal, iter == 1 ? w2 : w1, x, partial);
+            k_cg_scalars<<<1, 256, 0, st>>>(7, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            c->launches += 6;
+            if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
+        }
+        done += todo;
+        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        LV_CUDA(c, cudaStreamSynchronize(st));
+        if (c->h_red[SC_CONV] != 0.0) { conv = true; break; }
+    }
+    LV_CUDA(c, cudaGetLastError());
+    if (iters) *iters = (int)c->h_red[SC_ITER];
+    if (solved) *solved = conv ? 1 : 0;
+    return LV_OK;
+}
+
 // find_pressure!  pressure.jl:215-225
 int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver, const double *vbc_wall,
                         int32_t *iters_out, double *relres_out) {

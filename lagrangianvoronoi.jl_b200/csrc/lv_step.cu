@@ -308,6 +308,68 @@ __global__ void __launch_bounds__(ST_BLOCK) k_to_centroid(StepView S) { // p.x =
     if (s >= 0) S.x[i] = S.cen[s];
 }
 
+// ---- multiphase projector  relaxation.jl:75-206 -------------------------------------------------------------------
+// mul!(res, A::MultiphaseProjector, x)  relaxation.jl:91-123: two sweeps, only edges between different phases contribute
+__global__ void __launch_bounds__(ST_BLOCK) k_mp_tmp(StepView S, const double *__restrict__ xv, double2 *__restrict__ tmp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const int s0 = S.prim[i];
+    const double2 x = S.x[i];
+    const double ph = S.phase[i], xi = xv[i];
+    double tx = 0.0, ty = 0.0;
+    FOR_NEIGHBORS(S, i, x) {
+        if (ph != S.phase[q]) {
+            const double lrr = lr_ratio(make_double2(x.x - y.x, x.y - y.y), ea, eb);
+            const double mx = 0.5 * (ea.x + eb.x), my = 0.5 * (ea.y + eb.y);
+            const double sc = lrr * (xi - xv[q]);
+            tx -= sc * (mx - x.x);
+            ty -= sc * (my - x.y);
+        }
+    }
+    const double A = s0 >= 0 ? S.area[s0] : 1.0;
+    tmp[i] = make_double2(tx / A, ty / A);
+}
+// second sweep of mul! (tvec = tmp_vec) and, with tvec = dv and sign = +1, the right-hand side of refresh! (:162-177)
+__global__ void __launch_bounds__(ST_BLOCK) k_mp_apply(StepView S, const double2 *__restrict__ tvec, double *__restrict__ res) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const double2 x = S.x[i], ti = tvec[i];
+    const double ph = S.phase[i];
+    double r = 0.0;
+    FOR_NEIGHBORS(S, i, x) {
+        if (ph != S.phase[q]) {
+            const double lrr = lr_ratio(make_double2(x.x - y.x, x.y - y.y), ea, eb);
+            const double mx = 0.5 * (ea.x + eb.x), my = 0.5 * (ea.y + eb.y);
+            const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);
+            const double2 tj = tvec[q];
+            const double a = (ti.x - tj.x) * (mx - zx) + (ti.y - tj.y) * (my - zy);
+            const double b = (ti.x + tj.x) * (x.x - y.x) + (ti.y + tj.y) * (x.y - y.y);
+            r -= lrr * (a - 0.5 * b);
+        }
+    }
+    res[i] = r;
+}
+// p.dv += lr_ratio*(res_i - res_j)*(m - p.x)/area(p) over interface edges, cells of poor quality skipped (:191-203)
+__global__ void __launch_bounds__(ST_BLOCK) k_mp_update(StepView S, const double *__restrict__ res, double quality_threshold, double2 *__restrict__ dv_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const int s0 = S.prim[i];
+    const double2 x = S.x[i];
+    double2 dv = S.dv[i];
+    const double ph = S.phase[i], ri = res[i];
+    if (!(S.quality[i] < quality_threshold) && s0 >= 0) {
+        const double A = S.area[s0];
+        FOR_NEIGHBORS(S, i, x) {
+            if (ph != S.phase[q]) {
+                const double mx = 0.5 * (ea.x + eb.x), my = 0.5 * (ea.y + eb.y);
+                const double sc = lr_ratio(make_double2(x.x - y.x, x.y - y.y), ea, eb) * (ri - res[q]);
+                dv = make_double2(dv.x + (sc * (mx - x.x)) / A, dv.y + (sc * (my - x.y)) / A);
+            }
+        }
+    }
+    dv_out[i] = dv;
+}
+
 // ---- state management --------------------------------------------------------------------------------------------
 static const char *const FIELD_NAMES[] = {"x", "v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu", "phase", "D"};
 static const int FIELD_NC[] = {2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 4};
@@ -510,6 +572,39 @@ int32_t lv_step_lloyd(LvHandle c, int32_t niter) {
         if (S.n > 0) { k_to_centroid<<<GRID(S.n)>>>(S); c->launches++; }
     }
     return state_remesh(c);
+}
+
+// multiphase_projection!(solver)  relaxation.jl:179-206: MINRES (atol = rtol = 1e-4, itmax = 200 in the reference) on the
+// matrix-free projector, then the correction of dv.  *solved = 0 reproduces the reference's @warn (it carries on).
+int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, double rtol, double atol, int32_t itmax, int32_t *iters,
+                                      int32_t *solved) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(need_mesh(c));
+    if (c->comm) return lv_set_error(c, LV_EINVAL, "the multiphase projector is single-GPU in this build");
+    LV_TRY(lv_pr_ensure(c));
+    StepView S = make_view(c);
+    const int n = (int)S.n;
+    if (n == 0) return LV_OK;
+    double *b = c->d_vec[6], *sol = c->d_vec[5];
+    double2 *tmp = (double2 *)c->st_tmp;
+    k_mp_apply<<<GRID(S.n)>>>(S, S.dv, b); // refresh!: b_i = -sum lrr (dot(dv_i - dv_j, m-z) - 0.5 dot(dv_i + dv_j, x-y))
+    c->launches++;
+    auto apply = [&](const double *in, double *out) -> int {
+        k_mp_tmp<<<GRID(S.n)>>>(S, in, tmp);
+        k_mp_apply<<<GRID(S.n)>>>(S, tmp, out);
+        c->launches += 2;
+        return LV_OK;
+    };
+    int it = 0, ok = 1;
+    LV_TRY(lv_minres_apply(c, n, apply, b, sol, rtol, atol, itmax, &it, &ok));
+    if (iters) *iters = it;
+    if (solved) *solved = ok;
+    k_mp_update<<<GRID(S.n)>>>(S, sol, quality_threshold, tmp);
+    LV_CUDA(c, cudaMemcpyAsync(S.dv, tmp, sizeof(double2) * (size_t)S.n, cudaMemcpyDeviceToDevice, c->stream));
+    c->launches++;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
 }
 
 // find_pressure!(solver, dt, niter; boundary_velocity) on the resident state  pressure.jl:215-225

@@ -29,7 +29,7 @@ BDARY_UP, BDARY_RIGHT, BDARY_DOWN, BDARY_LEFT = -1, -2, -3, -4  # polygon.jl:4-7
 
 # per-polygon fields of @Euler_vars (celldefs.jl:7-27): name -> components
 _FIELDS = {"rho": 1, "v": 2, "e": 1, "P": 1, "c2": 1, "dv": 2, "mass": 1, "momentum": 2, "energy": 1, "quality": 1,
-           "mu": 1}
+           "mu": 1, "phase": 1}
 
 
 def _host_empty(shape, dtype):

@@ -26,7 +26,7 @@ import numpy as np
 from ._capi import LV_SOLVER_CG, LV_SOLVER_MINRES, check, ptr
 from .host import PressureSolver, VoronoiGrid, _FIELDS, _host_empty, _wall_velocities
 
-_STATE_FIELDS = ["v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu"]
+_STATE_FIELDS = ["v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu", "phase"]
 
 
 def state_set(grid: VoronoiGrid, name: str, arr) -> None:
@@ -114,3 +114,14 @@ def find_dv(grid: VoronoiGrid, dt: float, alpha: float = 1.0) -> None:
 
 def relaxation_step(grid: VoronoiGrid, dt: float, rusanov: bool = True) -> None:
     check(grid._L.lv_step_relaxation_step(grid._h, float(dt), int(rusanov)), grid._h)
+
+
+def multiphase_projection(grid: VoronoiGrid, quality_threshold: float = 0.25, rtol: float = 1e-4, atol: float = 1e-4, itmax: int = 200):
+    """multiphase_projection!(solver)  relaxation.jl:179-206 (MultiphaseSolver defaults).  Returns (iterations, solved)."""
+    it, ok = C.c_int32(), C.c_int32()
+    check(grid._L.lv_step_multiphase_projection(grid._h, float(quality_threshold), float(rtol), float(atol), int(itmax),
+                                                C.byref(it), C.byref(ok)), grid._h)
+    if not ok.value:
+        import warnings
+        warnings.warn("multiphase projector did not converge within tolerance")  # relaxation.jl:184-187
+    return it.value, bool(ok.value)

@@ -725,16 +725,23 @@ static void vec_fill(int64_t n, double a, double *x) {
  * (third-party, un-vendored: Manifest.toml:465-469; call site pressure.jl:219).  Restated
  * from the published algorithm -- iterate-level parity UNPINNED.  M = I, lambda = 0,
  * window = 5, etol = sqrt(eps), conlim = 1/sqrt(eps). */
+typedef void (*lvo_matvec_fn)(const lvo_grid *g, const double *x, double *y);
+static int minres_core(const lvo_grid *g, lvo_matvec_fn matvec, int64_t n, const double *b, double *x0, double rtol, double atol,
+                       int itmax, int warm_start, int *solved_out);
 int lvo_minres(const lvo_grid *g, const double *b, double *x0, double rtol, double atol, int itmax, int warm_start) {
-    int64_t n = g->A_n;
+    return minres_core(g, lvo_pressure_matvec, g->A_n, b, x0, rtol, atol, itmax, warm_start, NULL);
+}
+static int minres_core(const lvo_grid *g, lvo_matvec_fn matvec, int64_t n, const double *b, double *x0, double rtol, double atol,
+                       int itmax, int warm_start, int *solved_out) {
     const double epsM = 2.220446049250313e-16;
     const double etol = sqrt(epsM), ctol = sqrt(epsM); /* conlim = 1/sqrt(eps) -> ctol = 1/conlim */
     enum { WINDOW = 5 };
     double *r1 = (double *)malloc(sizeof(double) * (size_t)n * 7);
     double *r2 = r1 + n, *v = r2 + n, *yv = v + n, *w1 = yv + n, *w2 = w1 + n, *x = w2 + n;
     double err_vec[WINDOW] = {0, 0, 0, 0, 0};
+    if (solved_out) *solved_out = 1;
     if (warm_start) { /* r1 = b - A*dx */
-        lvo_pressure_matvec(g, x0, r1);
+        matvec(g, x0, r1);
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; i++) r1[i] = b[i] - r1[i];
     } else vec_copy(n, b, r1);
@@ -760,7 +767,7 @@ int lvo_minres(const lvo_grid *g, const double *b, double *x0, double rtol, doub
     double *w = w2;
     while (!(solved || tired || ill_cond)) {
         iter += 1;
-        lvo_pressure_matvec(g, v, yv);
+        matvec(g, v, yv);
         vec_scal(n, 1.0 / beta, yv);
         if (iter >= 2) vec_axpy(n, -beta / oldbeta, r1, yv);
         double alpha = vec_dot(n, v, yv) / beta;
@@ -829,6 +836,7 @@ int lvo_minres(const lvo_grid *g, const double *b, double *x0, double rtol, doub
     }
     if (warm_start) vec_axpy(n, 1.0, x0, x); /* x += dx */
     vec_copy(n, x, x0);
+    if (solved_out) *solved_out = solved || ill_cond;
     free(r1);
     return iter;
 }
@@ -1119,4 +1127,84 @@ int lvo_relaxation_step(lvo_grid *g, double dt, int rusanov) { /* relaxation.jl:
         p->x = V(p->x.x + dt * p->dv.x, p->x.y + dt * p->dv.y);
     }
     return lvo_remesh(g);
+}
+
+/* ------------------------------------------------------------------ relaxation.jl:75-206 (multiphase projector) */
+static void mp_pass2(const lvo_grid *g, const vec2 *t, double *res) { /* second sweep of mul! (:107-121) and refresh! (:162-177) */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < g->n; i++) {
+        const poly_t *p = g->polygons[i];
+        double r = 0.0;
+        FOR_NEIGHBORS(g, p, q, e, y) {
+            if (p->phase != q->phase) {
+                double lrr = lr_ratio(vsub(p->x, y), e);
+                vec2 m = midpoint_e(e), z = midpoint_v(p->x, y);
+                int64_t j = e.label - 1;
+                r -= lrr * (vdot(vsub(t[i], t[j]), vsub(m, z)) - 0.5 * vdot(vadd(t[i], t[j]), vsub(p->x, y)));
+            }
+        }
+        res[i] = r;
+    }
+}
+static vec2 *g_mp_tmp = NULL; /* tmp_vec of the MultiphaseProjector (:83) */
+static void mp_matvec(const lvo_grid *g, const double *x, double *res) { /* relaxation.jl:91-123 */
+    vec2 *tmp = g_mp_tmp;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < g->n; i++) {
+        const poly_t *p = g->polygons[i];
+        vec2 t = V(0.0, 0.0);
+        FOR_NEIGHBORS(g, p, q, e, y) {
+            if (p->phase != q->phase) {
+                double lrr = lr_ratio(vsub(p->x, y), e);
+                vec2 m = midpoint_e(e);
+                int64_t j = e.label - 1;
+                double s = lrr * (x[i] - x[j]);
+                vec2 d = vsub(m, p->x);
+                t = vsub(t, V(s * d.x, s * d.y));
+            }
+        }
+        double A = poly_area(p);
+        tmp[i] = V(t.x / A, t.y / A);
+    }
+    mp_pass2(g, tmp, res);
+}
+int lvo_multiphase_projection(lvo_grid *g, double quality_threshold, double rtol, double atol, int itmax, int *iters, int *solved) {
+    int64_t n = g->n;
+    double *b = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    double *res = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    vec2 *dv = (vec2 *)malloc(sizeof(vec2) * (size_t)(n > 0 ? n : 1));
+    g_mp_tmp = (vec2 *)malloc(sizeof(vec2) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) dv[i] = g->polygons[i]->dv;
+    mp_pass2(g, dv, b); /* refresh!  :162-177 */
+    int ok = 1;
+    int it = minres_core(g, mp_matvec, n, b, res, rtol, atol, itmax, 0, &ok); /* :182 */
+    if (iters) *iters = it;
+    if (solved) *solved = ok;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) { /* :191-203 */
+        poly_t *p = g->polygons[i];
+        if (p->quality < quality_threshold) continue;
+        double A = poly_area(p);
+        vec2 d = p->dv;
+        FOR_NEIGHBORS(g, p, q, e, y) {
+            if (p->phase != q->phase) {
+                int64_t j = e.label - 1;
+                vec2 m = midpoint_e(e);
+                double s = lr_ratio(vsub(p->x, y), e) * (res[i] - res[j]);
+                vec2 w = vsub(m, p->x);
+                d = V(d.x + (s * w.x) / A, d.y + (s * w.y) / A);
+            }
+        }
+        dv[i] = d;
+    }
+    for (int64_t i = 0; i < n; i++) g->polygons[i]->dv = dv[i];
+    free(b); free(res); free(dv); free(g_mp_tmp); g_mp_tmp = NULL;
+    return LVO_OK;
+}
+void lvo_gravity_step(lvo_grid *g, double gx, double gy, double dt) { /* pressure.jl:77-82 */
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < g->n; i++) {
+        poly_t *p = g->polygons[i];
+        p->v = V(p->v.x + dt * gx, p->v.y + dt * gy);
+    }
 }

@@ -92,6 +92,10 @@ void lvo_viscous_step(lvo_grid *g, double dt, int artificial_viscosity); /* diff
 void lvo_find_dv(lvo_grid *g, double dt, double alpha);           /* relaxation.jl:10-25 */
 int lvo_relaxation_step(lvo_grid *g, double dt, int rusanov);     /* relaxation.jl:36-73 */
 
+/* relaxation.jl:75-206 multiphase projector: MINRES (cold start) + correction of dv */
+int lvo_multiphase_projection(lvo_grid *g, double quality_threshold, double rtol, double atol, int itmax, int *iters, int *solved);
+void lvo_gravity_step(lvo_grid *g, double gx, double gy, double dt); /* pressure.jl:77-82 */
+
 void lvo_set_threads(int nthreads);
 int lvo_get_threads(void);
 

@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.lvo_viscous_step.argtypes = [vp, C.c_double, C.c_int]
         L.lvo_find_dv.argtypes = [vp, C.c_double, C.c_double]
         L.lvo_relaxation_step.argtypes = [vp, C.c_double, C.c_int]
+        L.lvo_multiphase_projection.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.lvo_gravity_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         L.lvo_set_threads.argtypes = [C.c_int]
         L.lvo_get_threads.restype = C.c_int
         _lib = L
@@ -258,3 +260,12 @@ class OracleGrid:
 
     def relaxation_step(self, dt, rusanov=True) -> int:
         return int(lib().lvo_relaxation_step(self._g, float(dt), int(rusanov)))
+
+    def multiphase_projection(self, quality_threshold=0.25, rtol=1e-4, atol=1e-4, itmax=200):
+        it, ok = C.c_int(), C.c_int()
+        st = lib().lvo_multiphase_projection(self._g, float(quality_threshold), float(rtol), float(atol), int(itmax), C.byref(it), C.byref(ok))
+        assert st == 0
+        return it.value, bool(ok.value)
+
+    def gravity_step(self, g, dt):
+        lib().lvo_gravity_step(self._g, float(g[0]), float(g[1]), float(dt))

@@ -123,3 +123,76 @@ def test_taylor_green_on_the_gpu(lv, oracle):
     assert k == 80
     E_err, v_err, P_err = errs
     assert E_err < 1e-8 and v_err < 0.01 and P_err < 0.01, errs
+
+
+def _two_phase(lv, oracle, n_side=40):
+    """A Rayleigh-Taylor style set-up (examples/rayleightaylor.jl:55-62): heavy fluid above a wavy interface, walls in y."""
+    xy, dr, bmin, bmax = make_points("jitter", n_side, 2)
+    n = len(xy)
+    og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=True, yperiodic=False)
+    og.set_points(xy); assert og.remesh() == 0
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=True, yperiodic=False)
+    g.set_points(xy)
+    up = xy[:, 1] > 0.5 + 0.05 * np.cos(2 * np.pi * xy[:, 0])
+    phase = np.where(up, 0.0, 1.0)
+    rho = np.where(up, 1.8, 1.0)
+    area = og.area()
+    v = np.zeros((n, 2)); P = 10.0 - rho * 0.5 * xy[:, 1]
+    e = 0.5 * (v ** 2).sum(1) + P / (rho * 0.4)
+    for name, val in (("phase", phase), ("rho", rho), ("mass", rho * area), ("v", v), ("P", P), ("e", e), ("mu", 1e-3 + 0 * rho)):
+        og.set(name, val)
+        getattr(g, name)[...] = val
+    lv.stepping.to_device(g)
+    return g, og, dr
+
+
+def test_multiphase_projection_matches_oracle(lv, oracle):
+    """multiphase_projection! (relaxation.jl:179-206): same MINRES on the same matrix-free projector on both sides."""
+    S = lv.stepping
+    g, og, dr = _two_phase(lv, oracle)
+    rng = np.random.default_rng(1)
+    dv = 0.05 * rng.standard_normal((g.n, 2))
+    q = 0.1 + 0.9 * rng.random(g.n)                                   # some cells below the 0.25 quality threshold
+    for nm, val in (("dv", dv), ("quality", q)):
+        og.set(nm, val); S.state_set(g, nm, val)
+    it, ok = S.multiphase_projection(g)                                 # reference settings: 1e-4, 1e-4, 200
+    it0, ok0 = og.multiphase_projection()
+    assert abs(it - it0) <= 2 and ok == ok0
+    a, b = S.state_get(g, "dv"), og.get("dv")
+    assert np.abs(a - b).max() <= 1e-3 * np.abs(b).max()               # both stop at the loose reference tolerance (1e-4)
+    assert np.abs(b - dv).max() > 1e-3                                  # the projection did change dv at the interface
+    low = q < 0.25
+    assert np.array_equal(a[low], dv[low])                              # poor cells are left alone (relaxation.jl:194-196)
+    # tight tolerances: converged projections agree closely
+    for nm, val in (("dv", dv),):
+        og.set(nm, val); S.state_set(g, nm, val)
+    it1, _ = S.multiphase_projection(g, rtol=1e-11, atol=1e-11, itmax=5000)
+    it2, _ = og.multiphase_projection(rtol=1e-11, atol=1e-11, itmax=5000)
+    a, b = S.state_get(g, "dv"), og.get("dv")
+    err = np.abs(a - b).max() / np.abs(b).max()
+    print("multiphase tight:", it1, it2, err)
+    # the projector is singular (rows of cells away from the interface vanish); Krylov's MINRES then stops on its
+    # conditioning / forward-error estimates, both sides alike, a few digits short of the requested tolerance
+    assert abs(it1 - it2) <= 3 and err <= 1e-6
+
+
+def test_rayleigh_taylor_steps_match_oracle(lv, oracle):
+    """The step! of examples/rayleightaylor.jl:90-102 (gravity, multiphase projector) for a few steps, GPU vs oracle."""
+    S = lv.stepping
+    g, og, dr = _two_phase(lv, oracle, 32)
+    dt = 0.05 * dr
+    solver = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    for _ in range(3):
+        S.move(g, dt); assert og.move(dt) == 0
+        S.gravity_step(g, (0.0, -1.0), dt); og.gravity_step((0.0, -1.0), dt)
+        S.ideal_eos(g, 1.4, 0.0); og.ideal_eos(1.4, 0.0)
+        S.find_pressure_resident(solver, dt); og.find_pressure(dt, 10, rtol=1e-12, atol=0.0, itmax=20000, solver="cg")
+        S.pressure_step(g, dt); og.pressure_step(dt)
+        S.find_D(g); og.find_D()
+        S.viscous_step(g, dt); og.viscous_step(dt)
+        S.find_dv(g, dt); og.find_dv(dt)
+        S.multiphase_projection(g, rtol=1e-11, atol=1e-11, itmax=5000); og.multiphase_projection(rtol=1e-11, atol=1e-11, itmax=5000)
+        S.relaxation_step(g, dt); assert og.relaxation_step(dt) == 0
+    for nm in ("x", "v", "e", "mass"):
+        a, b = S.state_get(g, nm), og.get(nm)
+        assert np.abs(a - b).max() <= 1e-7 * np.abs(b).max(), nm
