@@ -232,11 +232,19 @@ def run_ours(args):
                        f"halo (send, recv) per peer = {sg.halo_counts}")
         args.no_e2e = True  # the host-buffer drop-in API is single-GPU (one Julia process, one GPU)
 
+        phase_ev = []
+
         def step_dev():
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(stream)
             sg.remesh()
             sg.remesh()
+            ev[1].record(stream)
             solver.upload_fields(f_dev["mass"], f_dev["rho"], f_dev["c2"], f_dev["P"], f_dev["v"], device=True)
+            ev[2].record(stream)
             iters, _ = solver.find_pressure_dev(dt, args.niter)
+            ev[3].record(stream)
+            phase_ev.append(ev)
             return int(iters.sum())
 
     def step_e2e():
@@ -269,6 +277,11 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     launches = g.launch_count() - l0
     prof = {k: g.prof_get(k) for k in ("cells", "clip", "assemble", "matvec", "vecops")}
+    wall_phases = None
+    if world > 1:
+        last = phase_ev[-args.steps:]
+        wall_phases = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in last) / args.steps
+                       for k, nm in enumerate(("remesh_x2_incl_ghost_exchange", "field_upload", "find_pressure"))}
     g.prof_enable(False)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -326,7 +339,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (no flush needed)", "krylov_iters_per_step": iters_total // args.steps},
         "submetrics": {"remesh_mcells_s": 2 * n_total * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
                        "cg_mcell_iters_s": n_total * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
-                       "s_per_step": ms_max / args.steps / 1e3,
+                       "s_per_step": ms_max / args.steps / 1e3, "wall_phase_ms_per_step_rank0": wall_phases,
                        "phase_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()},
                                                  host_and_exchange=(ms_max - sum(v[0] for v in prof.values())) / args.steps)},
         "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
