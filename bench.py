@@ -248,10 +248,14 @@ def run_ours(args):
             return int(iters.sum())
 
     def step_e2e():
+        # host buffers in, host buffers out: positions / fields go up, rowptr + edges + areas + centroids + P come back.
+        # The edge view is downloaded lazily (second stream) so that it overlaps the pressure solve; the step ends
+        # only when every byte is in host memory.
         g.P[...] = P
-        lv.remesh(g)
-        lv.remesh(g)
+        lv.remesh(g, lazy=True)
+        lv.remesh(g, lazy=True)
         lv.find_pressure(solver, dt, args.niter)
+        lv.wait_edges(g)
         return int(solver.iters.sum())
 
     def barrier():

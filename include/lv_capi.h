@@ -90,6 +90,11 @@ int32_t lv_remesh_dev(LvHandle h, int64_t n, const double *xy_dev);
 int32_t lv_mesh_nnz(LvHandle h, int64_t *nnz); /* synchronises */
 int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area,
                          double *centroid);
+/* Lazy edge view: after lv_set_async_edges(h, 1), lv_remesh / lv_mesh_download return once rowptr, areas and centroids
+ * are on the host and copy the 40-byte edge records on a second stream, overlapping whatever runs next (typically
+ * find_pressure!); the host must call lv_mesh_wait before it reads the edge buffer.  The buffer should be pinned. */
+int32_t lv_set_async_edges(LvHandle h, int32_t on);
+int32_t lv_mesh_wait(LvHandle h);
 /* which kernel produced the current mesh: level 0/1 = linked-slot kernel (12/16 slots), 2/3/4 =
  * edge-list kernel (16/32/128 edges); anomalies = remeshes replayed by the edge-list kernel because
  * the linked-slot kernel met a degenerate configuration (results are identical either way) */

@@ -7,7 +7,7 @@ fallback: every compute call goes to the CUDA library and fails loudly without i
 """
 from ._capi import LvError, build_library, library_path, load_library, EDGE_DTYPE  # noqa: F401
 from .host import (Rectangle, VoronoiGrid, PressureSolver, remesh, find_pressure, area, centroid,  # noqa: F401
-                   neighbors_csr, mul)
+                   neighbors_csr, mul, wait_edges)
 from . import synthetic  # noqa: F401
 from . import distributed  # noqa: F401
 from . import stepping  # noqa: F401
@@ -15,4 +15,4 @@ from . import populate  # noqa: F401
 from . import io  # noqa: F401
 
 __all__ = ["LvError", "build_library", "library_path", "load_library", "EDGE_DTYPE", "Rectangle", "VoronoiGrid",
-           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "synthetic", "distributed", "stepping", "populate", "io"]
+           "PressureSolver", "remesh", "find_pressure", "area", "centroid", "neighbors_csr", "mul", "wait_edges", "synthetic", "distributed", "stepping", "populate", "io"]

@@ -47,6 +47,25 @@ int lv_ensure(LvContext *c, void **ptr, int64_t *cap, int64_t need, size_t elt) 
     return LV_OK;
 }
 
+__global__ void k_publish_flags(const int *flags, const int *extra, int *host) {
+    const int t = threadIdx.x;
+    if (t < 8) host[t] = flags[t];
+    if (t == 8 && extra) host[8] = *extra;
+    __threadfence_system();
+}
+int lv_publish_flags(LvContext *c, const int *extra) {
+    if (c->flags_mapped) {
+        k_publish_flags<<<1, 32, 0, c->stream>>>(c->d_flags, extra, c->h_flags);
+        c->launches++;
+        LV_CUDA(c, cudaGetLastError());
+    } else {
+        if (extra) LV_CUDA(c, cudaMemcpyAsync(c->h_flags + 8, extra, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LV_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
 static cudaEvent_t prof_event(LvContext *c) {
     if (!c->prof_free.empty()) { cudaEvent_t e = c->prof_free.back(); c->prof_free.pop_back(); return e; }
     cudaEvent_t e = nullptr;
@@ -126,6 +145,7 @@ int32_t lv_create(const LvGridDesc *d, int32_t device, LvHandle *out) {
         return LV_ECUDA;
     }
     c->dr = dr; c->h = h; c->r_max = r_max;
+    { const char *fm = getenv("LV_FLAG_MODE"); c->flags_mapped = !(fm && !strcmp(fm, "memcpy")); }
     const int xp = d->xperiodic != 0, yp = d->yperiodic != 0;
     for (int k = 0; k < 2; k++) { c->bmin[k] = d->bmin[k]; c->bmax[k] = d->bmax[k]; }
     // cropping_rect  voronoigrid.jl:29-30 (same association as the source)
@@ -170,8 +190,8 @@ int32_t lv_create(const LvGridDesc *d, int32_t device, LvHandle *out) {
         if ((st = lv_alloc(c, (void **)&c->d_cell_cnt, sizeof(int) * (size_t)(c->ncell + 2))) != LV_OK) break;
         if ((st = lv_alloc(c, (void **)&c->d_cell_start, sizeof(int) * (size_t)(c->ncell + 2))) != LV_OK) break;
         if ((st = lv_alloc(c, (void **)&c->d_flags, sizeof(int) * 8)) != LV_OK) break;
-        if (cudaMallocHost((void **)&c->h_flags, sizeof(int) * 16) != cudaSuccess) { st = LV_ECUDA; break; }
-        if (cudaMallocHost((void **)&c->h_red, sizeof(double) * 64) != cudaSuccess) { st = LV_ECUDA; break; }
+        if (cudaHostAlloc((void **)&c->h_flags, sizeof(int) * 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { st = LV_ECUDA; break; }
+        if (cudaHostAlloc((void **)&c->h_red, sizeof(double) * 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { st = LV_ECUDA; break; }
     } while (0);
     if (st != LV_OK) {
         if (g_create_error.empty() || st == LV_ECUDA)
@@ -189,7 +209,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
                     c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
-                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage};
+                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1]};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
     for (double *v : c->st_field) if (v) cudaFree(v);
@@ -201,6 +221,9 @@ int32_t lv_destroy(LvHandle c) {
     for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_conv_done) cudaEventDestroy(c->ev_conv_done);
+    for (int k = 0; k < 2; k++) if (c->ev_stage_done[k]) cudaEventDestroy(c->ev_stage_done[k]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     free(c->h_path);
     delete c;
@@ -360,8 +383,16 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
     size_t off_cen = off_area + sizeof(double) * (size_t)n;
     size_t off_e = (off_cen + sizeof(double2) * (size_t)n + 15) & ~(size_t)15;
     size_t total = off_e + (edges ? sizeof(LvEdge) * (size_t)nnz : 0) + 64;
-    LV_TRY(lv_ensure(c, &c->d_stage, &c->cap_stage, (int64_t)total, 1)); // grow-only: no cudaMalloc/cudaFree per remesh
-    char *base = (char *)c->d_stage;
+    // two staging buffers alternate in the lazy mode, so that the background copy of one edge view overlaps the next
+    // remesh AND its conversion; a buffer is reused only after the copy that read it has finished
+    const int sb = c->async_edges ? (c->stage_cur ^= 1) : 0;
+    if (c->stage_pending[sb]) {
+        if ((int64_t)total > c->cap_stage_buf[sb]) { LV_CUDA(c, cudaEventSynchronize(c->ev_stage_done[sb])); }
+        else LV_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_stage_done[sb], 0));
+        c->stage_pending[sb] = false;
+    }
+    LV_TRY(lv_ensure(c, &c->d_stage_buf[sb], &c->cap_stage_buf[sb], (int64_t)total, 1)); // grow-only: no cudaMalloc/cudaFree per remesh
+    char *base = (char *)c->d_stage_buf[sb];
     int *deg = (int *)(base + off_deg), *rl = (int *)(base + off_rl);
     long long *r64 = (long long *)(base + off_r64);
     double *area_l = (double *)(base + off_area);
@@ -381,7 +412,17 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
         if (e == cudaSuccess && rowptr) e = cudaMemcpyAsync(rowptr, r64, sizeof(long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess && area) e = cudaMemcpyAsync(area, area_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess && centroid) e = cudaMemcpyAsync(centroid, cen_l, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && edges) e = cudaMemcpyAsync(edges, e_l, sizeof(LvEdge) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && edges) {
+            if (c->async_edges) {
+                // the 40 B/edge view is the bulk of the device->host traffic: copy it on a second stream so that it
+                // overlaps whatever the caller runs next (lv_mesh_wait orders the host against it)
+                e = cudaEventRecord(c->ev_conv_done, c->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_conv_done, 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(edges, e_l, sizeof(LvEdge) * (size_t)nnz, cudaMemcpyDeviceToHost, c->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(c->ev_stage_done[sb], c->copy_stream);
+                c->stage_pending[sb] = (e == cudaSuccess);
+            } else e = cudaMemcpyAsync(edges, e_l, sizeof(LvEdge) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "mesh download failed: %s", cudaGetErrorString(e));
     } while (0);
@@ -390,6 +431,33 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
 }
 
 extern "C" {
+
+extern "C" int32_t lv_mesh_wait(LvHandle c);
+// lazy edge view: with on != 0 lv_remesh / lv_mesh_download return as soon as rowptr, areas and centroids are on the
+// host and stream the edge records in the background; lv_mesh_wait blocks until they have landed
+int32_t lv_set_async_edges(LvHandle c, int32_t on) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (on && !c->copy_stream) {
+        LV_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_conv_done, cudaEventDisableTiming));
+        LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_done[0], cudaEventDisableTiming));
+        LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_done[1], cudaEventDisableTiming));
+    }
+    if (!on) LV_TRY(lv_mesh_wait(c));
+    c->async_edges = on != 0;
+    return LV_OK;
+}
+int32_t lv_mesh_wait(LvHandle c) {
+    if (!c) return LV_EINVAL;
+    for (int k = 0; k < 2; k++)
+        if (c->stage_pending[k]) {
+            LV_CUDA(c, cudaSetDevice(c->device));
+            LV_CUDA(c, cudaEventSynchronize(c->ev_stage_done[k]));
+            c->stage_pending[k] = false;
+        }
+    return LV_OK;
+}
 
 int32_t lv_mesh_download(LvHandle c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
     if (!c) return LV_EINVAL;

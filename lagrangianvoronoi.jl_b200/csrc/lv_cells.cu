@@ -252,9 +252,7 @@ int lv_cells_build(LvContext *c) {
     LV_TRY(lv_exclusive_scan_i32(c, c->d_cell_cnt, c->d_cell_start, ncell_ext));
     // slot count is needed on the host to size the slot-indexed buffers
     int nslot = 0;
-    LV_CUDA(c, cudaMemcpyAsync(c->h_flags + 8, c->d_cell_start + ncell_ext, sizeof(int), cudaMemcpyDeviceToHost, st));
-    LV_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, st));
-    LV_CUDA(c, cudaStreamSynchronize(st));
+    LV_TRY(lv_publish_flags(c, c->d_cell_start + ncell_ext));
     nslot = c->h_flags[8];
     if (c->h_flags[LVF_NAN]) return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf");
     c->nslot = nslot;

@@ -319,8 +319,7 @@ int lv_clip_run(LvContext *c) {
             else LV_TRY((launch_clip<128, 32>(c, a)));
         }
         c->clip_last_level = level;
-        LV_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
-        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        LV_TRY(lv_publish_flags(c, nullptr));
         if (nslot == 0) { c->nnz = 0; return LV_OK; }
         if (c->h_flags[LVF_NAN]) return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf");
         if (c->h_flags[LVF_DESTROYED]) return lv_set_error(c, LV_EDESTROYED, "The Voronoi Mesh has been destroyed.");

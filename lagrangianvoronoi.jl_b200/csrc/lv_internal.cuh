@@ -83,8 +83,13 @@ struct LvContext {
     // scratch for scans / label-order staging
     void *d_scratch = nullptr;
     int64_t cap_scratch = 0;
-    void *d_stage = nullptr; // label-order staging of the mesh for the device->host copy
-    int64_t cap_stage = 0;
+    void *d_stage_buf[2] = {nullptr, nullptr}; // label-order staging of the mesh for the device->host copy
+    int64_t cap_stage_buf[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr; // background device->host copy of the edge view (lv_set_async_edges)
+    cudaEvent_t ev_conv_done = nullptr, ev_stage_done[2] = {nullptr, nullptr};
+    bool async_edges = false, stage_pending[2] = {false, false};
+    int stage_cur = 0;
+    bool flags_mapped = true; // status words via mapped pinned memory (default) or cudaMemcpyAsync (LV_FLAG_MODE=memcpy)
     // pressure (slot order)
     bool pr_valid = false;
     int64_t pr_cap = 0;
@@ -146,6 +151,11 @@ struct LvContext {
 };
 
 enum LvFlag { LVF_DESTROYED = 0, LVF_NAN = 1, LVF_OVERFLOW = 2, LVF_TICKET = 3, LVF_NNZ = 4, LVF_CONV = 5 };
+
+// Device status words reach the host through mapped pinned memory (a 1-block kernel stores them, the host reads them
+// after a stream synchronise) instead of a device->host memcpy: small reads must not queue behind a multi-GB
+// background copy of the edge view on the same copy engine (lv_set_async_edges).
+int lv_publish_flags(LvContext *c, const int *extra_dev_int /* nullable: lands in h_flags[8] */);
 
 // ---- error helpers -------------------------------------------------------------------------
 int lv_set_error(LvContext *c, int code, const char *fmt, ...);

@@ -549,6 +549,17 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
     }
 }
 
+// What the host looks at between batches (CONV, ITER, RES2, BNORM2) goes to mapped pinned memory with one tiny kernel
+// per batch -- not a device->host memcpy, which would queue behind a background copy of the edge view, and not a
+// store from every scalar kernel, whose system-scope fence would stall behind that copy's PCIe traffic.
+__global__ void k_publish_scalars(const double *__restrict__ scal, double *host) {
+    if (threadIdx.x == 0) {
+        host[SC_CONV] = scal[SC_CONV]; host[SC_ITER] = scal[SC_ITER];
+        host[SC_RES2] = scal[SC_RES2]; host[SC_BNORM2] = scal[SC_BNORM2];
+        __threadfence_system();
+    }
+}
+
 // ---- MINRES vector kernels (vectors: r1, r2 (= v, M = I), y, w1, w2, x; see lv_pr_solve_minres) ----------------
 __global__ void __launch_bounds__(PR_BLOCK) k_mr_init(int nslot, const double *__restrict__ b, const double *__restrict__ Ax0, double *__restrict__ r1,
                                                       double *__restrict__ r2, double *__restrict__ w1, double *__restrict__ w2,
@@ -738,7 +749,8 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 LV_TRY(lv_halo_signal(c));
             }
             done += todo;
-            LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+            if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
+            else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
             LV_CUDA(c, cudaStreamSynchronize(st));
             if (c->h_red[SC_CONV] != 0.0) break;
         }
@@ -778,7 +790,8 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
             }
             done += todo;
-            LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+            if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
+            else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
             LV_CUDA(c, cudaStreamSynchronize(st));
             if (c->h_red[SC_CONV] != 0.0) break;
         }
@@ -794,7 +807,8 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         k_resid<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, partial, NBMAX);
         c->launches++;
         LV_TRY(finish(3));
-        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
+        else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
         LV_CUDA(c, cudaStreamSynchronize(st));
         const double bn = c->h_red[SC_BNORM2], rn = c->h_red[SC_RES2];
         *relres = bn > 0.0 ? sqrt(rn / bn) : sqrt(rn);
@@ -837,7 +851,8 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
             if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
         }
         done += todo;
-        LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
+        else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
         LV_CUDA(c, cudaStreamSynchronize(st));
         if (c->h_red[SC_CONV] != 0.0) { conv = true; break; }
     }

@@ -470,8 +470,7 @@ int32_t lv_step_move(LvHandle c, double dt) { // move!(grid, dt)  move.jl:9-21
     StepView S = make_view(c);
     LV_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream));
     if (S.n > 0) { k_move<<<GRID(S.n)>>>(S, dt, c->bmin[0], c->bmin[1], c->bmax[0], c->bmax[1], c->d_flags); c->launches++; }
-    LV_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_flags, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
-    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    LV_TRY(lv_publish_flags(c, nullptr));
     if (c->h_flags[LVF_NAN]) return lv_set_error(c, LV_ENAN, "Velocity field invalidated.");
     return state_remesh(c);
 }

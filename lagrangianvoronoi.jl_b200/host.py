@@ -198,8 +198,16 @@ class VoronoiGrid:
         return rowptr, e, ar, ce
 
 
-def remesh(grid: VoronoiGrid, edges: bool = True) -> None:
+def wait_edges(grid: VoronoiGrid) -> None:
+    """Block until the edge view of the last lazy remesh has landed in ``grid.edges``."""
+    check(grid._L.lv_mesh_wait(grid._h), grid._h)
+
+
+def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
     """remesh!(grid)  voronoigrid.jl:89-108.
+
+    ``lazy=True`` returns once ``rowptr``, areas and centroids are back and lets the edge records (40 B each, the bulk
+    of the traffic) arrive in the background; call ``wait_edges(grid)`` before reading ``grid.edges``.
 
     Gathers ``grid.x``, runs the cell-list build and the clipping kernel on the GPU and leaves
     ``grid.rowptr`` / ``grid.edges`` (the flat ``p.edges`` view), areas and centroids on the host.
@@ -217,6 +225,9 @@ def remesh(grid: VoronoiGrid, edges: bool = True) -> None:
                           ptr(grid._centroid)), grid._h)
         grid.edges = None
         return
+    if bool(lazy) != getattr(grid, "_lazy_edges", False):
+        check(L.lv_set_async_edges(grid._h, int(bool(lazy))), grid._h)
+        grid._lazy_edges = bool(lazy)
     buf = getattr(grid, "_edge_buf", None)
     if buf is None or buf.shape[0] < 6 * n + 64:  # grow-only pinned buffer: page-locking GBs per call would dominate
         grid._edge_buf = _host_empty((7 * n + 64,), EDGE_DTYPE)

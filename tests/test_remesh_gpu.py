@@ -165,3 +165,20 @@ def test_set_rects_like_piston(lv, oracle):
     lv.remesh(g)
     _assert_mesh_equal(g, og, lv)
     assert abs(lv.area(g).sum() - 0.8) < 1e-12
+
+
+def test_lazy_edge_download_is_identical(lv):
+    """lv_set_async_edges: the edge view arrives on a second stream; after wait_edges it is the same bytes."""
+    xy, dr, bmin, bmax = make_points("jitter", 200, 4)
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=True, yperiodic=True)
+    g.set_points(xy)
+    lv.remesh(g)
+    ref = (g.rowptr.copy(), g.edges.copy())
+    g.edges[...] = 0
+    for _ in range(3):                                      # back-to-back lazy remeshes reuse the staging buffer safely
+        lv.remesh(g, lazy=True)
+    assert np.array_equal(g.rowptr, ref[0])                 # rowptr, area, centroid are synchronous
+    lv.wait_edges(g)
+    assert g.edges.tobytes() == ref[1].tobytes()
+    lv.remesh(g)                                            # back to the synchronous mode
+    assert g.edges.tobytes() == ref[1].tobytes()
