@@ -196,6 +196,8 @@ int32_t lv_peer_plan(LvHandle h, int32_t npeers, const uint8_t *handles, const i
  * taken in rank order, so the result is deterministic and identical on every rank. */
 int32_t lv_mailbox_export(LvHandle h, uint8_t *out64);
 int32_t lv_mailbox_plan(LvHandle h, int32_t nranks, const uint8_t *handles);
+/* back to ncclSend/Recv halos and ncclAllReduce dots (every rank must call it when any rank failed to map a peer) */
+int32_t lv_peer_disable(LvHandle h);
 /* fill the ghost slots of a slot-ordered device vector (ncomp 1 or 2) from their owners */
 int32_t lv_halo_exchange_dev(LvHandle h, double *vec_dev, int32_t ncomp);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
     "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
-    "lv_halo_plan", "lv_halo_exchange_dev", "lv_peer_export", "lv_peer_plan", "lv_mailbox_export", "lv_mailbox_plan",
+    "lv_halo_plan", "lv_halo_exchange_dev", "lv_peer_export", "lv_peer_plan", "lv_mailbox_export", "lv_mailbox_plan", "lv_peer_disable",
     "lv_state_set", "lv_state_get", "lv_state_ptr", "lv_state_remesh", "lv_step_move", "lv_step_eos", "lv_step_find_pressure",
     "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection",
 ]
@@ -115,6 +115,7 @@ def load_library() -> C.CDLL:
     L.lv_peer_plan.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint8), vp]
     L.lv_mailbox_export.argtypes = [vp, C.POINTER(C.c_uint8)]
     L.lv_mailbox_plan.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint8)]
+    L.lv_peer_disable.argtypes = [vp]
     L.lv_state_set.argtypes = [vp, C.c_char_p, vp, C.c_int64]
     L.lv_state_get.argtypes = [vp, C.c_char_p, vp]
     L.lv_state_ptr.argtypes = [vp, C.c_char_p, C.POINTER(vp), ip]

@@ -498,11 +498,8 @@ int32_t lv_mesh_faces(LvHandle c, double *length, double *midpoint, int64_t cap)
     if (cap < nnz) return lv_set_error(c, LV_ECAPACITY, "face buffer too small");
     if (nnz == 0) return LV_OK;
     // label-order edges first, then lengths / midpoints of those records
-    size_t bytes = sizeof(LvEdge) * (size_t)nnz + sizeof(double) * 3 * (size_t)nnz + 256;
     (void)n;
-    std::vector<LvEdge> tmp; // host staging keeps this rarely used call simple
-    tmp.resize((size_t)nnz);
-    (void)bytes;
+    std::vector<LvEdge> tmp((size_t)nnz); // host staging keeps this rarely used call simple
     LV_TRY(lv_mesh_to_labels(c, nullptr, tmp.data(), nnz, nullptr, nullptr));
     for (int64_t k = 0; k < nnz; k++) {
         const LvEdge &e = tmp[(size_t)k];

@@ -253,11 +253,7 @@ __global__ void __launch_bounds__(BLOCK) k_clip(ClipArgs a) {
 template <int MAXE, int BLOCK>
 static int launch_clip(LvContext *c, const ClipArgs &a) {
     const size_t smem = (size_t)MAXE * BLOCK * (sizeof(double2) * 2 + sizeof(int)) + sizeof(LvPathNode) * (size_t)c->gp.npath;
-    static bool configured = false;
-    if (!configured) {
-        LV_CUDA(c, cudaFuncSetAttribute(k_clip<MAXE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    LV_CUDA(c, cudaFuncSetAttribute(k_clip<MAXE, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (int)((c->nslot + BLOCK - 1) / BLOCK);
     if (ntiles == 0) return LV_OK;
     k_clip<MAXE, BLOCK><<<ntiles, BLOCK, smem, c->stream>>>(a);

@@ -374,6 +374,14 @@ int32_t lv_peer_plan(LvHandle c, int32_t npeers, const uint8_t *handles, const i
     return LV_OK;
 }
 
+// fall back to the NCCL halo / allreduce (used when a rank could not map a peer: all ranks must switch together)
+int32_t lv_peer_disable(LvHandle c) {
+    if (!c) return LV_EINVAL;
+    c->peer_ready = false;
+    c->mailbox_ready = false;
+    return LV_OK;
+}
+
 // exchange a caller's slot-ordered device vector (tests; the solver calls lv_halo_exchange directly)
 int32_t lv_halo_exchange_dev(LvHandle c, double *vec_dev, int32_t ncomp) {
     if (!c || !vec_dev || (ncomp != 1 && ncomp != 2)) return LV_EINVAL;

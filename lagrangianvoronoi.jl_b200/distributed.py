@@ -262,9 +262,21 @@ class StripGrid:
                 flat = []
                 for t in allm:
                     flat += t.cpu().tolist()
-                check(self._L.lv_mailbox_plan(g._h, self.world, (C.c_uint8 * (64 * self.world))(*flat)), g._h)
+                st = self._L.lv_mailbox_plan(g._h, self.world, (C.c_uint8 * (64 * self.world))(*flat))
+                self._agree_on_peer_memory(st == 0)
         self.xy_own = torch.zeros((0, 2), dtype=torch.float64, device=self.dev)
         self.lab_own = torch.zeros(0, dtype=torch.int64, device=self.dev)
+
+    def _agree_on_peer_memory(self, ok: bool) -> None:
+        """CUDA IPC mapping can be refused (container policy).  All ranks switch to the NCCL path together."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if self.rank == 0:
+                import warnings
+                warnings.warn("peer-memory halo unavailable (cudaIpcOpenMemHandle failed on some rank): using NCCL send/recv")
+            self.use_peer_memory = False
+            check(self._L.lv_peer_disable(self.grid._h), self.grid._h)
 
     # -- generators -----------------------------------------------------------------------------------
     def set_owned(self, xy, labels) -> None:
@@ -358,7 +370,8 @@ class StripGrid:
             harr = (C.c_uint8 * (128 * npeer))(*flat)
             self._remote_keep = remote
             torch.cuda.current_stream(self.dev).synchronize()
-            check(L.lv_peer_plan(g._h, npeer, harr, ptr(remote) if remote.numel() else None), g._h)
+            st = L.lv_peer_plan(g._h, npeer, harr, ptr(remote) if remote.numel() else None)
+            self._agree_on_peer_memory(st == 0)
 
     # -- results --------------------------------------------------------------------------------------
     def owned_index(self) -> torch.Tensor:
