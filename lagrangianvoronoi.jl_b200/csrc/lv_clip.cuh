@@ -27,6 +27,7 @@ struct ClipArgs {
     unsigned long long *tile_state;
     int *flags;
     long long cap_nnz;
+    int force_anomaly; // test hook (LV_CLIP_FORCE_ANOMALY=1): pretend some polygons are not generic
 };
 
 

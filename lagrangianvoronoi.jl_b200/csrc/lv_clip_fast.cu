@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
             }
         }
         __syncwarp();
+        if (a.force_anomaly && active && (slot % 1009) == 7) bad = true;
         if (bad) atomicOr(&a.flags[LVF_OVERFLOW], OVF_ANOMALY);
 
         // ---- row placement: one atomicAdd per warp

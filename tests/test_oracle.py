@@ -177,3 +177,38 @@ def test_taylor_green_reference_thresholds(oracle):
     assert k == 80
     E_err, v_err, P_err = errs
     assert E_err < 1e-8 and v_err < 0.01 and P_err < 0.01
+
+
+def test_random_clouds_property(oracle):
+    """Property test (hypothesis): for arbitrary seeded clouds -- uniform, clustered, with walls or periodic -- the cells
+    tile the domain, adjacency is symmetric and every polygon is a closed clockwise chain."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(seed=st.integers(0, 10 ** 6), n=st.integers(150, 700), per=st.booleans(), clustered=st.booleans())
+    def prop(seed, n, per, clustered):
+        rng = np.random.default_rng(seed)
+        xy = rng.random((n, 2))
+        if clustered:
+            xy[: n // 3] = 0.5 + 0.05 * rng.standard_normal((n // 3, 2))
+            xy = np.clip(xy, 1e-6, 1 - 1e-6)
+        dr = 1.0 / np.sqrt(n)
+        g = oracle.OracleGrid((0, 0), (1, 1), dr, r_max=30 * dr, xperiodic=per, yperiodic=per)
+        g.set_points(xy)
+        status = g.remesh()
+        if status != 0:        # sparse corners may exceed r_max: the reference throws, nothing to check
+            return
+        rowptr, edges = g.mesh()
+        assert abs(g.area().sum() - 1.0) < 1e-10
+        rows = np.repeat(np.arange(1, n + 1), np.diff(rowptr))
+        lab = edges["label"]
+        pos = lab > 0
+        pairs = set(zip(rows[pos].tolist(), lab[pos].tolist()))
+        assert all((b, a) in pairs for a, b in pairs)
+        if per:
+            assert pos.all() and rowptr[-1] == 6 * n
+        for i in range(0, n, max(1, n // 20)):
+            e = edges[rowptr[i]:rowptr[i + 1]]
+            assert np.array_equal(e["v2"], np.roll(e["v1"], -1, axis=0))
+
+    prop()

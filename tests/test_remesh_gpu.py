@@ -182,3 +182,72 @@ def test_lazy_edge_download_is_identical(lv):
     assert g.edges.tobytes() == ref[1].tobytes()
     lv.remesh(g)                                            # back to the synchronous mode
     assert g.edges.tobytes() == ref[1].tobytes()
+
+
+def _degenerate_sets(seed):
+    """Inputs on which the clipping decisions hinge on SIGNUM_EPS and the cut order (excluded from the north star's
+    bit-exact claim, yet the GPU path must still reproduce the reference because its fast kernel detects what it cannot
+    replay exactly and hands the remesh to the edge-list kernel)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    g = (np.arange(24) + 0.5) / 24
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    lat = np.stack([X.ravel(), Y.ravel()], 1)
+    out["square lattice"] = lat
+    sel = rng.random(len(lat)) < 0.7
+    out["lattice with holes"] = lat[sel]
+    out["lattice + 1e-13 noise"] = lat + 1e-13 * rng.standard_normal(lat.shape)
+    th = np.linspace(0, 2 * np.pi, 48, endpoint=False)
+    rings = [0.5 + r * np.stack([np.cos(th), np.sin(th)], 1) for r in (0.1, 0.2, 0.3, 0.4)]
+    out["concentric co-circular rings"] = np.concatenate([[[0.5, 0.5]]] + rings)
+    base = rng.random((300, 2)) * 0.9 + 0.05
+    out["near-duplicate pairs"] = np.concatenate([base, base + 1e-9])
+    a = (4 / 3) ** 0.25 / 24; b = (3 / 4) ** 0.25 / 24
+    i, j = np.meshgrid(np.arange(-1, 30), np.arange(0, 32), indexing="ij")
+    hexp = np.stack([((i + (j % 2) / 2) * a).ravel(), (j * b).ravel()], 1)
+    out["hex lattice"] = hexp[(hexp >= 0).all(1) & (hexp <= 1).all(1)]
+    out["collinear row + cloud"] = np.concatenate([np.stack([np.linspace(0.05, 0.95, 40), np.full(40, 0.5)], 1), rng.random((200, 2))])
+    return out
+
+
+@pytest.mark.parametrize("per", [False, True])
+def test_degenerate_inputs_still_match_the_reference(lv, oracle, per):
+    dr = 1 / 24
+    kinds = {}
+    for name, xy in _degenerate_sets(3).items():
+        og = oracle.OracleGrid((0, 0), (1, 1), dr, xperiodic=per, yperiodic=per)
+        og.set_points(xy)
+        st = og.remesh()
+        g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), dr, xperiodic=per, yperiodic=per)
+        g.set_points(xy)
+        if st != 0:
+            with pytest.raises(lv.LvError):
+                lv.remesh(g)
+            continue
+        lv.remesh(g)
+        rowptr, edges = og.mesh()
+        assert np.array_equal(g.rowptr, rowptr), name
+        assert g.edges.tobytes() == edges.tobytes(), name
+        assert lv.area(g).tobytes() == og.area().tobytes(), name
+        kinds[name] = g.clip_info()[0]
+    assert len(kinds) >= 5
+    print("kernel level per degenerate input:", kinds)
+
+
+def test_anomaly_replay_ladder(lv, oracle, monkeypatch):
+    """When the linked-slot kernel reports a polygon it cannot replay exactly, the whole remesh is replayed by the
+    edge-list kernel.  The hook LV_CLIP_FORCE_ANOMALY=1 makes the fast kernel report a few polygons."""
+    xy, dr, bmin, bmax = make_points("poisson", 72, 6)
+    og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=True, yperiodic=False)
+    og.set_points(xy); assert og.remesh() == 0
+    monkeypatch.setenv("LV_CLIP_FORCE_ANOMALY", "1")
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=True, yperiodic=False)
+    g.set_points(xy)
+    lv.remesh(g)
+    level, anomalies = g.clip_info()
+    assert level >= 2 and anomalies == 1
+    _assert_mesh_equal(g, og, lv)
+    monkeypatch.delenv("LV_CLIP_FORCE_ANOMALY")
+    lv.remesh(g)                                          # the replay is per remesh: next time the fast kernel is back
+    assert g.clip_info() == (0, 1) or g.clip_info() == (1, 1)
+    _assert_mesh_equal(g, og, lv)
