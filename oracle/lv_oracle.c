@@ -129,7 +129,7 @@ struct lvo_grid {
 };
 
 static int g_threads = 0;
-void lvo_set_threads(int nthreads) { g_threads = nthreads; if (nthreads > 0) omp_set_num_threads(nthreads); }
+void lvo_set_threads(int nthreads) { g_threads = nthreads; omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs()); }
 int lvo_get_threads(void) { return g_threads > 0 ? g_threads : omp_get_max_threads(); }
 
 /* stable merge sort of path nodes (Julia's default sort! is stable; neighborlist.jl:40-41) */
