@@ -33,6 +33,12 @@ void lv_free(LvContext *c, void *ptr, size_t bytes) {
     cudaFree(ptr);
     c->dev_bytes -= (int64_t)bytes;
 }
+// persistent staging for host<->device field transfers (contents undefined on return)
+int lv_io_stage(LvContext *c, void **ptr, size_t bytes) {
+    LV_TRY(lv_ensure(c, &c->d_io_stage, &c->cap_io_stage, (int64_t)(bytes ? bytes : 16), 1));
+    *ptr = c->d_io_stage;
+    return LV_OK;
+}
 // grow-only buffer; contents are NOT preserved
 int lv_ensure(LvContext *c, void **ptr, int64_t *cap, int64_t need, size_t elt) {
     if (*ptr && *cap >= need) return LV_OK;
@@ -209,7 +215,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
                     c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
-                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1]};
+                    c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1], c->d_io_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
     for (double *v : c->st_field) if (v) cudaFree(v);
@@ -372,6 +378,15 @@ __global__ void __launch_bounds__(256) k_label_copy(int64_t n, const int *__rest
         }
 }
 
+// device-visible alias of a pinned (mapped) host buffer, or nullptr for pageable memory; LV_DIRECT_STORE=0 disables it
+void *lv_mapped_alias(const void *host) {
+    static const bool enabled = [] { const char *e = getenv("LV_DIRECT_STORE"); return !(e && e[0] == '0'); }();
+    if (!enabled || !host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     const int64_t n = c->n, nnz = c->nnz;
@@ -400,18 +415,31 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
     LvEdge *e_l = (LvEdge *)(base + off_e);
     const int nb = (int)((n + 256) / 256);
     int st = LV_OK;
+    // lazy mode: the copy engine is busy with the previous edge view for ~80 ms, and a cudaMemcpy of the small per-cell
+    // arrays would queue behind it.  When the caller's buffers are pinned (hence mapped under UVA) the conversion kernel
+    // stores them straight into host memory instead: coalesced 256-512 B per warp, concurrent with the DMA.
+    long long *r64_out = r64; double *area_out = area_l; double2 *cen_out = cen_l;
+    bool direct_r = false, direct_a = false, direct_c = false;
+    if (c->async_edges) {
+        direct_r = rowptr && (r64_out = (long long *)lv_mapped_alias(rowptr)) != nullptr;
+        direct_a = area && (area_out = (double *)lv_mapped_alias(area)) != nullptr;
+        direct_c = centroid && (cen_out = (double2 *)lv_mapped_alias(centroid)) != nullptr;
+        if (!direct_r) r64_out = r64;
+        if (!direct_a) area_out = area_l;
+        if (!direct_c) cen_out = cen_l;
+    }
     do {
         k_label_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, deg);
         c->launches++;
         if ((st = lv_exclusive_scan_i32(c, deg, rl, n)) != LV_OK) break;
         k_label_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
-                                                c->d_area, c->d_cen, rowptr ? r64 : nullptr, edges ? e_l : nullptr,
-                                                area ? area_l : nullptr, centroid ? cen_l : nullptr);
+                                                c->d_area, c->d_cen, rowptr ? r64_out : nullptr, edges ? e_l : nullptr,
+                                                area ? area_out : nullptr, centroid ? cen_out : nullptr);
         c->launches++;
         cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess && rowptr) e = cudaMemcpyAsync(rowptr, r64, sizeof(long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && area) e = cudaMemcpyAsync(area, area_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && centroid) e = cudaMemcpyAsync(centroid, cen_l, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && rowptr && !direct_r) e = cudaMemcpyAsync(rowptr, r64, sizeof(long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && area && !direct_a) e = cudaMemcpyAsync(area, area_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && centroid && !direct_c) e = cudaMemcpyAsync(centroid, cen_l, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess && edges) {
             if (c->async_edges) {
                 // the 40 B/edge view is the bulk of the device->host traffic: copy it on a second stream so that it

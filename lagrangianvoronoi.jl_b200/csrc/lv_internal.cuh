@@ -85,6 +85,8 @@ struct LvContext {
     int64_t cap_scratch = 0;
     void *d_stage_buf[2] = {nullptr, nullptr}; // label-order staging of the mesh for the device->host copy
     int64_t cap_stage_buf[2] = {0, 0};
+    void *d_io_stage = nullptr;                // grow-only label-order staging of per-cell fields (host <-> slot order);
+    int64_t cap_io_stage = 0;                  // persistent because cudaFree would wait for the background edge copies
     cudaStream_t copy_stream = nullptr; // background device->host copy of the edge view (lv_set_async_edges)
     cudaEvent_t ev_conv_done = nullptr, ev_stage_done[2] = {nullptr, nullptr};
     bool async_edges = false, stage_pending[2] = {false, false};
@@ -175,6 +177,8 @@ int lv_set_error(LvContext *c, int code, const char *fmt, ...);
 int lv_ensure(LvContext *c, void **ptr, int64_t *cap, int64_t need, size_t elt); // grow-only device buffer
 int lv_alloc(LvContext *c, void **ptr, size_t bytes);
 void lv_free(LvContext *c, void *ptr, size_t bytes);
+int lv_io_stage(LvContext *c, void **ptr, size_t bytes);
+void *lv_mapped_alias(const void *host); // device alias of a pinned host buffer, nullptr for pageable memory
 
 struct LvProfScope { // CUDA-event bracket on the handle's stream; resolved lazily by lv_prof_resolve
     LvContext *c;

@@ -907,21 +907,32 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
     const int64_t n = c->n;
     struct Item { const double *src; double *dst; int nc; double fill; };
     Item items[] = {{mass, c->d_mass, 1, 0.0}, {rho, c->d_rho, 1, 1.0}, {c2, c->d_c2, 1, 1.0}, {P, c->d_P, 1, 0.0}, {v, (double *)c->d_v, 2, 0.0}};
-    // label-order staging on the device (scratch is also used by scans, so use a private buffer)
-    void *stage = nullptr;
-    if (!dev) LV_TRY(lv_alloc(c, &stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)));
+    // label-order staging on the device: one persistent buffer with a sub-range per field, so that the five uploads
+    // run back to back on the copy engine and no cudaMalloc / cudaFree (device-wide sync) sits on the path
+    char *stage = nullptr;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    if (!dev) LV_TRY(lv_io_stage(c, (void **)&stage, sizeof(double) * 6 * nn));
     int st = LV_OK;
+    size_t off = 0;
+    const double *src_dev[5];
+    int k = 0;
     for (const Item &it : items) {
-        if (!it.src) continue;
-        const double *src_dev = it.src;
-        if (!dev) {
-            cudaError_t e = cudaMemcpyAsync(stage, it.src, sizeof(double) * (size_t)it.nc * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        src_dev[k] = it.src;
+        if (it.src && !dev) {
+            cudaError_t e = cudaMemcpyAsync(stage + off, it.src, sizeof(double) * (size_t)it.nc * (size_t)n, cudaMemcpyHostToDevice, c->stream);
             if (e != cudaSuccess) { st = lv_set_error(c, LV_ECUDA, "field upload failed: %s", cudaGetErrorString(e)); break; }
-            src_dev = (const double *)stage;
+            src_dev[k] = (const double *)(stage + off);
+            off += sizeof(double) * (size_t)it.nc * nn;
         }
-        if ((st = lv_gather_to_slots(c, src_dev, it.dst, it.nc, it.fill)) != LV_OK) break;
+        k++;
     }
-    if (!dev) { cudaStreamSynchronize(c->stream); lv_free(c, stage, sizeof(double) * 2 * (size_t)(n > 0 ? n : 1)); }
+    k = 0;
+    for (const Item &it : items) {
+        if (st != LV_OK) break;
+        if (it.src) st = lv_gather_to_slots(c, src_dev[k], it.dst, it.nc, it.fill);
+        k++;
+    }
+    if (!dev) cudaStreamSynchronize(c->stream); // the host buffers may be reused as soon as we return
     // neighbours' density, pressure and velocity across the strip edges
     if (st == LV_OK && rho) st = lv_halo_exchange(c, c->d_rho, 1);
     if (st == LV_OK && P) st = lv_halo_exchange(c, c->d_P, 1);
@@ -946,16 +957,19 @@ int32_t lv_fields_upload_dev(LvHandle c, const double *mass, const double *rho, 
 static int download_slots(LvContext *c, const double *src_slot, double *dst_host, int nc) {
     const int64_t n = c->n;
     if (n == 0) return LV_OK;
-    void *stage = nullptr;
-    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)nc * (size_t)n));
+    // while an edge view is still streaming to the host the copy engine is taken: scatter straight into the caller's
+    // buffer when it is pinned (mapped), otherwise through the staging buffer + cudaMemcpy
+    double *direct = (c->stage_pending[0] || c->stage_pending[1]) ? (double *)lv_mapped_alias(dst_host) : nullptr;
+    void *stage = direct;
+    if (!direct) LV_TRY(lv_io_stage(c, &stage, sizeof(double) * (size_t)nc * (size_t)n));
     int st = lv_scatter_to_labels(c, src_slot, (double *)stage, nc);
     if (st == LV_OK) {
-        cudaError_t e = cudaMemcpyAsync(dst_host, stage, sizeof(double) * (size_t)nc * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaSuccess;
+        if (!direct) e = cudaMemcpyAsync(dst_host, stage, sizeof(double) * (size_t)nc * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "download failed: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(c->stream);
-    lv_free(c, stage, sizeof(double) * (size_t)nc * (size_t)n);
     return st;
 }
 
@@ -1052,7 +1066,7 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
     const int64_t n = c->n;
     if (n == 0) return LV_OK;
     void *stage = nullptr;
-    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)n));
+    LV_TRY(lv_io_stage(c, &stage, sizeof(double) * (size_t)n));
     int st = LV_OK;
     cudaError_t e = cudaMemcpyAsync(stage, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) st = lv_set_error(c, LV_ECUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -1060,7 +1074,6 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
     if (st == LV_OK) st = lv_halo_exchange(c, c->d_vec[3], 1);
     if (st == LV_OK) st = lv_pr_matvec(c, c->d_vec[3], c->d_vec[4]);
     cudaStreamSynchronize(c->stream);
-    lv_free(c, stage, sizeof(double) * (size_t)n);
     if (st == LV_OK) st = download_slots(c, c->d_vec[4], y, 1);
     return st;
 }
@@ -1099,7 +1112,7 @@ int32_t lv_pressure_solve(LvHandle c, int32_t solver, const double *b, double *x
     const int64_t n = c->n;
     if (n == 0) return LV_OK;
     void *stage = nullptr;
-    LV_TRY(lv_alloc(c, &stage, sizeof(double) * (size_t)n));
+    LV_TRY(lv_io_stage(c, &stage, sizeof(double) * (size_t)n));
     int st = LV_OK;
     const double *srcs[2] = {b, x};
     double *dsts[2] = {c->d_b, c->d_P};
@@ -1109,7 +1122,6 @@ int32_t lv_pressure_solve(LvHandle c, int32_t solver, const double *b, double *x
         if (st == LV_OK) st = lv_gather_to_slots(c, (const double *)stage, dsts[k], 1, 0.0);
         cudaStreamSynchronize(c->stream);
     }
-    lv_free(c, stage, sizeof(double) * (size_t)n);
     if (st == LV_OK) st = lv_pr_solve(c, solver, rtol, atol, itmax, iters, relres);
     if (st == LV_OK) st = download_slots(c, c->d_P, x, 1);
     return st;
