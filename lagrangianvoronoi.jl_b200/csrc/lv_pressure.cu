@@ -175,8 +175,8 @@ __device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
 // (A variant that staged each warp tile's col / w through shared memory measured 1.7x slower on
 // B200 -- three dependent memory round trips per tile instead of one -- and was dropped.)
 #define MV_U 8
-template <bool DOT>
-__global__ void __launch_bounds__(PR_BLOCK) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
+template <bool DOT, int MINB>
+__global__ void __launch_bounds__(PR_BLOCK, MINB) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                      const int *__restrict__ col, const double *__restrict__ w,
                                                      const double *__restrict__ diag, const double *__restrict__ x,
                                                      double *__restrict__ y, double *__restrict__ partial,
@@ -223,13 +223,43 @@ static inline int pr_grid(const LvContext *c, int64_t n) {
     return (int)(nb < cap ? (nb < 1 ? 1 : nb) : cap);
 }
 
+// Grid of the matvec: exactly one resident wave.  At 48 registers only 5 blocks of 256 threads fit an SM, so the
+// 8-per-SM grid above ran 1.6 waves and the second one left 40 % of the machine idle (the kernel is latency bound,
+// so throughput follows the number of resident warps).  LV_MV_GRID=legacy restores the old sizing.
+// MINB = 6 caps the kernel at 40 registers (no spills; 48 without the cap): 6 instead of 5 resident blocks per SM.
+// LV_MV_MINB=1 selects the uncapped build, LV_MV_GRID=legacy the old grid (A/B switches for the bench).
+static int mv_minb() {
+    static int v = 0;
+    if (v == 0) { const char *e = getenv("LV_MV_MINB"); v = (e && e[0] == '1') ? 1 : 6; }
+    return v;
+}
+template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char *e = getenv("LV_MV_GRID");
+        int occ = 0;
+        cudaError_t st = mv_minb() == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 1>, PR_BLOCK, 0)
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 6>, PR_BLOCK, 0);
+        if ((e && !strcmp(e, "legacy")) || st != cudaSuccess || occ < 1) occ = 8;
+        per_sm = occ;
+    }
+    int64_t nb = (n + PR_BLOCK - 1) / PR_BLOCK, cap = (int64_t)c->num_sms * per_sm;
+    if (cap > 4096) cap = 4096;
+    return (int)(nb < cap ? (nb < 1 ? 1 : nb) : cap);
+}
+template <bool DOT>
+static void mv_launch(LvContext *c, int grid, cudaStream_t st, int ns, const double *x, double *y, double *partial, const double *scal) {
+    if (mv_minb() == 1) k_matvec<DOT, 1><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal);
+    else k_matvec<DOT, 6><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal);
+    c->launches++;
+}
+
 int lv_pr_matvec(LvContext *c, const double *x, double *y) {
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     LvProfScope prof(c, LV_PROF_MATVEC);
     const int ns = (int)c->nslot;
     if (ns == 0) return LV_OK;
-    k_matvec<false><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, nullptr, c->d_red);
-    c->launches++;
+    mv_launch<false>(c, mv_grid<false>(c, ns), c->stream, ns, x, y, nullptr, c->d_red);
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
 }
@@ -638,16 +668,15 @@ __global__ void __launch_bounds__(PR_BLOCK) k_axpy1(int nslot, const double *__r
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) y[i] += x[i];
 }
 
-// x += alpha p ; r -= alpha Ap ; partial(r.r)
-__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xr(int nslot, const double *__restrict__ scal, const double *__restrict__ p,
-                                                           const double *__restrict__ Ap, double *__restrict__ x,
-                                                           double *__restrict__ r, double *__restrict__ partial) {
+// r -= alpha Ap ; partial(r.r).  The x update rides along with the p update below, which reads p anyway:
+// 8 instead of 9 vector streams per iteration, same arithmetic per element.
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_r(int nslot, const double *__restrict__ scal, const double *__restrict__ Ap,
+                                                          double *__restrict__ r, double *__restrict__ partial) {
     __shared__ double sm[32];
     if (scal[SC_CONV] != 0.0) return;
     const double alpha = scal[SC_ALPHA];
     double rr = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
-        x[i] += alpha * p[i];
         const double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
         rr += ri * ri;
@@ -656,14 +685,22 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xr(int nslot, const doub
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// p = r + beta p
-__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_p(int nslot, const double *__restrict__ scal, const double *__restrict__ r,
-                                                          double *__restrict__ p) {
-    if (scal[SC_CONV] != 0.0 && scal[SC_ITER] == 0.0) return;
-    // after convergence beta is stale but p is never used again
-    if (scal[SC_CONV] != 0.0) return;
-    const double beta = scal[SC_BETA];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) p[i] = r[i] + beta * p[i];
+// x += alpha p ; p = r + beta p.  `iter` is this iteration's 1-based index: the iteration that converged still
+// applies its x update (and skips the p update, which nobody reads); later queued iterations are no-ops.
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xp(int nslot, int iter, const double *__restrict__ scal, const double *__restrict__ r,
+                                                           double *__restrict__ x, double *__restrict__ p) {
+    const bool conv = scal[SC_CONV] != 0.0;
+    if (conv && scal[SC_ITER] != (double)iter) return;
+    const double alpha = scal[SC_ALPHA], beta = scal[SC_BETA];
+    if (conv) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) x[i] += alpha * p[i];
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+        const double pi = p[i];
+        x[i] += alpha * pi;
+        p[i] = r[i] + beta * pi;
+    }
 }
 
 // residual check: partial(|b - Ax|^2), partial(|b|^2)
@@ -694,9 +731,11 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     double *x = c->d_P, *b = c->d_b, *r = c->d_vec[0], *p = c->d_vec[1], *Ap = c->d_vec[2];
     double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
     const int NBMAX = 4096;
-    const int nb = pr_grid(c, ns);
-    // finish a reduction: locally, or through a 2-scalar NCCL allreduce when the grid is decomposed
+    const int nb = pr_grid(c, ns), nb_mv = mv_grid<true>(c, ns), nb_mv0 = mv_grid<false>(c, ns);
+    // finish a reduction over the partials of the kernel launched just before (mode 1: the matvec's grid): locally,
+    // or through a 2-scalar allreduce when the grid is decomposed
     auto finish = [&](int mode) -> int {
+        const int nb = mode == 1 ? nb_mv : pr_grid(c, ns);
         MailArgs mail{nullptr, 1, 0, 0};
         if (!c->comm) { k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol, mail); c->launches++; return LV_OK; }
         if (c->mailbox_ready) {
@@ -713,8 +752,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     };
     auto matvec_plain = [&](const double *in, double *out) {
         LvProfScope prof(c, LV_PROF_MATVEC);
-        k_matvec<false><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, in, out, nullptr, scal);
-        c->launches++;
+        mv_launch<false>(c, nb_mv0, st, ns, in, out, nullptr, scal);
     };
     LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
     matvec_plain(x, Ap);
@@ -737,14 +775,13 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 LV_TRY(lv_halo_pull_p(c, p)); // ghost columns of the search direction, read from the neighbours' memory
                 {
                     LvProfScope prof(c, LV_PROF_MATVEC);
-                    k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, p, Ap, partial, scal);
-                    c->launches++;
+                    mv_launch<true>(c, nb_mv, st, ns, p, Ap, partial, scal);
                 }
                 LvProfScope prof(c, LV_PROF_VECOPS);
                 LV_TRY(finish(1));
-                k_cg_update_xr<<<nb, PR_BLOCK, 0, st>>>(ns, scal, p, Ap, x, r, partial);
+                k_cg_update_r<<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial);
                 LV_TRY(finish(2));
-                k_cg_update_p<<<nb, PR_BLOCK, 0, st>>>(ns, scal, r, p);
+                k_cg_update_xp<<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p);
                 c->launches += 2;
                 LV_TRY(lv_halo_signal(c));
             }
@@ -774,8 +811,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 LV_TRY(lv_halo_pull_p(c, r2));
                 {
                     LvProfScope prof(c, LV_PROF_MATVEC);
-                    k_matvec<true><<<nb, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, r2, y, partial, scal);
-                    c->launches++;
+                    mv_launch<true>(c, nb_mv, st, ns, r2, y, partial, scal);
                 }
                 LvProfScope prof(c, LV_PROF_VECOPS);
                 k_mr_a<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r2, r1, y, partial);
