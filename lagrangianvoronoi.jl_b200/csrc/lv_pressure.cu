@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned c
 }
 
 // Later passes, sweep 2: b_i = A_i P_i/(rho c2 dt^2) + bvel_i + sum lrr (GP_i - GP_j).(m - z)   pressure.jl:171,189-202
-__global__ void __launch_bounds__(PR_BLOCK) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
+__global__ void __launch_bounds__(PR_BLOCK, 8) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
                                                        const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mz_in,
                                                        const double *__restrict__ area, const double *__restrict__ rho,
