@@ -156,7 +156,7 @@ def run_reference(args):
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -228,7 +228,7 @@ def run_ours(args):
                  {"mass": np.where(area > 0, area, 1.0), "rho": np.ones(nl), "c2": np.full(nl, args.c0 ** 2), "P": P, "v": v}.items()}
         n = int(sg.mask_loc.sum().item())
         parallelism = (f"{world} y-strips ({args.scaling} scaling), ghost generators by torch.distributed send/recv per remesh, "
-                       f"CG halo = {'ncclSend/Recv' if args.nccl_halo else 'NVLink peer-memory loads (CUDA IPC)'} + 2-scalar ncclAllReduce per iteration; "
+                       f"CG halo = {'ncclSend/Recv + 2-scalar ncclAllReduce per dot product' if not sg.use_peer_memory else 'NVLink peer-memory loads (CUDA IPC) + 2-scalar all-reduce through peer mailboxes fused into the scalar kernel'}; "
                        f"halo (send, recv) per peer = {sg.halo_counts}")
         args.no_e2e = True  # the host-buffer drop-in API is single-GPU (one Julia process, one GPU)
 
@@ -356,14 +356,32 @@ def run_ours(args):
         res = cpu_step_rate(args.cpu_side, args.c0, args.niter, args.seed, 1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["detail"] = {k: res[k] for k in ("remesh_mcells_s", "krylov_mcell_iters_s", "s_per_step_sample")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-if __name__ == "__main__":
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL / torchrun banners that libraries write
+    to fd 1) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # native libraries (NCCL prints its version banner on stdout) must not pollute the JSON channel
     a = parse()
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()
