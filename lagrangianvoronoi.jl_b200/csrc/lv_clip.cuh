@@ -40,13 +40,14 @@ struct ClipArgs {
 #define OVF_NNZ 2    // the CSR edge buffers are too small
 #define OVF_ANOMALY 4 // the fast kernel met a case it does not handle exactly (rerun with the edge-list kernel)
 
-// CSR column of a candidate slot l: the primary slot of its generator when this rank owns it, the
-// candidate slot itself for ghost generators (their values arrive by halo exchange at that slot)
+// CSR column of a candidate slot l: always the PRIMARY slot of its generator (an image entry only lends its position
+// to the clipping).  Ghost generators (multi-GPU) have a primary slot on this rank as well, and that is the one slot per
+// ghost the halo exchange fills.
 __device__ __forceinline__ int lv_col_of(const ClipArgs &a, int l) {
     const unsigned e = a.ent_label[l];
     if (!(e & LV_IMAGE_BIT)) return l;
     const int p = a.prim_of_label[e & ~LV_IMAGE_BIT];
-    return (p >= 0 && a.own[p]) ? p : l;
+    return p >= 0 ? p : l;
 }
 
 int lv_clip_launch_fast(LvContext *c, const ClipArgs &a, int level); // lv_clip_fast.cu

@@ -7,10 +7,15 @@ The reference is shared-memory only; this is the decompo
 * before a remesh every rank sends the generators whose buckets (primary or periodic image) fall into a
   neighbour's halo window -- ``H`` bucket rows either side, ``H`` = the largest row offset the reference's
   neighbour walk can reach before it throws (voronoigrid.jl:63-65) -- with ``torch.distributed`` send/recv;
-* owned and ghost generators are merged in global-label order, so the local cell list finds labels in the
-  same order as the single-GPU (= ``julia -t 1``) run and connectivity does not depend on the GPU count;
-* after the remesh the ranks agree on a halo plan (which of my slots a neighbour needs, in its order); the
-  library then exchanges ghost values with NCCL send/recv inside the Krylov loop and allreduces the dots.
+* owned generators come first, ghosts are appended peer by peer in the order they were sent; the library orders
+  every bucket by the global label it is given as key, so the local cell list finds labels in the same order as
+  the single-GPU (= ``julia -t 1``) run and connectivity does not depend on the GPU count;
+* the halo plan needs no negotiation: sender and receiver both use the order of the sent list (primary slots of
+  ``sent_sel[q]`` on one side, primary slots of the ghost labels on the other).  Per remesh a rank talks to its
+  strip neighbours only -- counts, ghost generators, and (peer-memory halo) one message with its slot addresses
+  and CUDA IPC handles; there is no collective over the whole group;
+* inside the Krylov loop the library pulls ghost values over NVLink from the neighbours' memory and sums the dot
+  products through peer mailboxes (NCCL send/recv + allreduce as the fallback).
 
 Everything in this module is plain ``torch`` + ``torch.distributed`` and works on CPU tensors with the
 ``gloo`` backend (tests) as well as on CUDA tensors with ``nccl``; the compute calls go to liblvb200.
@@ -27,6 +32,8 @@ import torch.distributed as dist
 from . import _capi
 from ._capi import check, load_library, ptr
 from .host import PressureSolver, Rectangle, VoronoiGrid
+
+_CHECK_PLAN = bool(int(__import__("os").environ.get("LV_CHECK_PLAN", "0")))  # extra (synchronising) sanity checks
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -95,6 +102,37 @@ def exchange_variable(send: dict, world: int, rank: int, device, dtype, width: i
     return recv
 
 
+def exchange_with_peers(send: dict, peers, device, dtype, width: int, group=None, counts_in: dict = None) -> dict:
+    """Neighbour-only variant of exchange_variable: every rank in ``peers`` gets ``send[q]`` ([k, width], possibly
+    empty) and sends one back.  No collective over the whole group: counts travel as one-element messages between
+    neighbours (skipped when the caller knows them: ``counts_in[q]``), payloads with batched isend/irecv."""
+    peers = list(peers)
+    if not peers:
+        return {}
+    if counts_in is None:
+        cs = {q: torch.tensor([send[q].shape[0]], dtype=torch.int64, device=device) for q in peers}
+        cr = {q: torch.zeros(1, dtype=torch.int64, device=device) for q in peers}
+        ops = []
+        for q in peers:
+            ops.append(dist.P2POp(dist.irecv, cr[q], q, group=group))
+            ops.append(dist.P2POp(dist.isend, cs[q], q, group=group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        got = torch.cat([cr[q] for q in peers]).cpu().tolist()  # one device sync for all peers
+        counts_in = {q: int(k) for q, k in zip(peers, got)}
+    ops, recv = [], {}
+    for q in peers:
+        recv[q] = torch.empty((counts_in[q], width), dtype=dtype, device=device)
+        if counts_in[q] > 0:
+            ops.append(dist.P2POp(dist.irecv, recv[q], q, group=group))
+        if send[q].shape[0] > 0:
+            ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
+
+
 class StripPlan:
     """Geometry of the decomposition: who owns which bucket rows and which peers exist."""
 
@@ -110,6 +148,7 @@ class StripPlan:
         row_lo = int(math.floor((bmin[1] - self.oy) / self.h))
         row_hi = int(math.floor((bmax[1] - self.oy) / self.h))
         self.R = partition_rows(self.n2, row_lo, min(row_hi, self.n2 - 1), world)
+        self.row_lo, self.row_hi = row_lo, min(row_hi, self.n2 - 1)
         if world > 1 and np.diff(self.R)[1:-1].min(initial=10 ** 9) < self.H:
             raise ValueError(f"strips thinner than the halo ({self.H} bucket rows): use fewer ranks for this grid")
         if world > 1 and min(self.R[1] - row_lo, row_hi + 1 - self.R[-2]) < self.H:
@@ -117,7 +156,7 @@ class StripPlan:
 
     def window(self, q: int):
         """Bucket rows whose entries rank q needs: its own rows plus H rows either side."""
-        return int(self.R[q]) - self.H, int(self.R[q + 1]) + self.H
+        return max(int(self.R[q]) - self.H, 0), min(int(self.R[q + 1]) + self.H, self.n2)  # rows outside the grid hold nothing
 
     def peers(self):
         """Ranks whose windows can overlap my rows: the strip neighbours, wrapping when y is periodic."""
@@ -136,14 +175,49 @@ class StripPlan:
     def owner(self, y: torch.Tensor) -> torch.Tensor:
         return owner_of_rows(bucket_row(y, self.oy, self.h), self.R)
 
-    def select_ghosts(self, xy: torch.Tensor, labels: torch.Tensor):
-        """Per peer: the rows [x, y, label] of my generators that fall into its halo window, and their
-        indices in my owned arrays (the halo plan refers to ghosts by their position in this list)."""
-        out, sels = {}, {}
+    def near_bounds(self):
+        """(A, B, everything): a generator of this strip can only be in a peer's window -- directly or through a
+        y-image -- if v = (y - oy)/h satisfies v < A or v >= B.  Derived from the windows themselves (each shifted by
+        0, +period, -period and widened by one row for rounding); ``everything`` is set when a window lies strictly
+        inside the strip (thin strips), in which case no prefilter is possible."""
+        e_lo = max(int(self.R[self.rank]), self.row_lo)
+        e_hi = min(int(self.R[self.rank + 1]), self.row_hi + 1)
+        shifts = (0.0, self.yperiod / self.h, -self.yperiod / self.h) if self.yperiodic else (0.0,)
+        A, B, everything = -math.inf, math.inf, False
         for q in self.peers():
             lo, hi = self.window(q)
-            m = ghost_mask_for(xy[:, 1], self.oy, self.h, self.yperiodic, self.yperiod, lo, hi)
-            sel = torch.nonzero(m, as_tuple=False).squeeze(1)
+            for sr in shifts:
+                a, b = lo - sr - 1.0, hi - sr + 1.0
+                if a <= e_lo:
+                    A = max(A, b)
+                elif b >= e_hi:
+                    B = min(B, a)
+                else:
+                    everything = True
+        return A, B, everything
+
+    def select_ghosts(self, xy: torch.Tensor, labels: torch.Tensor):
+        """Per peer: the rows [x, y, label] of my generators that fall into its halo window, and their
+        indices in my owned arrays (the halo plan refers to ghosts by their position in this list).
+
+        Only generators near the strip's edges (``near_bounds``) can be in anybody's window, so one cheap pass over
+        all generators picks those and the per-peer window tests run on that small subset."""
+        out, sels = {}, {}
+        peers = self.peers()
+        if not peers:
+            return out, sels
+        y = xy[:, 1]
+        v = (y - self.oy) / self.h                      # bucket_row(y) == floor(v); comparisons with integers need no floor
+        A, B, everything = self.near_bounds()
+        if everything or A >= B:
+            near = torch.arange(y.numel(), device=y.device)
+        else:
+            near = torch.nonzero((v < A) | (v >= B), as_tuple=False).squeeze(1)
+        y_near = y[near]
+        for q in peers:
+            lo, hi = self.window(q)
+            m = ghost_mask_for(y_near, self.oy, self.h, self.yperiodic, self.yperiod, lo, hi)
+            sel = near[m]
             payload = torch.empty((sel.numel(), 3), dtype=torch.float64, device=xy.device)
             payload[:, :2] = xy[sel]
             payload[:, 2] = labels[sel].to(torch.float64)  # labels < 2^53 travel exactly in a double
@@ -181,7 +255,8 @@ def exchange_ghosts(plan: StripPlan, xy_own: torch.Tensor, lab_own: torch.Tensor
     n_own = int(xy_own.shape[0])
     if plan.world > 1:
         send, sels = plan.select_ghosts(xy_own, lab_own)
-        recv = exchange_variable(send, plan.world, plan.rank, xy_own.device, torch.float64, 3, group)
+        recv = exchange_with_peers(send, plan.peers(), xy_own.device, torch.float64, 3, group)
+        recv = {q: t for q, t in recv.items() if t.shape[0] > 0}
     else:
         sels, recv = {}, {}
     xs, ls, os_ = [xy_own], [lab_own], [torch.full_like(lab_own, plan.rank)]
@@ -283,6 +358,8 @@ class StripGrid:
         """Generators this rank owns (they must lie in its strip), global labels ascending."""
         self.xy_own = torch.as_tensor(xy, dtype=torch.float64, device=self.dev).contiguous()
         self.lab_own = torch.as_tensor(labels, dtype=torch.int64, device=self.dev).contiguous()
+        if self.lab_own.numel() and int(self.lab_own.max()) >= 2 ** 31:
+            raise ValueError("global labels must stay below 2^31")
 
     def migrate(self) -> None:
         """After a move: hand generators that left the strip to their new owner."""
@@ -295,8 +372,6 @@ class StripGrid:
         self.local = loc
         self.xy_loc, self.lab_loc, self.owner_loc = loc.xy, loc.lab, loc.owner
         self.n_loc = int(loc.xy.shape[0])
-        if self.n_loc and int(loc.lab.max()) >= 2 ** 31:
-            raise ValueError("global labels must stay below 2^31")
         self.key_loc = loc.lab.to(torch.int32).contiguous()
         self.mask_loc = torch.zeros(self.n_loc, dtype=torch.uint8, device=self.dev)
         self.mask_loc[: loc.n_own] = 1
@@ -315,63 +390,55 @@ class StripGrid:
         return torch.as_tensor(_DevArray(p.value, n.value, typestr), device=self.dev)
 
     def _build_halo_plan(self) -> None:
-        """Ghost slots are filled from their owners.  A ghost is named by its position in the list its owner
-        sent (no label search): I ask peer q for positions k, q answers with the primary slots of sent_sel[q][k]."""
+        """Ghost slots are filled from their owners.  Both sides use the order of the list the owner sent: the
+        receiver's slots are the primary slots of its ghost labels (appended peer by peer in that order), the
+        sender's slots are the primary slots of ``sent_sel[q]``.  Periodic-image entries of ghosts need no values
+        (edges refer to the primary slot).  For the peer-memory halo one neighbour-only message per peer carries
+        the sender's slots -- the addresses the receiver will load from -- and the CUDA IPC handles of its vector:
+        no collective over the whole group per remesh."""
         g, L, loc = self.grid, self._L, self.local
-        ent = self._dev_tensor(0, "<i4", torch.int32)                              # label | image bit (bit 31 = sign)
-        prim = self._dev_tensor(1, "<i4", torch.int32)
-        lab_local = ent & 0x7FFFFFFF
-        gs = torch.nonzero(lab_local >= loc.n_own, as_tuple=False).squeeze(1)       # slots of ghost entries
-        gl = lab_local[gs].to(torch.int64)
-        recv_slots, requests = {}, {}
-        for q in self.plan.peers():
+        prim = self._dev_tensor(1, "<i4", torch.int32)                             # primary slot of every local label
+        peers = self.plan.peers()
+        send_slots, recv_slots = {}, {}
+        empty64 = torch.zeros(0, dtype=torch.int64, device=self.dev)
+        for q in peers:
             a, b = loc.ghost_range.get(q, (0, 0))
-            m = (gl >= a) & (gl < b)
-            recv_slots[q] = gs[m].to(torch.int32)
-            requests[q] = (gl[m] - a).unsqueeze(1)
-        asked = exchange_variable(requests, self.world, self.rank, self.dev, torch.int64, 1, self.group)
-        peers, send_slots = [], {}
-        for q in self.plan.peers():
-            want = asked.get(q, torch.zeros((0, 1), dtype=torch.int64, device=self.dev)).squeeze(1)
-            sel = loc.sent_sel.get(q, torch.zeros(0, dtype=torch.int64, device=self.dev))
-            if want.numel() and int(want.max()) >= sel.numel():
-                raise RuntimeError("halo plan: a peer asked for a generator this rank did not send")
-            ss = prim[sel[want]]
-            if ss.numel() and int(ss.min()) < 0:
-                raise RuntimeError("halo plan: requested generator has no primary slot here")
-            send_slots[q] = ss.to(torch.int32)
-            peers.append(q)
+            recv_slots[q] = prim[a:b]
+            send_slots[q] = prim[loc.sent_sel.get(q, empty64)]
         npeer = len(peers)
+        s_all = torch.cat([send_slots[q] for q in peers]).contiguous() if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
+        r_all = torch.cat([recv_slots[q] for q in peers]).contiguous() if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
+        if _CHECK_PLAN and (s_all.numel() and int(s_all.min()) < 0 or r_all.numel() and int(r_all.min()) < 0):
+            raise RuntimeError("halo plan: a generator on the plan has no primary slot here")
         pr = (C.c_int32 * max(npeer, 1))(*peers)
         sc = (C.c_int64 * max(npeer, 1))(*[int(send_slots[q].numel()) for q in peers])
         rc = (C.c_int64 * max(npeer, 1))(*[int(recv_slots[q].numel()) for q in peers])
-        s_all = torch.cat([send_slots[q] for q in peers]) if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
-        r_all = torch.cat([recv_slots[q] for q in peers]) if npeer else torch.zeros(0, dtype=torch.int32, device=self.dev)
-        self._halo_keep = (s_all.contiguous(), r_all.contiguous())
+        self._halo_keep = (s_all, r_all)
         torch.cuda.current_stream(self.dev).synchronize()
-        check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(self._halo_keep[0]) if s_all.numel() else None, rc,
-                             ptr(self._halo_keep[1]) if r_all.numel() else None), g._h)
+        check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(s_all) if s_all.numel() else None, rc,
+                             ptr(r_all) if r_all.numel() else None), g._h)
         self.halo_counts = {q: (int(send_slots[q].numel()), int(recv_slots[q].numel())) for q in peers}
         if self.use_peer_memory and npeer:
-            # peer-memory halo: tell every peer where (in my numbering) the values it receives live, and map
-            # each other's vectors with CUDA IPC so the CG loop can read them over NVLink
-            reply = exchange_variable({q: send_slots[q].to(torch.int64).unsqueeze(1) for q in peers}, self.world, self.rank,
-                                      self.dev, torch.int64, 1, self.group)
-            remote = torch.cat([reply[q].squeeze(1) if q in reply else torch.zeros(0, dtype=torch.int64, device=self.dev)
-                                for q in peers]).to(torch.int32).contiguous()
+            # message to peer q: [16 words of IPC handles | my primary slots of what I sent it]; sizes are known on both sides
             mine = (C.c_uint8 * 128)()
             check(L.lv_peer_export(g._h, mine), g._h)
-            hbuf = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
-            allh = [torch.zeros(128, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
-            dist.all_gather(allh, hbuf, group=self.group)
-            flat = []
-            for q in peers:
-                flat += allh[q].cpu().tolist()
-            harr = (C.c_uint8 * (128 * npeer))(*flat)
+            if bytes(mine) != getattr(self, "_handle_bytes", None):
+                self._handle_bytes = bytes(mine)
+                self._handle_words = torch.frombuffer(bytearray(self._handle_bytes), dtype=torch.int64).to(self.dev)
+            msgs = {q: torch.cat([self._handle_words, send_slots[q].to(torch.int64)]).unsqueeze(1) for q in peers}
+            sizes = {q: 16 + int(recv_slots[q].numel()) for q in peers}
+            got = exchange_with_peers(msgs, peers, self.dev, torch.int64, 1, self.group, counts_in=sizes)
+            remote = torch.cat([got[q][16:, 0] for q in peers]).to(torch.int32).contiguous()
+            hw = torch.cat([got[q][:16, 0] for q in peers]).cpu().numpy().tobytes()   # one sync; also orders the stream
+            harr = (C.c_uint8 * (128 * npeer)).from_buffer_copy(hw)
             self._remote_keep = remote
             torch.cuda.current_stream(self.dev).synchronize()
             st = L.lv_peer_plan(g._h, npeer, harr, ptr(remote) if remote.numel() else None)
-            self._agree_on_peer_memory(st == 0)
+            if not getattr(self, "_peer_agreed", False):
+                self._agree_on_peer_memory(st == 0)  # collective, first plan only: mapping either works on this box or not
+                self._peer_agreed = True
+            else:
+                check(st, g._h)
 
     # -- results --------------------------------------------------------------------------------------
     def owned_index(self) -> torch.Tensor:

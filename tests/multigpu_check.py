@@ -6,6 +6,7 @@ Every rank computes the single-GPU mesh and pressure of the whole problem on its
 it owns in the strip decomposition: connectivity and vertices must be bit-identical (independent of the GPU
 count), the converged pressure within 1e-8 relative."""
 import os
+os.environ.setdefault("LV_CHECK_PLAN", "1")  # synchronising sanity checks of the halo plan
 import sys
 
 import numpy as np

@@ -109,3 +109,33 @@ def test_partition_and_halo_rows():
         assert int(sel.min()) == R[r] and int(sel.max()) == R[r + 1] - 1
     i2 = np.array([0, -1, 1, 6, -6, 7]); rr = np.array([0.0, 0.0, 0.0, 25.0, 25.0, 36.0])
     assert halo_rows(i2, rr, 25.0) == 6
+
+
+@pytest.mark.parametrize("world,yper,ymax", [(2, True, 1.0), (4, True, 1.03), (8, False, 2.0), (4, True, 0.517)])
+def test_select_ghosts_prefilter_equals_window_test(world, yper, ymax):
+    """select_ghosts looks only at generators near the strip edges; the result must equal the plain window test on
+    every generator, also when the period is not a multiple of the bucket size and for generators that have left
+    the strip since the last migration."""
+    from lvb200.distributed import StripPlan, ghost_mask_for
+    from oracle import oracle as orc
+    dr = 1.0 / 96
+    bmin, bmax = (0.0, 0.0), (1.0, ymax)
+    og = orc.OracleGrid(bmin, bmax, dr, xperiodic=True, yperiodic=yper)
+    info, path = og.info(), og.magic_path()
+    rng = np.random.default_rng(world)
+    X = torch.from_numpy(np.column_stack([rng.uniform(0, 1, 20000), rng.uniform(0, ymax, 20000)]))
+    lab = torch.arange(1, 20001, dtype=torch.int64)
+    for rank in range(world):
+        plan = StripPlan(info, path, og.h, og.r_max ** 2, bmin, bmax, True, yper, world, rank)
+        mine = plan.owner(X[:, 1]) == rank
+        # a few strays that belong elsewhere by now (moved, not yet migrated)
+        stray = torch.zeros_like(mine)
+        stray[rng.integers(0, 20000, 50)] = True
+        xy, lb = X[mine | stray], lab[mine | stray]
+        out, sels = plan.select_ghosts(xy, lb)
+        assert sorted(out) == plan.peers()
+        for q in plan.peers():
+            lo, hi = plan.window(q)
+            ref = torch.nonzero(ghost_mask_for(xy[:, 1], plan.oy, plan.h, plan.yperiodic, plan.yperiod, lo, hi)).squeeze(1)
+            assert torch.equal(sels[q], ref), (rank, q)
+            assert torch.equal(out[q][:, 2].to(torch.int64), lb[sels[q]])
