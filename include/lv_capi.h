@@ -92,7 +92,12 @@ int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap
                          double *centroid);
 /* Lazy edge view: after lv_set_async_edges(h, 1), lv_remesh / lv_mesh_download return once rowptr, areas and centroids
  * are on the host and copy the 40-byte edge records on a second stream, overlapping whatever runs next (typically
- * find_pressure!); the host must call lv_mesh_wait before it reads the edge buffer.  The buffer should be pinned. */
+ * find_pressure!); the host must call lv_mesh_wait before it reads the edge buffer.  The buffer should be pinned.
+ * While such a copy is in flight the copy engine is busy, so rowptr / area / centroid (lv_remesh) and P (lv_find_pressure,
+ * lv_pressure_download) are written straight into the caller's buffers by the conversion kernels when those buffers are
+ * pinned (cudaHostAlloc / cudaHostRegister: mapped under UVA); pageable buffers take the ordinary cudaMemcpy path.
+ * Environment switches (diagnostics): LV_DIRECT_STORE=0 disables the direct stores, LV_FLAG_MODE=memcpy reads status
+ * words with cudaMemcpy instead of mapped memory. */
 int32_t lv_set_async_edges(LvHandle h, int32_t on);
 int32_t lv_mesh_wait(LvHandle h);
 /* which kernel produced the current mesh: level 0/1 = linked-slot kernel (12/16 slots), 2/3/4 =

@@ -49,6 +49,19 @@ mutable struct DeviceContext
     fields::Dict{Symbol,Vector}  # gather / scatter staging for the pressure solve
 end
 
+# Page-lock a staging vector so that the library can DMA from / store into it directly (full PCIe rate, and the direct
+# stores described at lv_set_async_edges in include/lv_capi.h).  Re-registered when `resize!` moved the buffer.
+const CUDART = get(ENV, "LVB200_CUDART", "libcudart.so")
+const PINNED = IdDict{Any,Tuple{Ptr{Cvoid},Int}}()
+function pin!(v::Vector)
+    p, nb = Ptr{Cvoid}(pointer(v)), sizeof(v)
+    old = get(PINNED, v, (C_NULL, 0))
+    old == (p, nb) && return v
+    old[1] != C_NULL && ccall((:cudaHostUnregister, CUDART), Int32, (Ptr{Cvoid},), old[1])
+    nb > 0 && ccall((:cudaHostRegister, CUDART), Int32, (Ptr{Cvoid}, Csize_t, UInt32), p, nb, 0x01) == 0 && (PINNED[v] = (p, nb))
+    return v
+end
+
 const CONTEXTS = IdDict{Any,DeviceContext}()
 const DEVICE = Ref{Int32}(0)
 const ENABLED = Ref(false)
@@ -84,6 +97,7 @@ function remesh_b200!(grid::VoronoiGrid)
     n = length(grid.polygons)
     resize!(ctx.xy, n); resize!(ctx.rowptr, n + 1); resize!(ctx.area, n); resize!(ctx.centroid, n)
     length(ctx.edges) < 7n + 64 && resize!(ctx.edges, 7n + 64)
+    foreach(pin!, (ctx.xy, ctx.rowptr, ctx.area, ctx.centroid, ctx.edges))
     Threads.@threads for i in 1:n
         @inbounds ctx.xy[i] = grid.polygons[i].x
     end
@@ -145,6 +159,7 @@ function find_pressure_b200!(solver::PressureSolver, dt::Float64, niter::Int64 =
     n = length(grid.polygons)
     mass = staging(ctx, :mass, Float64, n); rho = staging(ctx, :rho, Float64, n); c2 = staging(ctx, :c2, Float64, n)
     P = staging(ctx, :P, Float64, n); v = staging(ctx, :v, RealVector, n)
+    foreach(pin!, (mass, rho, c2, P, v))
     Threads.@threads for i in 1:n
         @inbounds begin
             p = grid.polygons[i]
