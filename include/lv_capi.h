@@ -164,6 +164,9 @@ int32_t lv_step_pressure_step(LvHandle h, double dt);                  /* pressu
 int32_t lv_step_gravity(LvHandle h, double gx, double gy, double dt);  /* gravity_step!            pressure.jl:77-82 */
 int32_t lv_step_find_D(LvHandle h);                                    /* find_D!                  diffusion.jl:8-19 */
 int32_t lv_step_viscous_step(LvHandle h, double dt, int32_t artificial_viscosity); /* viscous_step! diffusion.jl:39-53 */
+/* bdary_friction!(grid, vDirichlet, dt) diffusion.jl:64-80; vwall[4][2] = the closure's value on the walls UP, RIGHT, DOWN, LEFT
+ * (NULL = all walls at rest), charfun = everywhere */
+int32_t lv_step_bdary_friction(LvHandle h, double dt, const double *vwall);
 int32_t lv_step_find_dv(LvHandle h, double dt, double alpha);          /* find_dv!                 relaxation.jl:10-25 */
 int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* relaxation_step!       relaxation.jl:36-73 (remeshes) */
 /* multiphase_projection!(solver) (relaxation.jl:179-206; MultiphaseProjector mul! :91-123, refresh! :162-177).  Reference

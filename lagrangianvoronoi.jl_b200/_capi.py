@@ -27,7 +27,7 @@ SYMBOLS = [
     "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
     "lv_halo_plan", "lv_halo_exchange_dev", "lv_peer_export", "lv_peer_plan", "lv_mailbox_export", "lv_mailbox_plan", "lv_peer_disable",
     "lv_state_set", "lv_state_get", "lv_state_ptr", "lv_state_remesh", "lv_step_move", "lv_step_eos", "lv_step_find_pressure",
-    "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection",
+    "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_bdary_friction", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection",
 ]
 
 
@@ -127,6 +127,7 @@ def load_library() -> C.CDLL:
     L.lv_step_gravity.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.lv_step_find_D.argtypes = [vp]
     L.lv_step_viscous_step.argtypes = [vp, C.c_double, C.c_int32]
+    L.lv_step_bdary_friction.argtypes = [vp, C.c_double, C.c_void_p]
     L.lv_step_find_dv.argtypes = [vp, C.c_double, C.c_double]
     L.lv_step_relaxation_step.argtypes = [vp, C.c_double, C.c_int32]
     L.lv_step_lloyd.argtypes = [vp, C.c_int32]

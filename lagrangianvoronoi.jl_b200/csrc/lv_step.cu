@@ -8,6 +8,7 @@
 //   pressure_step!     pressure.jl:10-25       gravity_step!                 pressure.jl:77-82
 //   find_D!            diffusion.jl:8-19       viscous_step!                 diffusion.jl:39-53
 //   find_dv!           relaxation.jl:10-25     relaxation_step!              relaxation.jl:36-73
+//   bdary_friction!    diffusion.jl:64-80
 // Every sweep is one thread per polygon walking its CSR row (slot = prim_of_label[label]); neighbour fields
 // are read by label.  Expressions keep the reference's association (compiled with -fmad=false), so results
 // agree with the CPU restatement to rounding of the sums' inputs, i.e. bit for bit in practice.
@@ -88,6 +89,42 @@ __global__ void __launch_bounds__(ST_BLOCK) k_move(StepView S, double dt, double
     v = make_double2(0.0, 0.0);
     if (try_move(S, bminx, bminy, bmaxx, bmaxy, x, v, dt, nx)) S.x[i] = nx;
     S.v[i] = v;
+}
+
+// ---- bdary_friction!  diffusion.jl:64-80 ---------------------------------------------------------------------
+// vDirichlet is a closure in the reference; the ABI takes the per-wall constants the examples use (cavity.jl:41-44),
+// indexed by -label-1 = UP, RIGHT, DOWN, LEFT.  Only the polygon's own fields are touched.
+struct WallVel { double v[8]; };
+__global__ void __launch_bounds__(ST_BLOCK) k_bdary_friction(StepView S, double dt, WallVel w) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    const int s = S.prim[i];
+    if (s < 0) return;
+    const double2 x = S.x[i];
+    double2 v = S.v[i];
+    const double mu = S.mu[i], mass = S.mass[i];
+    double e = S.e[i], tmp = 1.0;
+    const int r0 = S.rowptr[s], d = S.rdeg[s];
+    for (int k = r0; k < r0 + d; k++) {
+        const int lab = S.col[k];
+        if (lab >= 0) continue; // boundaries(p): wall codes are negative
+        const double2 a = S.v1[k], b = S.v2[k];
+        const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y);
+        double nx = a.y - b.y, ny = b.x - a.x; // normal_vector  polygon.jl:153-156
+        const double nn = sqrt(nx * nx + ny * ny);
+        nx /= nn; ny /= nn;
+        const double ex = a.x - b.x, ey = a.y - b.y;
+        const double lrr = sqrt(ex * ex + ey * ey) / fabs((mx - x.x) * nx + (my - x.y) * ny);
+        const double c = mu * lrr;
+        const int wk = (lab >= -4) ? -lab - 1 : -1;
+        const double vdx = wk >= 0 ? w.v[2 * wk] : 0.0, vdy = wk >= 0 ? w.v[2 * wk + 1] : 0.0;
+        const double fx = (c * vdx) / mass, fy = (c * vdy) / mass;
+        tmp += ((dt * mu) * lrr) / mass;
+        e += dt * (fx * v.x + fy * v.y);
+        v = make_double2(v.x + dt * fx, v.y + dt * fy);
+    }
+    S.e[i] = e;
+    S.v[i] = make_double2(v.x / tmp, v.y / tmp);
 }
 
 // ---- EOS  pressure.jl:32-70 ----------------------------------------------------------------------------
@@ -532,6 +569,18 @@ int32_t lv_step_viscous_step(LvHandle c, double dt, int32_t artificial_viscosity
         k_viscous_e<<<GRID(S.n)>>>(S, dt, avdr);
         c->launches += 2;
     }
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+int32_t lv_step_bdary_friction(LvHandle c, double dt, const double *vwall) { // bdary_friction!  diffusion.jl:64-80
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(need_mesh(c));
+    StepView S = make_view(c);
+    WallVel w;
+    for (int k = 0; k < 8; k++) w.v[k] = vwall ? vwall[k] : 0.0;
+    if (S.n > 0) { k_bdary_friction<<<GRID(S.n)>>>(S, dt, w); c->launches++; }
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
 }

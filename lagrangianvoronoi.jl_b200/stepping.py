@@ -108,6 +108,15 @@ def viscous_step(grid: VoronoiGrid, dt: float, artificial_viscosity: bool = True
     check(grid._L.lv_step_viscous_step(grid._h, float(dt), int(artificial_viscosity)), grid._h)
 
 
+def bdary_friction(grid: VoronoiGrid, dt: float, vwall=None) -> None:
+    """bdary_friction!(grid, vDirichlet, dt)  diffusion.jl:64-80.  ``vwall[4][2]``: the Dirichlet velocity on the walls
+    UP, RIGHT, DOWN, LEFT (the reference's closure evaluated per wall, e.g. the lid of examples/cavity.jl:41-44)."""
+    vw = np.ascontiguousarray(np.zeros((4, 2)) if vwall is None else vwall, dtype=np.float64)
+    if vw.shape != (4, 2):
+        raise ValueError("vwall must have shape (4, 2)")
+    check(grid._L.lv_step_bdary_friction(grid._h, float(dt), vw.ctypes.data), grid._h)
+
+
 def find_dv(grid: VoronoiGrid, dt: float, alpha: float = 1.0) -> None:
     check(grid._L.lv_step_find_dv(grid._h, float(dt), float(alpha)), grid._h)
 

@@ -1066,6 +1066,32 @@ void lvo_viscous_step(lvo_grid *g, double dt, int artificial_viscosity) { /* dif
     }
 }
 
+/* diffusion.jl:55-80 bdary_friction!: viscous drag of the walls (Dirichlet condition for a tangential wall velocity).
+ * vDirichlet is a closure in the reference; here it is the per-wall constant vwall[-label-1] (what examples/cavity.jl:41-44
+ * evaluates to), charfun = everywhere. */
+void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < g->n; i++) {
+        poly_t *p = g->polygons[i];
+        double tmp = 1.0;
+        for (int64_t k = 0; k < p->edges.last; k++) { /* boundaries(p): iterators.jl:50-57 */
+            edge_t e = p->edges.data[k];
+            if (!(e.label <= 0)) continue;
+            vec2 m = vscale(0.5, vadd(e.v1, e.v2));
+            vec2 nv = normal_vector(e);
+            double lrr = len_e(e) / fabs(vdot(vsub(m, p->x), nv));
+            vec2 vd = V(0.0, 0.0);
+            if (vwall && e.label < 0 && e.label >= -4) vd = V(vwall[2 * (-e.label - 1)], vwall[2 * (-e.label - 1) + 1]);
+            double c = p->mu * lrr;
+            vec2 f = V((c * vd.x) / p->mass, (c * vd.y) / p->mass);
+            tmp += ((dt * p->mu) * lrr) / p->mass;
+            p->e += dt * vdot(f, p->v);
+            p->v = V(p->v.x + dt * f.x, p->v.y + dt * f.y);
+        }
+        p->v = V(p->v.x / tmp, p->v.y / tmp);
+    }
+}
+
 /* ------------------------------------------------------------------ relaxation.jl:10-73 */
 void lvo_find_dv(lvo_grid *g, double dt, double alpha) { /* relaxation.jl:10-25 */
 #pragma omp parallel for schedule(static)

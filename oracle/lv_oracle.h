@@ -89,6 +89,7 @@ void lvo_ideal_eos(lvo_grid *g, double gamma, double Pmin);       /* pressure.jl
 void lvo_pressure_step(lvo_grid *g, double dt);                   /* pressure.jl:10-25 */
 void lvo_find_D(lvo_grid *g);                                     /* diffusion.jl:8-19 */
 void lvo_viscous_step(lvo_grid *g, double dt, int artificial_viscosity); /* diffusion.jl:39-53 */
+void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall); /* diffusion.jl:64-80; vwall[4][2] by -label-1 */
 void lvo_find_dv(lvo_grid *g, double dt, double alpha);           /* relaxation.jl:10-25 */
 int lvo_relaxation_step(lvo_grid *g, double dt, int rusanov);     /* relaxation.jl:36-73 */
 

@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         L.lvo_pressure_step.argtypes = [vp, C.c_double]
         L.lvo_find_D.argtypes = [vp]
         L.lvo_viscous_step.argtypes = [vp, C.c_double, C.c_int]
+        L.lvo_bdary_friction.argtypes = [vp, C.c_double, C.c_void_p]
         L.lvo_find_dv.argtypes = [vp, C.c_double, C.c_double]
         L.lvo_relaxation_step.argtypes = [vp, C.c_double, C.c_int]
         L.lvo_multiphase_projection.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -254,6 +255,11 @@ class OracleGrid:
 
     def viscous_step(self, dt, artificial_viscosity=True):
         lib().lvo_viscous_step(self._g, float(dt), int(artificial_viscosity))
+
+    def bdary_friction(self, dt, vwall=None):
+        """diffusion.jl:64-80 with per-wall constant Dirichlet velocities vwall[4][2] (UP, RIGHT, DOWN, LEFT)."""
+        vw = np.ascontiguousarray(np.zeros((4, 2)) if vwall is None else vwall, dtype=np.float64)
+        lib().lvo_bdary_friction(self._g, float(dt), vw.ctypes.data)
 
     def find_dv(self, dt, alpha=1.0):
         lib().lvo_find_dv(self._g, float(dt), float(alpha))

@@ -212,3 +212,37 @@ def test_random_clouds_property(oracle):
             assert np.array_equal(e["v2"], np.roll(e["v1"], -1, axis=0))
 
     prop()
+
+
+def test_bdary_friction_relaxes_wall_cells_towards_the_wall_velocity(oracle):
+    """diffusion.jl:64-80: v <- (v + dt*sum f)/(1 + dt*sum mu*lrr/m) on cells with wall edges, untouched elsewhere;
+    with a large dt the wall cells take the wall's velocity, and e picks up dt*f.v (velocity before the update)."""
+    xy, dr, bmin, bmax = make_points("poisson", 24, 2)
+    og = oracle.OracleGrid(bmin, bmax, dr)
+    og.set_points(xy); assert og.remesh() == 0
+    n = len(xy)
+    rng = np.random.default_rng(0)
+    v0 = rng.standard_normal((n, 2))
+    og.set("v", v0); og.set("mass", og.area().copy()); og.set("mu", np.full(n, 0.01)); og.set("e", np.zeros(n))
+    rowptr, edges = og.mesh()
+    wall = np.array([(edges["label"][rowptr[i]:rowptr[i + 1]] <= 0).any() for i in range(n)])
+    top_only = np.array([set(edges["label"][rowptr[i]:rowptr[i + 1]][edges["label"][rowptr[i]:rowptr[i + 1]] <= 0]) == {-1} for i in range(n)])
+    vwall = np.array([[1.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]])
+    og.bdary_friction(1e-3, vwall)
+    v1, e1 = og.get("v"), og.get("e")
+    assert np.array_equal(v1[~wall], v0[~wall]) and (e1[~wall] == 0).all()
+    assert (np.abs(v1[wall] - v0[wall]).max(1) > 0).all()
+    # one cell with a single lid edge, by hand
+    i = int(np.nonzero(top_only)[0][0])
+    e = edges[rowptr[i]:rowptr[i + 1]]
+    e = e[e["label"] == -1][0]
+    m = 0.5 * (e["v1"] + e["v2"])
+    nv = np.array([e["v1"][1] - e["v2"][1], e["v2"][0] - e["v1"][0]]); nv = nv / np.sqrt((nv ** 2).sum())
+    lrr = np.sqrt(((e["v1"] - e["v2"]) ** 2).sum()) / abs(((m - xy[i]) * nv).sum())
+    mass = og.get("mass")[i]
+    f = 0.01 * lrr * vwall[0] / mass
+    want = (v0[i] + 1e-3 * f) / (1.0 + 1e-3 * 0.01 * lrr / mass)
+    assert np.allclose(v1[i], want, rtol=1e-14) and np.isclose(e1[i], 1e-3 * (f * v0[i]).sum(), rtol=1e-13)
+    # stiff limit: the wall wins
+    og.set("v", v0); og.bdary_friction(1e9, vwall)
+    assert np.allclose(og.get("v")[top_only], vwall[0], atol=1e-6)

@@ -52,6 +52,9 @@ def test_explicit_sweeps_match_oracle(lv, oracle, kind, n_side, xper, yper):
     assert np.allclose(S.state_get(g, "D"), og.get("D"), rtol=1e-12, atol=1e-12 * np.abs(og.get("D")).max())
     S.viscous_step(g, dt, True); og.viscous_step(dt, True)
     _compare(lv, g, og, ["v", "e"])
+    vwall = np.array([[1.0, 0.0], [0.0, -0.5], [0.25, 0.0], [0.0, 0.0]])     # lid + moving side walls (cavity.jl:41-44)
+    S.bdary_friction(g, dt, vwall); og.bdary_friction(dt, vwall)
+    _compare(lv, g, og, ["v", "e"])
     S.find_dv(g, dt, 1.0); og.find_dv(dt, 1.0)
     _compare(lv, g, og, ["dv", "quality"])
     S.relaxation_step(g, dt, True); assert og.relaxation_step(dt, True) == 0
