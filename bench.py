@@ -230,7 +230,6 @@ def run_ours(args):
         parallelism = (f"{world} y-strips ({args.scaling} scaling), ghost generators by torch.distributed send/recv per remesh, "
                        f"CG halo = {'ncclSend/Recv + 2-scalar ncclAllReduce per dot product' if not sg.use_peer_memory else 'NVLink peer-memory loads (CUDA IPC) + 2-scalar all-reduce through peer mailboxes fused into the scalar kernel'}; "
                        f"halo (send, recv) per peer = {sg.halo_counts}")
-        args.no_e2e = True  # the host-buffer drop-in API is single-GPU (one Julia process, one GPU)
 
         phase_ev = []
 
@@ -295,7 +294,7 @@ def run_ours(args):
     ms_max = float(t.item())
 
     e2e = None
-    if not args.no_e2e:
+    if world == 1 and not args.no_e2e:
         # every step must solve the same problem (cold P), so the initial P is staged once per step in pinned host memory
         # outside the timed region -- a user's P is simply wherever their arrays are; no reset copy belongs to the step
         from lvb200.host import _host_empty
@@ -322,53 +321,123 @@ def run_ours(args):
         e2e = {"value": n_total * args.steps / (float(te.item()) / 1e3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / args.steps}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    hbm, peak_src = peaks()
-    mv_ms, mv_launched = prof["matvec"]
-    # launches that did work: one per CG iteration plus the initial residual of each of the niter passes
-    # (launches queued behind the convergence flag exit at once; their time stays in the numerator)
-    mv_cnt = iters_total + args.niter * args.steps
-    mv_avg = mv_ms / max(mv_cnt, 1)
-    achieved = MATVEC_BYTES_PER_CELL * n / (mv_avg * 1e-3) / 1e9 if mv_avg > 0 else 0.0
-    traffic = None
-    try:  # DRAM bytes per launch measured once with ncu --set full (profiles/), scaled to this run's cell count
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)["k_matvec"]
-        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["cells"]
-    except Exception:
-        pass
-    rem_ms = prof["cells"][0] + prof["clip"][0]
-    pr_ms = prof["assemble"][0] + prof["matvec"][0] + prof["vecops"][0]
-    line = {
-        "metric": METRIC, "value": n_total * args.steps / (ms_max / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic periodic random-jittered box, {n_total} cells over {world} GPU(s) (lattice side M={M}), dr=1/{M}, h=2dr, r_max=10dr, "
-                               f"Taylor-Green v/P, rho=1, c0={args.c0}, dt=0.1dr; step = 2 x remesh + find_pressure(niter={args.niter}, "
-                               f"CG rtol=atol=1e-6, itmax=1000)",
-                   "cells_total": n_total, "cells_rank0": n, "parallelism": parallelism,
-                   "l2": "inputs larger than L2 (no flush needed)", "krylov_iters_per_step": iters_total // args.steps},
-        "submetrics": {"remesh_mcells_s": 2 * n_total * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
-                       "cg_mcell_iters_s": n_total * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
-                       "s_per_step": ms_max / args.steps / 1e3, "wall_phase_ms_per_step_rank0": wall_phases,
-                       "phase_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()},
-                                                 host_and_exchange=(ms_max - sum(v[0] for v in prof.values())) / args.steps)},
-        "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
-                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if hbm else None, "peak_source": peak_src,
-                     "frac_of_nominal_8TBs": achieved / 8000.0, "avg_launch_ms": mv_avg, "launches": mv_cnt, "launches_queued": mv_launched,
-                     "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_CELL * n, "traffic": traffic},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
-    }
-    if world == 1 and not args.no_cpu:
-        res = cpu_step_rate(args.cpu_side, args.c0, args.niter, args.seed, 1)
-        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line["cpu_baseline"]["detail"] = {k: res[k] for k in ("remesh_mcells_s", "krylov_mcell_iters_s", "s_per_step_sample")}
-    emit(line)
+    line = None
+    if rank == 0:
+        hbm, peak_src = peaks()
+        mv_ms, mv_launched = prof["matvec"]
+        # launches that did work: one per CG iteration plus the initial residual of each of the niter passes
+        # (launches queued behind the convergence flag exit at once; their time stays in the numerator)
+        mv_cnt = iters_total + args.niter * args.steps
+        mv_avg = mv_ms / max(mv_cnt, 1)
+        achieved = MATVEC_BYTES_PER_CELL * n / (mv_avg * 1e-3) / 1e9 if mv_avg > 0 else 0.0
+        traffic = None
+        try:  # DRAM bytes per launch measured once with ncu --set full (profiles/), scaled to this run's cell count
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                t = json.load(f)["k_matvec"]
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * n / t["cells"]
+        except Exception:
+            pass
+        rem_ms = prof["cells"][0] + prof["clip"][0]
+        pr_ms = prof["assemble"][0] + prof["matvec"][0] + prof["vecops"][0]
+        line = {
+            "metric": METRIC, "value": n_total * args.steps / (ms_max / 1e3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic periodic random-jittered box, {n_total} cells over {world} GPU(s) (lattice side M={M}), dr=1/{M}, h=2dr, r_max=10dr, "
+                                   f"Taylor-Green v/P, rho=1, c0={args.c0}, dt=0.1dr; step = 2 x remesh + find_pressure(niter={args.niter}, "
+                                   f"CG rtol=atol=1e-6, itmax=1000)",
+                       "cells_total": n_total, "cells_rank0": n, "parallelism": parallelism,
+                       "l2": "inputs larger than L2 (no flush needed)", "krylov_iters_per_step": iters_total // args.steps},
+            "submetrics": {"remesh_mcells_s": 2 * n_total * args.steps / (rem_ms / 1e3) / 1e6 if rem_ms > 0 else None,
+                           "cg_mcell_iters_s": n_total * iters_total / (pr_ms / 1e3) / 1e6 if pr_ms > 0 else None,
+                           "s_per_step": ms_max / args.steps / 1e3, "wall_phase_ms_per_step_rank0": wall_phases,
+                           "phase_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()},
+                                                     host_and_exchange=(ms_max - sum(v[0] for v in prof.values())) / args.steps)},
+            "roofline": {"kernel": "k_matvec (CSR Voronoi-Laplacian matvec + fused p.Ap)", "bound": "hbm", "achieved": achieved,
+                         "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if hbm else None, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "avg_launch_ms": mv_avg, "launches": mv_cnt, "launches_queued": mv_launched,
+                         "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_CELL * n, "traffic": traffic},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            res = cpu_step_rate(args.cpu_side, args.c0, args.niter, args.seed, 1)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["detail"] = {k: res[k] for k in ("remesh_mcells_s", "krylov_mcell_iters_s", "s_per_step_sample")}
+    if world > 1 and not args.no_e2e:
+        e2e = e2e_strips(args, lv, sg, solver, g, dev, stream, rank, world, dt, n_total, line)
+        if rank == 0:
+            line["e2e"] = e2e
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_strips(args, lv, sg, solver, g, dev, stream, rank, world, dt, n_total, line):
+    """End-to-end leg of the strip (multi-GPU) API: every step each rank uploads its owned positions and the fields of
+    its local generator list from pinned host memory, remeshes twice (per-cell rowptr / areas / centroids come back to the
+    host each time; the edge records stay in HBM -- the strip API has no host-side polygon objects to fill), solves, and
+    reads P back.  A watchdog ends the run with ``e2e: null`` rather than hanging the job if a rank falls out."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    from lvb200._capi import check, ptr
+    from lvb200.host import _host_empty
+
+    def bail():
+        if rank == 0 and line is not None:
+            line["e2e"] = None
+            line["e2e_note"] = "multi-GPU e2e leg did not finish within its time limit"
+            emit(line)
+        os._exit(0)
+
+    dog = threading.Timer(240.0, bail)
+    dog.daemon = True
+    dog.start()
+    n_own, n_loc = int(sg.xy_own.shape[0]), int(sg.n_loc)
+    xy_h = _host_empty((n_own, 2), np.float64)
+    xy_h[...] = sg.xy_own.cpu().numpy()
+    lab_own = sg.lab_own
+    xy_loc = sg.xy_loc.cpu().numpy()
+    v, P = lv.synthetic.taylor_green_fields(xy_loc)
+    _, _, area, _ = sg.mesh_download(edges=False)
+    src = {"mass": np.where(area > 0, area, 1.0), "rho": np.ones(n_loc), "c2": np.full(n_loc, args.c0 ** 2), "P": P, "v": v}
+    f_h = {}
+    for k, a in src.items():
+        f_h[k] = _host_empty(a.shape, np.float64)
+        f_h[k][...] = a
+    rowptr_h, area_h, cen_h = _host_empty((n_loc + 1,), np.int64), _host_empty((n_loc,), np.float64), _host_empty((n_loc, 2), np.float64)
+    P_h = _host_empty((n_loc,), np.float64)
+
+    def step():
+        sg.xy_own = torch.from_numpy(xy_h).to(dev, non_blocking=True)
+        sg.lab_own = lab_own
+        for _ in range(2):
+            sg.remesh()
+            check(g._L.lv_mesh_download(g._h, ptr(rowptr_h), None, 0, ptr(area_h), ptr(cen_h)), g._h)
+        solver.upload_fields(f_h["mass"], f_h["rho"], f_h["c2"], f_h["P"], f_h["v"], device=False)
+        solver.find_pressure_dev(dt, args.niter)
+        solver.download_P(out=P_h)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    te = torch.tensor([1e3 * (time.perf_counter() - t0)], device=dev, dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    byt = torch.tensor([n_own * 16 + n_loc * 48, 2 * ((n_loc + 1) * 8 + n_loc * 24) + n_loc * 8], device=dev, dtype=torch.int64)
+    dist.all_reduce(byt)
+    dog.cancel()
+    ms = float(te.item())
+    return {"value": n_total * args.steps / (ms / 1e3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(byt[0]),
+            "d2h_bytes_per_step": int(byt[1]), "ms_per_step": ms / args.steps,
+            "note": "strip API: positions + fields up, rowptr/area/centroid (x2) + P down per rank; edge records stay in HBM"}
 
 
 def emit(line: dict) -> None:
