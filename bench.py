@@ -320,6 +320,15 @@ def run_ours(args):
         d2h = 2 * ((n + 1) * 8 + nnz * 40 + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
         e2e = {"value": n_total * args.steps / (float(te.item()) / 1e3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / args.steps}
+        # size-independent properties of the result at the full bench size, checked on the host copies after the timed
+        # region: Euler count of a periodic triangulation (sum of degrees = 6n), the cells tile the unit box, every
+        # pass converged, pressures are finite
+        try:
+            e2e["checks"] = {"euler_sum_deg_eq_6n": bool(nnz == 6 * n), "area_sum_minus_1": float(lv.area(g).sum() - 1.0),
+                             "all_passes_converged": bool((solver.iters < 1000).all()), "P_finite": bool(np.isfinite(g.P).all()),
+                             "labels_in_range": bool(g.edges["label"].min() >= 1 and g.edges["label"].max() <= n)}
+        except Exception as ex:  # never lose the measurement over a check
+            e2e["checks"] = {"error": repr(ex)}
 
     line = None
     if rank == 0:

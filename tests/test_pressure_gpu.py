@@ -103,10 +103,10 @@ def test_find_pressure_with_walls_and_moving_lid(lv, oracle):
     assert np.abs(g.P - P_ref).max() <= 1e-8 * np.abs(P_ref).max()
 
 
-def test_reference_default_tolerances_converge(lv):
-    """Reference settings (atol = rtol = 1e-6, itmax = 1000, niter = 10) at 256k cells: every pass
-    converges and the true residual is small; linearity of the operator as a size-independent check."""
-    M = 512
+@pytest.mark.parametrize("M", [512, 2048])
+def test_reference_default_tolerances_converge(lv, M):
+    """Reference settings (atol = rtol = 1e-6, itmax = 1000, niter = 10) at 256k and 4M cells: every pass
+    converges and the true residual is small; linearity and symmetry of the operator as size-independent checks."""
     xy = lv.synthetic.jittered_lattice(M, 0)
     g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1.0 / M, xperiodic=True, yperiodic=True)
     g.set_points(xy); lv.remesh(g)

@@ -76,9 +76,10 @@ def test_both_kernels_agree_and_fast_path_is_used(lv, oracle, monkeypatch):
             assert f[4] == (0, 0) or f[4] == (1, 0), f[4]     # no anomaly, linked-slot kernel
 
 
-def test_remesh_invariants_at_scale(lv):
-    """1M cells: size-independent properties (no oracle needed): torus Euler count, tiling, symmetry."""
-    M = 1024
+@pytest.mark.parametrize("M", [1024, 2048])
+def test_remesh_invariants_at_scale(lv, M):
+    """1M and 4M cells (the size of BASELINE's taylorgreen / rayleightaylor configs): size-independent properties, no
+    oracle needed: torus Euler count, tiling, symmetric adjacency, idempotence."""
     xy = lv.synthetic.jittered_lattice(M, 0)
     g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1.0 / M, xperiodic=True, yperiodic=True)
     g.set_points(xy)
