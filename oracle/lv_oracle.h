@@ -10,7 +10,9 @@
  * golden vectors for this path.  The restatement is pinned only by
  *   (1) the reference's single integration test thresholds
  *       (tests/taylorgreen.jl:112-114, restated in tests/test_oracle_taylorgreen.py),
- *   (2) invariants derived from the reference's definitions.
+ *   (2) the semi-analytic Sedov profile the reference ships for examples/sedov.jl
+ *       (examples/reference/sedov.csv; tests/test_oracle.py::test_sedov_blast_*), a physics-level pin,
+ *   (3) invariants derived from the reference's definitions.
  * The Krylov.jl 0.9.8 MINRES iteration (Manifest.toml:465-469) is un-vendored
  * third-party code restated from its published algorithm: iterate-level
  * "parity unpinned".  Solution-level parity is solver independent.

@@ -246,3 +246,30 @@ def test_bdary_friction_relaxes_wall_cells_towards_the_wall_velocity(oracle):
     # stiff limit: the wall wins
     og.set("v", v0); og.bdary_friction(1e9, vwall)
     assert np.allclose(og.get("v")[top_only], vwall[0], atol=1e-6)
+
+
+def test_sedov_blast_matches_the_references_semi_analytic_profile(oracle):
+    """examples/sedov.jl (one of BASELINE's configs) at N = 40 through the restatement: walls, ideal EOS, artificial
+    viscosity, adaptive dt.  The reference plots its result against examples/reference/sedov.csv; the same comparison
+    here pins the compressible path of the oracle to the reference's own fixture: shock position, wake profile,
+    undisturbed gas ahead of the shock, and total energy conserved to rounding."""
+    from . import sedov_case as S
+    N = 40
+    dr = 1.0 / N
+    og = oracle.OracleGrid((-1.0, -1.0), (1.0, 1.0), dr)
+    assert og.populate_hex() == 0                                       # sedov.jl:96
+    for k, val in S.initial_fields(og.get("x"), og.area()).items():
+        og.set(k, val)
+    E0 = (og.get("mass") * og.get("e")).sum()
+    for dt in S.time_steps(dr):                                          # step!  sedov.jl:106-118
+        assert og.move(dt) == 0
+        og.ideal_eos(S.GAMMA, S.P0)
+        og.find_pressure(dt, 10, solver="minres")
+        og.pressure_step(dt)
+        og.find_D(); og.viscous_step(dt, True)
+        og.find_dv(dt, 1.0)
+        assert og.relaxation_step(dt, True) == 0
+    assert abs((og.get("mass") * og.get("e")).sum() - E0) < 1e-13
+    c = S.compare_with_reference(og.get("x"), og.get("rho"), dr)
+    assert abs(c["r_shock"] - c["r_shock_ref"]) <= 2.0 * dr, c
+    assert c["peak"] > 3.0 and c["wake_rel_err"] < 0.10 and c["ahead_err"] < 1e-3, c

@@ -1,5 +1,7 @@
 """GPU parity tests of the device-resident explicit sweeps against the oracle, and the
 reference's own integration test (tests/taylorgreen.jl) run end to end on the GPU path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -201,3 +203,37 @@ def test_rayleigh_taylor_steps_match_oracle(lv, oracle):
     for nm in ("x", "v", "e", "mass"):
         a, b = S.state_get(g, nm), og.get(nm)
         assert np.abs(a - b).max() <= 1e-7 * np.abs(b).max(), nm
+
+
+@pytest.mark.skipif(os.environ.get("LV_RUN_SEDOV_GPU", "0") != "1",
+                    reason="written at the end of round 1 after the GPU budget ran out: not yet run on hardware "
+                           "(the same case passes on the CPU restatement, tests/test_oracle.py); set LV_RUN_SEDOV_GPU=1")
+def test_sedov_blast_on_the_gpu(lv, oracle):
+    """examples/sedov.jl (BASELINE config) at N = 40, every operator of the step on the GPU (CG pressure solve): same
+    comparison with the reference's semi-analytic profile as tests/test_oracle.py runs on the restatement."""
+    from . import sedov_case as C
+    S = lv.stepping
+    N = 40
+    dr = 1.0 / N
+    og = oracle.OracleGrid((-1.0, -1.0), (1.0, 1.0), dr)
+    assert og.populate_hex() == 0                                       # seeding only (populate.jl:149-174)
+    xy = og.get("x")
+    g = lv.VoronoiGrid(lv.Rectangle((-1.0, -1.0), (1.0, 1.0)), dr)
+    g.set_points(xy)
+    lv.remesh(g, edges=False)
+    for k, val in C.initial_fields(xy, lv.area(g).copy()).items():
+        getattr(g, k)[...] = val
+    E0 = (g.mass * g.e).sum()
+    S.to_device(g)
+    solver = lv.PressureSolver(g)
+    for dt in C.time_steps(dr):
+        S.move(g, dt)
+        S.ideal_eos(g, C.GAMMA, C.P0)
+        S.find_pressure_resident(solver, dt)
+        S.pressure_step(g, dt); S.find_D(g); S.viscous_step(g, dt, True); S.find_dv(g, dt)
+        S.relaxation_step(g, dt)
+    S.from_device(g)
+    assert abs((g.mass * g.e).sum() - E0) < 1e-13
+    c = C.compare_with_reference(g.x, g.rho, dr)
+    assert abs(c["r_shock"] - c["r_shock_ref"]) <= 2.0 * dr, c
+    assert c["peak"] > 3.0 and c["wake_rel_err"] < 0.10 and c["ahead_err"] < 1e-3, c
