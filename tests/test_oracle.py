@@ -273,3 +273,30 @@ def test_sedov_blast_matches_the_references_semi_analytic_profile(oracle):
     c = S.compare_with_reference(og.get("x"), og.get("rho"), dr)
     assert abs(c["r_shock"] - c["r_shock_ref"]) <= 2.0 * dr, c
     assert c["peak"] > 3.0 and c["wake_rel_err"] < 0.10 and c["ahead_err"] < 1e-3, c
+
+
+def test_gresho_vortex_stays_steady_and_converges(oracle):
+    """examples/gresho.jl (BASELINE config 0: walls, ideal EOS at Ma = 0.1, artificial viscosity) through the
+    restatement to t = 1: the exact solution is the initial condition, so the mass-weighted L2 velocity error
+    (gresho.jl:121-126) must stay small, shrink with resolution, and total energy must be conserved to rounding."""
+    from . import gresho_case as G
+    errs = []
+    for N in (32, 50):
+        dr = 1.0 / N
+        dt = 0.1 * dr
+        og = oracle.OracleGrid(G.BMIN, G.BMAX, dr)
+        og.set_points(G.circ_points(dr)); assert og.remesh() == 0
+        for k, val in G.initial_fields(og.get("x"), og.area()).items():
+            og.set(k, val)
+        E0 = (og.get("mass") * og.get("e")).sum()
+        for _ in range(round(1.0 / dt)):                                  # step!  gresho.jl:101-114
+            assert og.move(dt) == 0
+            og.ideal_eos(G.GAMMA, 0.0)
+            og.find_pressure(dt, 10, solver="minres")
+            og.pressure_step(dt)
+            og.find_D(); og.viscous_step(dt, True)
+            og.find_dv(dt, 1.0)
+            assert og.relaxation_step(dt, True) == 0
+        assert abs((og.get("mass") * og.get("e")).sum() - E0) < 1e-11 * abs(E0)
+        errs.append(G.l2_error(og.get("x"), og.get("v"), og.get("mass")))
+    assert errs[0] < 0.09 and errs[1] < 0.06 and errs[1] < 0.8 * errs[0], errs
