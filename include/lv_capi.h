@@ -104,6 +104,11 @@ int32_t lv_mesh_wait(LvHandle h);
  * edge-list kernel (16/32/128 edges); anomalies = remeshes replayed by the edge-list kernel because
  * the linked-slot kernel met a degenerate configuration (results are identical either way) */
 int32_t lv_clip_info(LvHandle h, int32_t *level, int64_t *anomalies);
+/* Order-independent witness of the connectivity of the rows this handle owns: out[0..3] = 16-bit-chunk sums of
+ * mix64(id_i, id_j) over all (row, edge) pairs, out[4] = number of pairs, out[5] = number of rows; id = 1-based global
+ * label (global_label_dev[local label], NULL: local label + 1; wall codes -1..-4 as they are).  Sums of several ranks
+ * add up, so a strip-decomposed mesh can be compared with the single-GPU mesh without gathering it. */
+int32_t lv_mesh_hash(LvHandle h, const int32_t *global_label_dev, uint64_t out[6]);
 /* face lengths len(e) (geometry.jl:136) and midpoints (geometry.jl:145) in the same CSR order */
 int32_t lv_mesh_faces(LvHandle h, double *length, double *midpoint, int64_t cap);
 
@@ -173,6 +178,9 @@ int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* rela
  * settings: quality_threshold 0.25, atol = rtol = 1e-4, itmax 200; *solved = 0 where the reference would @warn */
 int32_t lv_step_multiphase_projection(LvHandle h, double quality_threshold, double rtol, double atol, int32_t itmax,
                                       int32_t *iters, int32_t *solved);
+/* y = A x with A the MultiphaseProjector (mul!, relaxation.jl:91-123) and b = its right-hand side from the resident dv
+ * (refresh!, :162-177); host vectors in label order, NULL skips.  Exposed for direct operator parity checks. */
+int32_t lv_step_multiphase_apply(LvHandle h, const double *x, double *y, double *b);
 int32_t lv_step_lloyd(LvHandle h, int32_t niter);                      /* populate_lloyd! loop     populate.jl:132-145 */
 
 /* ---- multi-GPU: y-strips, one process per GPU ------------------------------ */
@@ -206,6 +214,8 @@ int32_t lv_mailbox_export(LvHandle h, uint8_t *out64);
 int32_t lv_mailbox_plan(LvHandle h, int32_t nranks, const uint8_t *handles);
 /* back to ncclSend/Recv halos and ncclAllReduce dots (every rank must call it when any rank failed to map a peer) */
 int32_t lv_peer_disable(LvHandle h);
+/* unmap all peer memory (call on every rank, then barrier, then lv_destroy) */
+int32_t lv_peer_close(LvHandle h);
 /* fill the ghost slots of a slot-ordered device vector (ncomp 1 or 2) from their owners */
 int32_t lv_halo_exchange_dev(LvHandle h, double *vec_dev, int32_t ncomp);
 

@@ -287,7 +287,9 @@ int32_t lv_sync(LvHandle c) {
 
 // ---- remesh -----------------------------------------------------------------------------------
 static int ensure_generators(LvContext *c, int64_t n, bool need_xy) {
-    if (n < 0 || n >= (int64_t)0x7fffffff) return lv_set_error(c, LV_EINVAL, "n = %lld out of range", (long long)n);
+    // labels (and the global ordering keys of lv_remesh_owned_dev) are packed as (key << 1 | image bit) into 32 bits by
+    // the bucket sort (lv_cells.cu:k_cells_order), so they must stay below 2^30
+    if (n < 0 || n >= ((int64_t)1 << 30)) return lv_set_error(c, LV_EINVAL, "n = %lld out of range (limit 2^30)", (long long)n);
     if (!c->d_prim_of_label || c->cap_n < n) {
         // grow both label-indexed buffers together so that cap_n describes both
         if (c->d_xy) { LV_CUDA(c, cudaStreamSynchronize(c->stream)); lv_free(c, c->d_xy, sizeof(double2) * (size_t)c->cap_n); c->d_xy = nullptr; }
@@ -303,6 +305,10 @@ static int ensure_generators(LvContext *c, int64_t n, bool need_xy) {
 static int remesh_common(LvContext *c, int64_t n) {
     c->mesh_valid = false;
     c->assembled = false;
+    // the pressure fields live in slot order and every remesh re-sorts the slots: whatever was uploaded before is
+    // permuted garbage now, so the "fields not uploaded" guards of lv_pr_assemble / lv_pr_rhs must fire again
+    c->pr_valid = false;
+    c->bvel_valid = false;
     c->n = n;
     LV_TRY(lv_cells_build(c));
     LV_TRY(lv_clip_run(c));
@@ -538,6 +544,56 @@ int32_t lv_mesh_faces(LvHandle c, double *length, double *midpoint, int64_t cap)
     return LV_OK;
 }
 
+} // extern "C"
+
+// ---- order-independent mesh witness ---------------------------------------------------------------
+// Sum over all owned rows and their edges of mix64(id_i, id_j), id = 1-based GLOBAL label (wall codes stay
+// negative), accumulated as four 16-bit-chunk sums so that partial sums of several ranks can be added with
+// ordinary integer arithmetic.  Equal for any decomposition of the same generator set iff the connectivity is.
+__device__ __forceinline__ unsigned long long lv_mix64(unsigned long long z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+    return z;
+}
+__global__ void __launch_bounds__(256) k_mesh_hash(int nslot, const unsigned char *__restrict__ own, const unsigned *__restrict__ ent_label,
+                                                   const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                   const int *__restrict__ key, unsigned long long *__restrict__ out /*[6]*/) {
+    unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0, cnt = 0, rows = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslot; s += gridDim.x * blockDim.x) {
+        if (!own[s]) continue;
+        rows++;
+        const unsigned li = ent_label[s] & ~LV_IMAGE_BIT;
+        const long long gi = key ? (long long)key[li] : (long long)li + 1;
+        const int r0 = rowptr[s], d = rdeg[s];
+        for (int k = 0; k < d; k++) {
+            const int j = col[r0 + k];
+            long long gj = j;
+            if (j >= 0) { const unsigned lj = ent_label[j] & ~LV_IMAGE_BIT; gj = key ? (long long)key[lj] : (long long)lj + 1; }
+            const unsigned long long h = lv_mix64(lv_mix64((unsigned long long)gi) ^ ((unsigned long long)gj * 0x9E3779B97F4A7C15ull));
+            a0 += h & 0xffffull; a1 += (h >> 16) & 0xffffull; a2 += (h >> 32) & 0xffffull; a3 += (h >> 48) & 0xffffull;
+            cnt++;
+        }
+    }
+    atomicAdd(&out[0], a0); atomicAdd(&out[1], a1); atomicAdd(&out[2], a2); atomicAdd(&out[3], a3);
+    atomicAdd(&out[4], cnt); atomicAdd(&out[5], rows);
+}
+
+extern "C" int32_t lv_mesh_hash(LvHandle c, const int32_t *global_label_dev, uint64_t out[6]) {
+    if (!c || !out) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
+    for (int k = 0; k < 6; k++) out[k] = 0;
+    if (c->nslot == 0) return LV_OK;
+    LV_TRY(lv_ensure(c, &c->d_scratch, &c->cap_scratch, 64, 1));
+    unsigned long long *d = (unsigned long long *)c->d_scratch;
+    LV_CUDA(c, cudaMemsetAsync(d, 0, 48, c->stream));
+    k_mesh_hash<<<c->num_sms * 4, 256, 0, c->stream>>>((int)c->nslot, c->d_own, c->d_ent_label, c->d_rowptr, c->d_deg, c->d_col, global_label_dev, d);
+    c->launches++;
+    LV_CUDA(c, cudaMemcpyAsync(out, d, 48, cudaMemcpyDeviceToHost, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+extern "C" {
 // ---- instrumentation ----------------------------------------------------------------------------
 int32_t lv_prof_enable(LvHandle c, int32_t on) { if (!c) return LV_EINVAL; c->prof_on = on != 0; return LV_OK; }
 int32_t lv_prof_reset(LvHandle c) {

@@ -382,6 +382,17 @@ int32_t lv_peer_disable(LvHandle c) {
     return LV_OK;
 }
 
+// unmap everything mapped from other ranks (peer vectors, flags, mailboxes).  Every rank calls this, then a barrier,
+// then lv_destroy: memory exported over CUDA IPC must not be freed while an importer still has it mapped.
+int32_t lv_peer_close(LvHandle c) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    close_peer_maps(c);
+    close_mailboxes(c);
+    return LV_OK;
+}
+
 // exchange a caller's slot-ordered device vector (tests; the solver calls lv_halo_exchange directly)
 int32_t lv_halo_exchange_dev(LvHandle c, double *vec_dev, int32_t ncomp) {
     if (!c || !vec_dev || (ncomp != 1 && ncomp != 2)) return LV_EINVAL;

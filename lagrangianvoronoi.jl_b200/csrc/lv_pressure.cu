@@ -11,7 +11,7 @@
 #define PR_BLOCK 256
 
 // scalars kept on the device between kernels (doubles in c->d_red[0..15])
-enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11,
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_SOLVED = 12 /* MINRES: stats.solved (tolerance met; not the ill-conditioned / NaN exits) */,
        // MINRES (Paige-Saunders, in the formulation of Krylov.jl 0.9.8 minres!) scalar state
        MR_BETA = 16, MR_OLDB = 17, MR_DBAR = 18, MR_EPS = 19, MR_CS = 20, MR_SN = 21, MR_PHIBAR = 22, MR_GAMMA = 23, MR_PHI = 24,
        MR_DELTA = 25, MR_ANORM2 = 26, MR_GMAX = 27, MR_GMIN = 28, MR_XENORM2 = 29, MR_ROOT = 30, MR_BETA1 = 31, MR_ERRV = 32 /* ..36 */,
@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
         scal[SC_TOL] = atol + rtol * beta1;
         scal[SC_ITER] = 0.0;
         scal[SC_CONV] = (beta1 == 0.0 || beta1 <= scal[SC_TOL]) ? 1.0 : 0.0;
+        scal[SC_SOLVED] = scal[SC_CONV];
     } else if (mode == 5) { // alpha = v.y / beta ; delta = cs*dbar + sn*alpha
         const double alpha = s1 / scal[MR_BETA];
         scal[SC_ALPHA] = alpha;
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
                             (iter >= 5 && err_lbnd <= etol * sqrt(scal[MR_XENORM2])) || (rNorm + 1.0 <= 1.0) || (rNorm <= tol);
         scal[SC_RR] = rNorm * rNorm;
         if (solved || ill || !(rNorm == rNorm)) scal[SC_CONV] = 1.0;
+        if (solved && rNorm == rNorm) scal[SC_SOLVED] = 1.0; // Krylov's stats.solved: false for the ill-conditioned and NaN exits
     }
 }
 
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
 // store from every scalar kernel, whose system-scope fence would stall behind that copy's PCIe traffic.
 __global__ void k_publish_scalars(const double *__restrict__ scal, double *host) {
     if (threadIdx.x == 0) {
-        host[SC_CONV] = scal[SC_CONV]; host[SC_ITER] = scal[SC_ITER];
+        host[SC_CONV] = scal[SC_CONV]; host[SC_ITER] = scal[SC_ITER]; host[SC_SOLVED] = scal[SC_SOLVED];
         host[SC_RES2] = scal[SC_RES2]; host[SC_BNORM2] = scal[SC_BNORM2];
         __threadfence_system();
     }
@@ -894,7 +896,7 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
     }
     LV_CUDA(c, cudaGetLastError());
     if (iters) *iters = (int)c->h_red[SC_ITER];
-    if (solved) *solved = conv ? 1 : 0;
+    if (solved) *solved = (conv && c->h_red[SC_SOLVED] != 0.0) ? 1 : 0; // relaxation.jl:184 warns when stats.solved is false
     return LV_OK;
 }
 

@@ -655,6 +655,35 @@ int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, doub
     return LV_OK;
 }
 
+// mul!(res, A::MultiphaseProjector, x) (relaxation.jl:91-123) and the right-hand side of refresh! (:162-177) on host
+// vectors in label order: the operator the projection solves with, exposed for direct parity checks.  NULL skips.
+int32_t lv_step_multiphase_apply(LvHandle c, const double *x, double *y, double *b) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(need_mesh(c));
+    LV_TRY(lv_pr_ensure(c));
+    StepView S = make_view(c);
+    if (S.n == 0) return LV_OK;
+    const size_t bytes = sizeof(double) * (size_t)S.n;
+    double *dx = c->d_vec[5], *dy = c->d_vec[6];
+    double2 *tmp = (double2 *)c->st_tmp;
+    if (x && y) {
+        LV_CUDA(c, cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        k_mp_tmp<<<GRID(S.n)>>>(S, dx, tmp);
+        k_mp_apply<<<GRID(S.n)>>>(S, tmp, dy);
+        c->launches += 2;
+        LV_CUDA(c, cudaMemcpyAsync(y, dy, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (b) {
+        k_mp_apply<<<GRID(S.n)>>>(S, S.dv, dy);
+        c->launches++;
+        LV_CUDA(c, cudaMemcpyAsync(b, dy, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
 // find_pressure!(solver, dt, niter; boundary_velocity) on the resident state  pressure.jl:215-225
 int32_t lv_step_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
                               const double *vbc_wall, int32_t *iters_out, double *relres_out) {

@@ -358,8 +358,25 @@ class StripGrid:
         """Generators this rank owns (they must lie in its strip), global labels ascending."""
         self.xy_own = torch.as_tensor(xy, dtype=torch.float64, device=self.dev).contiguous()
         self.lab_own = torch.as_tensor(labels, dtype=torch.int64, device=self.dev).contiguous()
-        if self.lab_own.numel() and int(self.lab_own.max()) >= 2 ** 31:
-            raise ValueError("global labels must stay below 2^31")
+        if self.lab_own.numel() and int(self.lab_own.max()) >= 2 ** 30:
+            raise ValueError("global labels must stay below 2^30 (the bucket sort packs key and image bit into 32 bits)")
+
+    def set_owned_from_host(self, xy_host: np.ndarray, labels_dev: torch.Tensor) -> None:
+        """Owned positions from (pinned) host memory, labels already on the device (end-to-end path)."""
+        self.xy_own = torch.from_numpy(xy_host).to(self.dev, non_blocking=True)
+        self.lab_own = labels_dev
+
+    def close(self) -> None:
+        """Collective teardown: unmap all peer memory, wait for every rank, then free.  Memory exported over CUDA IPC
+        must not be freed while another rank still has it mapped."""
+        g = self.grid
+        if g._h:
+            torch.cuda.synchronize(self.dev)
+            if self.world > 1:
+                check(self._L.lv_peer_close(g._h), g._h)
+                dist.barrier(group=self.group)
+            self._L.lv_destroy(g._h)
+            g._h = None
 
     def migrate(self) -> None:
         """After a move: hand generators that left the strip to their new owner."""

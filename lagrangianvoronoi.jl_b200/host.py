@@ -230,10 +230,12 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
         grid._lazy_edges = bool(lazy)
     buf = getattr(grid, "_edge_buf", None)
     if buf is None or buf.shape[0] < 6 * n + 64:  # grow-only pinned buffer: page-locking GBs per call would dominate
+        wait_edges(grid)  # a background copy of the previous lazy remesh may still be writing into the old buffer
         grid._edge_buf = _host_empty((7 * n + 64,), EDGE_DTYPE)
     st = L.lv_remesh(grid._h, n, ptr(grid.x), ptr(grid.rowptr), ptr(grid._edge_buf), grid._edge_buf.shape[0],
                      C.byref(nnz), ptr(grid._area), ptr(grid._centroid))
     if st == _capi.LV_ECAPACITY and nnz.value > grid._edge_buf.shape[0]:  # pragma: no cover - 7n is generous
+        wait_edges(grid)
         grid._edge_buf = _host_empty((nnz.value,), EDGE_DTYPE)
         st = L.lv_mesh_download(grid._h, ptr(grid.rowptr), ptr(grid._edge_buf), nnz.value, ptr(grid._area),
                                 ptr(grid._centroid))

@@ -59,7 +59,10 @@ def populate_circ(grid: VoronoiGrid, charfun=None, center=(0.0, 0.0), ic=None):
     c = np.asarray(center, dtype=np.float64)
     r_max = max(np.hypot(px - c[0], py - c[1]) for px in (x0, x1) for py in (y0, y1))
     pts = []
-    for r in np.arange(0.5 * grid.dr, r_max + 1e-300, grid.dr):
+    dr = grid.dr
+    # Julia's range (0.5dr):dr:r_max has floor((r_max - 0.5dr)/dr) + 1 elements (the end point included when it is hit)
+    nring = int(np.floor((r_max - 0.5 * dr) / dr * (1.0 + 4e-16))) + 1 if r_max >= 0.5 * dr else 0
+    for r in (0.5 * dr + k * dr for k in range(nring)):
         k_max = int(round(2.0 * np.pi * r / grid.dr))
         th = 2.0 * np.pi * np.arange(1, k_max + 1) / max(k_max, 1)
         pts.append(np.stack([c[0] + r * np.cos(th), c[1] + r * np.sin(th)], 1))

@@ -134,3 +134,12 @@ def multiphase_projection(grid: VoronoiGrid, quality_threshold: float = 0.25, rt
         import warnings
         warnings.warn("multiphase projector did not converge within tolerance")  # relaxation.jl:184-187
     return it.value, bool(ok.value)
+
+
+def multiphase_apply(grid: VoronoiGrid, x):
+    """(A x, b): mul!(res, A::MultiphaseProjector, x) (relaxation.jl:91-123) and the right-hand side refresh! builds from
+    the resident dv (relaxation.jl:162-177), both on the device."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y, b = np.zeros_like(x), np.zeros_like(x)
+    check(grid._L.lv_step_multiphase_apply(grid._h, ptr(x), ptr(y), ptr(b)), grid._h)
+    return y, b

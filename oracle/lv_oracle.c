@@ -1194,6 +1194,19 @@ static void mp_matvec(const lvo_grid *g, const double *x, double *res) { /* rela
     }
     mp_pass2(g, tmp, res);
 }
+/* direct application of the projector and of its right-hand side (tests): y = A x (relaxation.jl:91-123), b from dv (:162-177) */
+void lvo_multiphase_apply(lvo_grid *g, const double *x, double *y, double *b) {
+    int64_t n = g->n;
+    g_mp_tmp = (vec2 *)malloc(sizeof(vec2) * (size_t)(n > 0 ? n : 1));
+    if (x && y) mp_matvec(g, x, y);
+    if (b) {
+        vec2 *dv = (vec2 *)malloc(sizeof(vec2) * (size_t)(n > 0 ? n : 1));
+        for (int64_t i = 0; i < n; i++) dv[i] = g->polygons[i]->dv;
+        mp_pass2(g, dv, b);
+        free(dv);
+    }
+    free(g_mp_tmp); g_mp_tmp = NULL;
+}
 int lvo_multiphase_projection(lvo_grid *g, double quality_threshold, double rtol, double atol, int itmax, int *iters, int *solved) {
     int64_t n = g->n;
     double *b = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));

@@ -97,6 +97,7 @@ int lvo_relaxation_step(lvo_grid *g, double dt, int rusanov);     /* relaxation.
 
 /* relaxation.jl:75-206 multiphase projector: MINRES (cold start) + correction of dv */
 int lvo_multiphase_projection(lvo_grid *g, double quality_threshold, double rtol, double atol, int itmax, int *iters, int *solved);
+void lvo_multiphase_apply(lvo_grid *g, const double *x, double *y, double *b); /* y = A x (:91-123), b = refresh! (:162-177); NULL skips */
 void lvo_gravity_step(lvo_grid *g, double gx, double gy, double dt); /* pressure.jl:77-82 */
 
 void lvo_set_threads(int nthreads);

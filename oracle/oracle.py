@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L.lvo_find_dv.argtypes = [vp, C.c_double, C.c_double]
         L.lvo_relaxation_step.argtypes = [vp, C.c_double, C.c_int]
         L.lvo_multiphase_projection.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.lvo_multiphase_apply.argtypes = [vp, dp, dp, dp]
         L.lvo_gravity_step.argtypes = [vp, C.c_double, C.c_double, C.c_double]
         L.lvo_set_threads.argtypes = [C.c_int]
         L.lvo_get_threads.restype = C.c_int
@@ -272,6 +273,13 @@ class OracleGrid:
         st = lib().lvo_multiphase_projection(self._g, float(quality_threshold), float(rtol), float(atol), int(itmax), C.byref(it), C.byref(ok))
         assert st == 0
         return it.value, bool(ok.value)
+
+    def multiphase_apply(self, x):
+        """(A x, b): the matrix-free projector applied to x (relaxation.jl:91-123) and its right-hand side (:162-177)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y, b = np.zeros_like(x), np.zeros_like(x)
+        lib().lvo_multiphase_apply(self._g, _dp(x), _dp(y), _dp(b))
+        return y, b
 
     def gravity_step(self, g, dt):
         lib().lvo_gravity_step(self._g, float(g[0]), float(g[1]), float(dt))

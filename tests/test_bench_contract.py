@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-side", "64"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--side", "64"], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))  # torchrun exports this: the CPU arm must not inherit it
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, out.stdout
@@ -19,10 +20,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["cells_total"] == 64 * 64 and d["config"]["steps_timed"] == 1
 
 
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                          "--warmup", "0", "--cpu-side", "64"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+                          "--warmup", "0", "--side", "64"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
