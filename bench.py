@@ -383,7 +383,11 @@ def mesh_checks(env, hv, area_sum, box_area, n_total, M, My, seed, periodic):
     pairs, rows = int(hv[4]), int(hv[5])
     h = hash_combine(hv)
     exp = expected_hash(M, My, seed)
+    # sum of degrees = 6n - 2 x (vertices where four cells meet): the reference decides near-degenerate cuts with an ABSOLUTE
+    # epsilon (SIGNUM_EPS, polygon.jl:2) while the cut function scales with dr^2, so at dr = 1/8192 a handful of such vertices
+    # is expected (about 3e-8 per vertex and candidate) and none at dr = 1/4096
     return {"rows": rows, "rows_eq_cells": rows == n_total, "euler_sum_deg_eq_6n": pairs == 6 * n_total if periodic else None,
+            "sum_deg_minus_6n": pairs - 6 * n_total,
             "area_sum_minus_box": area_sum - box_area, "mesh_witness": h, "mesh_witness_expected_from_1gpu": exp,
             "mesh_witness_matches_1gpu": (h == exp) if exp else None}
 

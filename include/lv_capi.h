@@ -196,17 +196,29 @@ int32_t lv_comm_init(LvHandle h, int32_t rank, int32_t nranks, const uint8_t *id
 int32_t lv_remesh_owned_dev(LvHandle h, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev,
                             const int32_t *order_key_dev);
 /* device pointers into the slot-ordered cell list (0 ent_label u32, 1 prim_of_label i32, 2 own u8,
- * 3 ent_xy f64x2, 4 P f64, 5 area f64) for building the halo plan on the host */
+ * 3 ent_xy f64x2, 4 P f64, 5 area f64; strip mode: 6 local positions f64x2, 7 local global labels i32) */
 int32_t lv_device_array(LvHandle h, int32_t which, void **ptr, int64_t *count);
 /* per peer rank: how many values this rank sends / receives and the (device) slot lists, concatenated */
 int32_t lv_halo_plan(LvHandle h, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count,
                      const int32_t *send_slots_dev, const int64_t *recv_count, const int32_t *recv_slots_dev);
-/* Peer-memory halo of the CG search direction: lv_peer_export returns the CUDA IPC handles (64 + 64 bytes) of
- * this rank's vector and version flag; the host gathers them and gives every rank the handles of its peers
- * (order of lv_halo_plan) plus, per ghost value, its slot in the owner's numbering.  The CG loop then pulls
- * ghost values with NVLink loads ordered by the flags instead of pack / ncclSend / ncclRecv / unpack. */
-int32_t lv_peer_export(LvHandle h, uint8_t *out128);
-int32_t lv_peer_plan(LvHandle h, int32_t npeers, const uint8_t *handles, const int32_t *remote_slots_dev);
+/* Strip exchange over peer memory (csrc/lv_strip.cu): the library owns the local generator arrays (owned generators
+ * first, then the ghosts peer by peer) and one exchange area per rank that its strip neighbours map once over CUDA IPC.
+ * lv_strip_setup: peers (rank, this rank's index in the peer's own peer list, the bucket rows [lo, hi) that peer needs =
+ *   its rows +- the halo), the ghost capacity per peer (same on every rank) and the capacity of the local arrays;
+ *   returns the IPC handle (64 bytes) of this rank's area.  lv_strip_map: the peers' handles, in peer order.
+ * lv_strip_set_owned: positions (host or device) and global labels (device int32; NULL keeps them) of the generators this
+ *   rank owns.
+ * lv_strip_remesh: remesh!(grid) (voronoigrid.jl:89-108) on owned + ghosts: ghost selection, count + generator exchange
+ *   (NVLink pulls ordered by sequence words; one host synchronisation), cell list, clipping of the owned polygons with
+ *   buckets ordered by global label (=> meshes do not depend on the GPU count), halo plan.  counts_out (nullable, 9 values):
+ *   local generator count, ghosts sent to / received from each peer.  Collective over the strip neighbours.
+ * Afterwards every halo exchange of the pressure solve (fields, right-hand side, Krylov vectors) pulls from the neighbours'
+ * halo outboxes; the CG search direction is packed by the kernel that produces it. */
+int32_t lv_strip_setup(LvHandle h, int32_t npeers, const int32_t *peer_rank, const int32_t *idx_there, const int32_t *lo,
+                       const int32_t *hi, int64_t ghost_capacity, int64_t local_capacity, uint8_t *out64);
+int32_t lv_strip_map(LvHandle h, const uint8_t *handles);
+int32_t lv_strip_set_owned(LvHandle h, int64_t n_own, const double *xy, int32_t xy_on_host, const int32_t *global_label_dev);
+int32_t lv_strip_remesh(LvHandle h, int64_t *counts_out);
 /* Peer-memory allreduce of the two CG scalars: every rank exports a mailbox (CUDA IPC handle, 64 bytes), maps the
  * mailboxes of all ranks and from then on posts / collects partial sums with NVLink stores and flags; sums are
  * taken in rank order, so the result is deterministic and identical on every rank. */

@@ -196,6 +196,8 @@ int32_t lv_create(const LvGridDesc *d, int32_t device, LvHandle *out) {
         if ((st = lv_alloc(c, (void **)&c->d_cell_cnt, sizeof(int) * (size_t)(c->ncell + 2))) != LV_OK) break;
         if ((st = lv_alloc(c, (void **)&c->d_cell_start, sizeof(int) * (size_t)(c->ncell + 2))) != LV_OK) break;
         if ((st = lv_alloc(c, (void **)&c->d_flags, sizeof(int) * 8)) != LV_OK) break;
+        if ((st = lv_alloc(c, (void **)&c->d_tickets, sizeof(int) * 8)) != LV_OK) break;
+        if (cudaMemset(c->d_tickets, 0, sizeof(int) * 8) != cudaSuccess) { st = LV_ECUDA; break; }
         if (cudaHostAlloc((void **)&c->h_flags, sizeof(int) * 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { st = LV_ECUDA; break; }
         if (cudaHostAlloc((void **)&c->h_red, sizeof(double) * 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { st = LV_ECUDA; break; }
     } while (0);
@@ -214,7 +216,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
-                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_scratch,
+                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_tickets, c->d_scratch,
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1], c->d_io_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
@@ -302,7 +304,8 @@ static int ensure_generators(LvContext *c, int64_t n, bool need_xy) {
     return LV_OK;
 }
 
-static int remesh_common(LvContext *c, int64_t n) {
+} // extern "C"
+int lv_remesh_common(LvContext *c, int64_t n) {
     c->mesh_valid = false;
     c->assembled = false;
     // the pressure fields live in slot order and every remesh re-sorts the slots: whatever was uploaded before is
@@ -315,13 +318,14 @@ static int remesh_common(LvContext *c, int64_t n) {
     c->mesh_valid = true;
     return LV_OK;
 }
+extern "C" {
 
 int32_t lv_remesh_dev(LvHandle c, int64_t n, const double *xy_dev) {
     if (!c || (n > 0 && !xy_dev)) return lv_set_error(c, LV_EINVAL, "null argument");
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(ensure_generators(c, n, false));
     c->xy = (const double2 *)xy_dev; // used in place: positions are only read
-    int st = remesh_common(c, n);
+    int st = lv_remesh_common(c, n);
     c->owned_mask = nullptr; // one-shot: set by lv_remesh_owned_dev
     c->order_key = nullptr;
     return st;
@@ -508,7 +512,7 @@ int32_t lv_remesh(LvHandle c, int64_t n, const double *xy, int64_t *rowptr, LvEd
     c->xy = c->d_xy;
     c->owned_mask = nullptr;
     c->order_key = nullptr;
-    LV_TRY(remesh_common(c, n));
+    LV_TRY(lv_remesh_common(c, n));
     if (nnz) *nnz = c->nnz;
     if (rowptr || edges || area || centroid) LV_TRY(lv_mesh_to_labels(c, rowptr, edges, cap, area, centroid));
     return LV_OK;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *_
                                                      unsigned *__restrict__ ent_label, double2 *__restrict__ ent_xy,
                                                      const double2 *__restrict__ xy, int *__restrict__ prim_of_label,
                                                      const unsigned char *__restrict__ owned_mask, unsigned char *__restrict__ own,
-                                                     const int *__restrict__ order_key) {
+                                                     const int *__restrict__ order_key, int owned_count) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= ncell_ext) return;
     const int s0 = start[b], s1 = start[b + 1];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) k_cells_order(int ncell_ext, const int *_
         ent_xy[s0 + a] = xy[lab];
         const bool prim = !(e & LV_IMAGE_BIT);
         if (prim) prim_of_label[lab] = s0 + a;
-        own[s0 + a] = prim && (owned_mask == nullptr || owned_mask[lab]);
+        own[s0 + a] = prim && (owned_mask ? owned_mask[lab] != 0 : (owned_count < 0 || (int)lab < owned_count));
     }
 }
 
@@ -278,7 +278,8 @@ int lv_cells_build(LvContext *c) {
         k_cells_count_fill<true><<<nb, 256, 0, st>>>(c->gp, n, c->xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label,
                                                      c->d_flags);
         k_cells_order<<<(int)((ncell_ext + 127) / 128), 128, 0, st>>>((int)ncell_ext, c->d_cell_start, c->d_ent_label,
-                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label, c->owned_mask, c->d_own, c->order_key);
+                                                                      c->d_ent_xy, c->xy, c->d_prim_of_label, c->owned_mask, c->d_own, c->order_key,
+                                                                      (int)c->owned_count);
         c->launches += 2;
     }
     LV_CUDA(c, cudaGetLastError());

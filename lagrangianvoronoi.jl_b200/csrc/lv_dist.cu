@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(256) k_halo_unpack(int64_t n, const int *__res
     for (int k = 0; k < NC; k++) vec[(size_t)NC * s + k] = buf[(size_t)NC * i + k];
 }
 
-int lv_halo_exchange(LvContext *c, double *vec, int ncomp) {
+int lv_halo_exchange(LvContext *c, double *vec, int ncomp) { // ghost slots of a slot-ordered vector from their owners
+    if (lv_strip_peer_mode(c)) return lv_strip_halo_exchange(c, vec, ncomp); // NVLink pulls, no NCCL
+    return lv_halo_exchange_nccl(c, vec, ncomp);
+}
+
+int lv_halo_exchange_nccl(LvContext *c, double *vec, int ncomp) {
     if (!c->comm || c->peers.empty()) return LV_OK;
     ncclComm_t comm = (ncclComm_t)c->comm;
     cudaStream_t st = c->stream;
@@ -94,49 +99,10 @@ int lv_halo_exchange(LvContext *c, double *vec, int ncomp) {
     return LV_OK;
 }
 
-// ---- peer-memory halo (NVLink loads instead of pack / ncclSend / ncclRecv / unpack) -----------------------
 __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-__global__ void k_halo_signal(int *flag, int version) {
-    __threadfence_system(); // everything this stream wrote before is visible to the peers first
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(version) : "memory");
-}
-// one launch per peer: wait until the peer has published `version`, then gather my ghost values from its vector
-__global__ void __launch_bounds__(256) k_halo_pull(int64_t n, const int *__restrict__ recv_slots, const int *__restrict__ remote_slots,
-                                                   const double *peer_vec, const int *peer_flag, int version, double *__restrict__ vec) {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_sys(peer_flag) < version) { }
-    }
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) vec[recv_slots[i]] = __ldcv(peer_vec + remote_slots[i]);
-}
-
-int lv_halo_signal(LvContext *c) {
-    if (!c->comm || !c->peer_ready) return LV_OK;
-    c->pver++;
-    k_halo_signal<<<1, 1, 0, c->stream>>>(c->d_peer_flag, c->pver);
-    c->launches++;
-    return LV_OK;
-}
-
-int lv_halo_pull_p(LvContext *c, double *p) {
-    if (!c->comm) return LV_OK;
-    if (!c->peer_ready || p != c->d_vec[1]) return lv_halo_exchange(c, p, 1);
-    for (size_t k = 0; k < c->peers.size(); k++) {
-        const auto &pr = c->peers[k];
-        if (pr.nrecv == 0) continue;
-        const auto &pm = c->peer_maps[k];
-        const int nb = (int)((pr.nrecv + 255) / 256);
-        k_halo_pull<<<nb, 256, 0, c->stream>>>(pr.nrecv, c->d_recv_slots + pr.recv_off, c->d_remote_slots + pr.recv_off,
-                                               (const double *)pm.vec_base, (const int *)pm.flag_base, c->pver, p);
-        c->launches++;
-    }
-    LV_CUDA(c, cudaGetLastError());
-    return LV_OK;
 }
 
 // mailbox layout per rank: [parity 2][rank 64] of {double v[2]; int flag; int pad} = 24 -> 32 bytes
@@ -188,22 +154,11 @@ static void close_mailboxes(LvContext *c) {
     c->mailbox_ready = false;
 }
 
-static void close_peer_maps(LvContext *c) {
-    for (auto &pm : c->peer_maps) {
-        if (pm.vec_base) cudaIpcCloseMemHandle(pm.vec_base);
-        if (pm.flag_base) cudaIpcCloseMemHandle(pm.flag_base);
-    }
-    c->peer_maps.clear();
-    c->peer_ready = false;
-}
-
 void lv_dist_destroy(LvContext *c) {
-    close_peer_maps(c);
+    lv_strip_destroy(c);
     close_mailboxes(c);
     cudaFree(c->d_mailbox); c->d_mailbox = nullptr;
     cudaFree(c->d_mailbox_ptrs); c->d_mailbox_ptrs = nullptr;
-    cudaFree(c->d_remote_slots); c->d_remote_slots = nullptr;
-    cudaFree(c->d_peer_flag); c->d_peer_flag = nullptr;
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
     cudaFree(c->d_send_slots); cudaFree(c->d_recv_slots); cudaFree(c->d_send_buf); cudaFree(c->d_recv_buf);
@@ -275,25 +230,6 @@ int32_t lv_halo_plan(LvHandle c, int32_t npeers, const int32_t *peer_rank, const
     return LV_OK;
 }
 
-// CUDA IPC handles of this rank's search-direction vector (64 B) and version flag (64 B); the host gathers
-// them from all ranks and hands every rank its peers' handles through lv_peer_plan
-int32_t lv_peer_export(LvHandle c, uint8_t *out128) {
-    if (!c || !out128) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
-    LV_TRY(lv_pr_ensure(c));
-    if (!c->d_peer_flag) {
-        LV_CUDA(c, cudaMalloc((void **)&c->d_peer_flag, 256));
-        LV_CUDA(c, cudaMemset(c->d_peer_flag, 0, 256));
-    }
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    cudaIpcMemHandle_t hv, hf;
-    LV_CUDA(c, cudaIpcGetMemHandle(&hv, c->d_vec[1]));
-    LV_CUDA(c, cudaIpcGetMemHandle(&hf, c->d_peer_flag));
-    memcpy(out128, &hv, 64);
-    memcpy(out128 + 64, &hf, 64);
-    return LV_OK;
-}
-
 // CUDA IPC handle (64 B) of this rank's allreduce mailbox; lv_mailbox_plan maps the mailboxes of all ranks
 int32_t lv_mailbox_export(LvHandle c, uint8_t *out64) {
     if (!c || !out64) return LV_EINVAL;
@@ -334,50 +270,10 @@ int32_t lv_mailbox_plan(LvHandle c, int32_t nranks, const uint8_t *handles /* nr
     return LV_OK;
 }
 
-// peers in the order of lv_halo_plan; handles[k] = what peer k exported; remote_slots_dev[i] = slot, in its
-// owner's numbering, of the value that lands in recv slot i (same concatenated order as recv_slots)
-int32_t lv_peer_plan(LvHandle c, int32_t npeers, const uint8_t *handles, const int32_t *remote_slots_dev) {
-    if (!c || npeers != (int32_t)c->peers.size()) return lv_set_error(c, LV_EINVAL, "lv_peer_plan: call lv_halo_plan first");
-    LV_CUDA(c, cudaSetDevice(c->device));
-    LV_CUDA(c, cudaStreamSynchronize(c->stream));
-    // reopen only what changed (opening an IPC handle is expensive; the vector is reallocated rarely)
-    bool same = c->peer_maps.size() == (size_t)npeers;
-    for (int k = 0; same && k < npeers; k++)
-        same = c->peer_maps[k].rank == c->peers[k].rank && !memcmp(c->peer_maps[k].handle, handles + 128 * k, 128);
-    if (!same) {
-        close_peer_maps(c);
-        for (int k = 0; k < npeers; k++) {
-            LvContext::PeerMap pm;
-            pm.rank = c->peers[k].rank;
-            memcpy(pm.handle, handles + 128 * k, 128);
-            cudaIpcMemHandle_t hv, hf;
-            memcpy(&hv, handles + 128 * k, 64);
-            memcpy(&hf, handles + 128 * k + 64, 64);
-            cudaError_t e = cudaIpcOpenMemHandle(&pm.vec_base, hv, cudaIpcMemLazyEnablePeerAccess);
-            if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pm.flag_base, hf, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                close_peer_maps(c);
-                return lv_set_error(c, LV_ECUDA, "cudaIpcOpenMemHandle(peer %d) failed: %s", pm.rank, cudaGetErrorString(e));
-            }
-            c->peer_maps.push_back(pm);
-        }
-    }
-    const int64_t ro = c->halo_recv_total;
-    if (ro > c->cap_remote) {
-        cudaFree(c->d_remote_slots);
-        c->cap_remote = ro + ro / 8 + 1024;
-        LV_CUDA(c, cudaMalloc((void **)&c->d_remote_slots, sizeof(int) * (size_t)c->cap_remote));
-    }
-    if (ro > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_remote_slots, remote_slots_dev, sizeof(int) * (size_t)ro, cudaMemcpyDeviceToDevice, c->stream));
-    c->peer_ready = true;
-    return LV_OK;
-}
-
 // fall back to the NCCL halo / allreduce (used when a rank could not map a peer: all ranks must switch together)
 int32_t lv_peer_disable(LvHandle c) {
     if (!c) return LV_EINVAL;
-    c->peer_ready = false;
+    c->strip.mapped = false;
     c->mailbox_ready = false;
     return LV_OK;
 }
@@ -388,7 +284,7 @@ int32_t lv_peer_close(LvHandle c) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
-    close_peer_maps(c);
+    lv_strip_unmap(c);
     close_mailboxes(c);
     return LV_OK;
 }
@@ -412,6 +308,8 @@ int32_t lv_device_array(LvHandle c, int32_t which, void **ptr, int64_t *count) {
     case 3: *ptr = c->d_ent_xy; *count = c->nslot; break;
     case 4: *ptr = c->d_P; *count = c->nslot; break;
     case 5: *ptr = c->d_area; *count = c->nslot; break;
+    case 6: *ptr = c->strip.loc_xy; *count = c->strip.n_loc; break;  // strip mode: local generators (owned first, then ghosts)
+    case 7: *ptr = c->strip.loc_key; *count = c->strip.n_loc; break; // ... and their global labels (int32)
     default: return lv_set_error(c, LV_EINVAL, "unknown device array %d", which);
     }
     return LV_OK;

@@ -15,6 +15,7 @@
 #include <functional>
 #include "../../include/lv_capi.h"
 
+#define LV_SP_MAXP 4 // strip neighbours per rank (2 in practice)
 #define LV_IMAGE_BIT 0x80000000u // set in ent_label[] for periodic-image slots
 
 struct LvPathNode { // neighborlist.jl:6-9, truncated table (see lv_capi.cu:build_magic_path)
@@ -75,6 +76,7 @@ struct LvContext {
     unsigned long long *d_tile_state = nullptr; // look-back scan state of the clip kernel
     int64_t cap_tiles = 0;
     int *d_flags = nullptr; // [8] device status words, see LvFlag
+    int *d_tickets = nullptr; // [8] last-block tickets of fused kernels (0 matvec, 1 update_r, 2 update_xp); [7] = a peer wait timed out
     int *h_flags = nullptr; // pinned mirror
     int clip_level = 0;     // sticky polygon-capacity level (see lv_clip_run)
     int clip_last_level = 0; // level that produced the current mesh
@@ -123,15 +125,34 @@ struct LvContext {
     int *d_send_slots = nullptr, *d_recv_slots = nullptr; // concatenated per peer
     double *d_send_buf = nullptr, *d_recv_buf = nullptr;  // 2 components per entry
     int64_t halo_send_total = 0, halo_recv_total = 0, cap_halo_send = 0, cap_halo_recv = 0;
-    // peer-memory halo of the CG search direction: ghost values are pulled straight out of the neighbours'
-    // vectors over NVLink (CUDA IPC mappings), ordered by a per-rank version flag (lv_dist.cu)
-    struct PeerMap { int rank; unsigned char handle[128]; void *vec_base = nullptr; void *flag_base = nullptr; };
-    std::vector<PeerMap> peer_maps;
-    int *d_remote_slots = nullptr; // [halo_recv_total] slot of each ghost value in its owner's vector
-    int64_t cap_remote = 0;
-    int *d_peer_flag = nullptr;    // this rank's version flag (exported to the peers)
-    int pver = 0;                  // version of the search direction last published
-    bool peer_ready = false;
+    // strip exchange over peer memory (lv_strip.cu): the library owns the local generator arrays (owned first, then the
+    // ghosts peer by peer) and one exported exchange area per rank that its strip neighbours map once (CUDA IPC).  Ghost
+    // generators, their counts and the halo values of every slot-ordered vector are PULLED out of the owner's area over
+    // NVLink, ordered by sequence flags in the area's header; nothing is reallocated after lv_strip_setup.
+    struct StripPeer {
+        int rank = -1, idx_there = 0; // my index in that peer's peer list
+        int lo = 0, hi = 0;           // bucket rows [lo, hi) whose generators that peer needs (its rows +- H)
+        char *area = nullptr;         // the peer's exchange area, mapped
+        int64_t nsend = 0, nrecv = 0, soff = 0, roff = 0;
+    };
+    struct Strip {
+        bool on = false;
+        int npeers = 0;
+        StripPeer peer[LV_SP_MAXP];
+        int64_t capg = 0, cap_loc = 0, n_own = 0, n_loc = 0;
+        char *area = nullptr;      // my exchange area (exported)
+        size_t area_bytes = 0;
+        double2 *loc_xy = nullptr; // [cap_loc]
+        int *loc_key = nullptr;    // [cap_loc] global labels (bucket ordering key)
+        int *sel = nullptr;        // [MAXP][capg] owned indices sent to each peer, in the order of the outbox
+        int *cnt = nullptr;        // [8] device counters: [0..4) ghosts selected per peer, [4..6) send-slot bounds
+        int *h_counts = nullptr;   // mapped pinned [16]
+        int *send_pos0 = nullptr, *send_pos1 = nullptr; // [cap_slot] slot -> position in the halo outbox, or -1
+        int64_t cap_pos = 0;
+        int gseq = 0, hseq = 0;    // remeshes / halo exchanges issued so far (same on every rank)
+        bool mapped = false;
+    } strip;
+    int64_t owned_count = -1; // >= 0: labels below it are owned (strip mode), instead of owned_mask
     // peer-memory allreduce of the CG scalars: every rank owns a mailbox (2 parities x nranks x {2 doubles, flag})
     // that all other ranks write into over NVLink; sums are taken in rank order (deterministic)
     void *d_mailbox = nullptr;             // this rank's mailbox (exported)
@@ -215,11 +236,60 @@ struct __align__(16) LvMailSlot { double v[2]; int flag; int pad[3]; };
 // multi-GPU (lv_dist.cu): both are no-ops when the handle has no communicator
 int lv_halo_exchange(LvContext *c, double *vec_slot, int ncomp); // fill ghost slots from their owners
 int lv_allreduce_sum(LvContext *c, double *dev_scalars, int count);
-int lv_halo_signal(LvContext *c);               // publish "my search direction is ready" (after it was written)
-int lv_halo_pull_p(LvContext *c, double *p);    // ghost slots of p from the peers' memory, or NCCL exchange as fallback
 void lv_dist_destroy(LvContext *c);
+int lv_halo_exchange_nccl(LvContext *c, double *vec_slot, int ncomp); // pack / ncclSend / ncclRecv / unpack (lv_dist.cu)
+// strip exchange over peer memory (lv_strip.cu)
+inline bool lv_strip_peer_mode(const LvContext *c) { return c->strip.on && c->strip.mapped; }
+int lv_strip_halo_exchange(LvContext *c, double *vec_slot, int ncomp); // pack -> signal -> pull through the exchange areas
+int lv_strip_halo_post(LvContext *c, const double *vec_slot, int ncomp);   // pack -> signal (the pull comes later)
+int lv_strip_halo_pull(LvContext *c, double *vec_slot);                // pull only (the producer kernel packed and signalled)
+void lv_strip_destroy(LvContext *c);
+void lv_strip_unmap(LvContext *c);
+struct LvHaloPack { // what a producer kernel needs to pack its freshly written values for the neighbours and signal them
+    const int *send_pos0, *send_pos1, *bounds; // slot -> outbox position (-1: none); bounds[0..1]: slots outside [b0, b1) may be sent
+    double *outbox;                             // this exchange's half of my halo outbox
+    int *flag, *ticket;                         // header word the neighbours wait on; last-block ticket
+    int seq;                                    // value to publish
+};
+int lv_strip_pack_args(LvContext *c, LvHaloPack *out); // advances the exchange sequence
+int lv_remesh_common(LvContext *c, int64_t n);
 
 // ---- device helpers shared by kernels ---------------------------------------------------------
+#define LV_WAIT_TIMEOUT_CYCLES 40000000000ll // ~20 s: only a dead peer gets there
+__device__ __forceinline__ int lv_ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lv_st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded wait until *flag >= v (flag may live in a peer's memory).  A peer that never arrives sets *dead, which turns
+// every later wait into a no-op; the host then reports an error instead of hanging the GPU.
+__device__ __forceinline__ bool lv_wait_ge(const int *flag, int v, int *dead) {
+    if (*(volatile int *)dead) return false;
+    if (lv_ld_acquire_sys(flag) >= v) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        for (int k = 0; k < 64; k++)
+            if (lv_ld_acquire_sys(flag) >= v) return true;
+        if (*(volatile int *)dead) return false;
+        if (clock64() - t0 > LV_WAIT_TIMEOUT_CYCLES) { *(volatile int *)dead = 1; __threadfence(); return false; }
+    }
+}
+// true in exactly one block of the grid: the one that arrives last.  Every block must call it (all threads).
+__device__ __forceinline__ bool lv_last_block(int *ticket) {
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
 __device__ __forceinline__ double lv_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
 
 // y = x + get_arrow(q, x)   voronoigrid.jl:116-125 with the caller's `x + arrow` (voronoigrid.jl:72)

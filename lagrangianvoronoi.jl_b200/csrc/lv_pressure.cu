@@ -11,7 +11,7 @@
 #define PR_BLOCK 256
 
 // scalars kept on the device between kernels (doubles in c->d_red[0..15])
-enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_SOLVED = 12 /* MINRES: stats.solved (tolerance met; not the ill-conditioned / NaN exits) */,
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_DEAD = 13 /* a peer wait timed out */, SC_SOLVED = 12 /* MINRES: stats.solved (tolerance met; not the ill-conditioned / NaN exits) */,
        // MINRES (Paige-Saunders, in the formulation of Krylov.jl 0.9.8 minres!) scalar state
        MR_BETA = 16, MR_OLDB = 17, MR_DBAR = 18, MR_EPS = 19, MR_CS = 20, MR_SN = 21, MR_PHIBAR = 22, MR_GAMMA = 23, MR_PHI = 24,
        MR_DELTA = 25, MR_ANORM2 = 26, MR_GMAX = 27, MR_GMIN = 28, MR_XENORM2 = 29, MR_ROOT = 30, MR_BETA1 = 31, MR_ERRV = 32 /* ..36 */,
@@ -167,6 +167,135 @@ __device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
     return r; // valid in thread 0
 }
 
+// one block: finish reductions and update the scalars.  mode 0: init, 1: alpha, 2: beta, 3: residual check
+// stage 0: reduce the partials and update (single GPU); stage 1: reduce only, leaving the two local sums in
+// scal[SC_TMP0..1] for the NCCL allreduce; stage 2: update from the (now global) sums in scal[SC_TMP0..1].
+// stage 3 (multi-GPU with mapped mailboxes): reduce, exchange the two local sums with every rank through the
+// NVLink mailboxes (rank-ordered, deterministic sum) and update -- one launch, no NCCL in the Krylov loop.
+// The mailbox exchange always runs, also after convergence, so that all ranks keep the same sequence numbers.
+struct MailArgs { LvMailSlot *const *boxes; int nranks, rank, seq; int *dead; };
+// Called by all 256 threads of ONE block: the stand-alone kernel k_cg_scalars, or the block of a producer kernel that
+// arrives last (lv_last_block) -- then no separate launch sits between the producer and the consumer of the scalars.
+__device__ __noinline__ void cg_finish(int mode, int stage, int nblk, int nblk_max, const double *partial, double *scal, double rtol,
+                                       double atol, MailArgs mail) {
+    __shared__ double sm[32];
+    __shared__ double sh[2], m0[LV_MB_MAX_RANKS], m1[LV_MB_MAX_RANKS];
+    if (stage == 3) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3) b2 += __ldcg(&partial[nblk_max + k]); }
+        const double t1 = block_sum(a, sm);
+        const double t2 = block_sum(b2, sm);
+        if (threadIdx.x == 0) { sh[0] = t1; sh[1] = t2; }
+        __syncthreads();
+        const int q = threadIdx.x, par = mail.seq & 1;
+        if (q < mail.nranks) {
+            LvMailSlot *dst = mail.boxes[q] + par * LV_MB_MAX_RANKS + mail.rank;
+            dst->v[0] = sh[0];
+            dst->v[1] = sh[1];
+            __threadfence_system();
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(&dst->flag), "r"(mail.seq) : "memory");
+            LvMailSlot *src = mail.boxes[mail.rank] + par * LV_MB_MAX_RANKS + q;
+            lv_wait_ge(&src->flag, mail.seq, mail.dead); // bounded: a dead peer must not hang the GPU
+            m0[q] = __ldcv(&src->v[0]);
+            m1[q] = __ldcv(&src->v[1]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double g1 = 0.0, g2 = 0.0;
+            for (int k = 0; k < mail.nranks; k++) { g1 += m0[k]; g2 += m1[k]; }
+            scal[SC_TMP0] = g1;
+            scal[SC_TMP1] = g2;
+        }
+        __syncthreads();
+        stage = 2; // fall through to the update from scal[SC_TMP0..1]
+    }
+    if (stage != 1 && mode != 0 && mode != 3 && mode != 4 && scal[SC_CONV] != 0.0) return;
+    double s1, s2;
+    if (stage != 2) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3) b2 += __ldcg(&partial[nblk_max + k]); }
+        s1 = block_sum(a, sm);
+        s2 = block_sum(b2, sm);
+        if (stage == 1) {
+            if (threadIdx.x == 0) { scal[SC_TMP0] = s1; scal[SC_TMP1] = s2; }
+            return;
+        }
+    } else { s1 = scal[SC_TMP0]; s2 = scal[SC_TMP1]; }
+    if (threadIdx.x != 0) return;
+    if (mode == 0) {
+        scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_BNORM2] = s2;
+        const double tol = atol + rtol * sqrt(s1); // Krylov: eps = atol + rtol*||r0||
+        scal[SC_TOL] = tol;
+        scal[SC_ITER] = 0.0;
+        scal[SC_CONV] = (sqrt(s1) <= tol) ? 1.0 : 0.0;
+    } else if (mode == 1) {
+        scal[SC_PAP] = s1;
+        scal[SC_ALPHA] = scal[SC_RR] / s1;
+    } else if (mode == 2) {
+        const double rr_old = scal[SC_RR];
+        scal[SC_BETA] = s1 / rr_old;
+        scal[SC_RR] = s1;
+        scal[SC_ITER] += 1.0;
+        if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
+    } else if (mode == 3) {
+        scal[SC_RES2] = s1; scal[SC_BNORM2] = s2;
+    } else if (mode == 4) { // MINRES init: beta1 = ||r0||
+        const double beta1 = sqrt(s1);
+        scal[MR_BETA1] = beta1; scal[MR_BETA] = beta1; scal[MR_OLDB] = 0.0; scal[MR_DBAR] = 0.0; scal[MR_EPS] = 0.0;
+        scal[MR_CS] = -1.0; scal[MR_SN] = 0.0; scal[MR_PHIBAR] = beta1; scal[MR_ANORM2] = 0.0; scal[MR_GMAX] = 0.0;
+        scal[MR_GMIN] = __longlong_as_double(0x7ff0000000000000ll); scal[MR_XENORM2] = 0.0;
+        for (int k = 0; k < 5; k++) scal[MR_ERRV + k] = 0.0;
+        scal[SC_TOL] = atol + rtol * beta1;
+        scal[SC_ITER] = 0.0;
+        scal[SC_CONV] = (beta1 == 0.0 || beta1 <= scal[SC_TOL]) ? 1.0 : 0.0;
+        scal[SC_SOLVED] = scal[SC_CONV];
+    } else if (mode == 5) { // alpha = v.y / beta ; delta = cs*dbar + sn*alpha
+        const double alpha = s1 / scal[MR_BETA];
+        scal[SC_ALPHA] = alpha;
+        scal[MR_DELTA] = scal[MR_CS] * scal[MR_DBAR] + scal[MR_SN] * alpha;
+    } else if (mode == 6) { // new beta, plane rotation
+        const double alpha = scal[SC_ALPHA], oldb = scal[MR_BETA], cs = scal[MR_CS], sn = scal[MR_SN], dbar = scal[MR_DBAR];
+        const double beta = sqrt(s1);
+        scal[MR_OLDB] = oldb; scal[MR_BETA] = beta;
+        scal[MR_ANORM2] = scal[MR_ANORM2] + alpha * alpha + oldb * oldb + beta * beta;
+        const double gbar = sn * dbar - cs * alpha;
+        scal[MR_EPS] = sn * beta;
+        scal[MR_DBAR] = -cs * beta;
+        scal[MR_ROOT] = sqrt(gbar * gbar + scal[MR_DBAR] * scal[MR_DBAR]);
+        double gamma = sqrt(gbar * gbar + beta * beta);
+        gamma = gamma > 2.220446049250313e-16 ? gamma : 2.220446049250313e-16;
+        scal[MR_GAMMA] = gamma;
+        scal[MR_CS] = gbar / gamma; scal[MR_SN] = beta / gamma;
+        scal[MR_PHI] = scal[MR_CS] * scal[MR_PHIBAR];
+        scal[MR_PHIBAR] = scal[MR_SN] * scal[MR_PHIBAR];
+    } else if (mode == 7) { // stopping tests (s1 = ||x||^2)
+        const double epsM = 2.220446049250313e-16, etol = sqrt(epsM), ctol = sqrt(epsM);
+        const int iter = (int)scal[SC_ITER] + 1;
+        scal[SC_ITER] = (double)iter;
+        const double gamma = scal[MR_GAMMA], phi = scal[MR_PHI];
+        scal[MR_ERRV + (iter % 5)] = phi;
+        double err_lbnd = 0.0;
+        if (iter >= 5) { double e2 = 0.0; for (int k = 0; k < 5; k++) e2 += scal[MR_ERRV + k] * scal[MR_ERRV + k]; err_lbnd = sqrt(e2); }
+        scal[MR_GMAX] = scal[MR_GMAX] > gamma ? scal[MR_GMAX] : gamma;
+        scal[MR_GMIN] = scal[MR_GMIN] < gamma ? scal[MR_GMIN] : gamma;
+        const double ANorm = sqrt(scal[MR_ANORM2]), xNorm = sqrt(s1), Acond = scal[MR_GMAX] / scal[MR_GMIN], rNorm = scal[MR_PHIBAR];
+        const double test1 = rNorm / (ANorm * xNorm), test2 = scal[MR_ROOT] / ANorm, tol = scal[SC_TOL];
+        scal[MR_XENORM2] = scal[MR_XENORM2] + phi * phi;
+        const bool ill = (1.0 + 1.0 / Acond <= 1.0) || (1.0 / Acond <= ctol);
+        const bool solved = (1.0 + test2 <= 1.0) || (test2 <= tol) || (1.0 + test1 <= 1.0) || (test1 <= tol) ||
+                            (iter >= 5 && err_lbnd <= etol * sqrt(scal[MR_XENORM2])) || (rNorm + 1.0 <= 1.0) || (rNorm <= tol);
+        scal[SC_RR] = rNorm * rNorm;
+        if (solved || ill || !(rNorm == rNorm)) scal[SC_CONV] = 1.0;
+        if (solved && rNorm == rNorm) scal[SC_SOLVED] = 1.0; // Krylov's stats.solved: false for the ill-conditioned and NaN exits
+    }
+}
+__global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nblk, int nblk_max, const double *__restrict__ partial,
+                                                    double *__restrict__ scal, double rtol, double atol, MailArgs mail) {
+    cg_finish(mode, stage, nblk, nblk_max, partial, scal, rtol, atol, mail);
+}
+// what a producer kernel needs to finish its reduction in its last block
+struct FuseArgs { int *ticket; int stage, nblk_max; double rtol, atol; MailArgs mail; };
+
 // ---- K4: matvec  pressure.jl:119-130, with optional fused dot(x, y) partial ----------------------
 // One thread per row, grid-stride.  Rows are in bucket (slot) order and the rows of 32 consecutive
 // slots are contiguous in the edge arrays, so a warp's col / w reads fall into a handful of lines
@@ -175,16 +304,17 @@ __device__ __forceinline__ double block_sum(double v, double *sm /*>=32*/) {
 // (A variant that staged each warp tile's col / w through shared memory measured 1.7x slower on
 // B200 -- three dependent memory round trips per tile instead of one -- and was dropped.)
 #define MV_U 8
-template <bool DOT, int MINB>
+template <bool DOT, int MINB, bool FUSE>
 __global__ void __launch_bounds__(PR_BLOCK, MINB) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                      const int *__restrict__ col, const double *__restrict__ w,
                                                      const double *__restrict__ diag, const double *__restrict__ x,
                                                      double *__restrict__ y, double *__restrict__ partial,
-                                                     const double *__restrict__ scal) {
+                                                     double *scal, FuseArgs fz) {
     __shared__ double sm[32];
-    if (DOT && scal[SC_CONV] != 0.0) return;
+    const bool idle = DOT && scal[SC_CONV] != 0.0; // converged: queued launches are no-ops (the fused finish still runs
+    if (idle && !FUSE) return;                     // so that all ranks keep the same mailbox sequence numbers)
     double acc = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (idle ? 0 : nslot); i += gridDim.x * blockDim.x) {
         const double xi = x[i];
         double yi = diag[i] * xi;
         const int r0 = rowptr[i], d = rdeg[i];
@@ -213,6 +343,10 @@ __global__ void __launch_bounds__(PR_BLOCK, MINB) k_matvec(int nslot, const int 
     if (DOT) {
         const double s = block_sum(acc, sm);
         if (threadIdx.x == 0) partial[blockIdx.x] = s;
+        if (FUSE && lv_last_block(fz.ticket)) { // mode 1: alpha = rr / p.Ap, finished here instead of in a one-block launch
+            cg_finish(1, fz.stage, gridDim.x, fz.nblk_max, partial, scal, fz.rtol, fz.atol, fz.mail);
+            if (threadIdx.x == 0) *fz.ticket = 0;
+        }
     }
 }
 
@@ -238,8 +372,8 @@ template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
     if (per_sm == 0) {
         const char *e = getenv("LV_MV_GRID");
         int occ = 0;
-        cudaError_t st = mv_minb() == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 1>, PR_BLOCK, 0)
-                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 6>, PR_BLOCK, 0);
+        cudaError_t st = mv_minb() == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 1, DOT>, PR_BLOCK, 0)
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 6, DOT>, PR_BLOCK, 0);
         if ((e && !strcmp(e, "legacy")) || st != cudaSuccess || occ < 1) occ = 8;
         per_sm = occ;
     }
@@ -247,10 +381,11 @@ template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
     if (cap > 4096) cap = 4096;
     return (int)(nb < cap ? (nb < 1 ? 1 : nb) : cap);
 }
-template <bool DOT>
-static void mv_launch(LvContext *c, int grid, cudaStream_t st, int ns, const double *x, double *y, double *partial, const double *scal) {
-    if (mv_minb() == 1) k_matvec<DOT, 1><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal);
-    else k_matvec<DOT, 6><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal);
+template <bool DOT, bool FUSE = false>
+static void mv_launch(LvContext *c, int grid, cudaStream_t st, int ns, const double *x, double *y, double *partial, double *scal,
+                      const FuseArgs &fz = FuseArgs()) {
+    if (mv_minb() == 1) k_matvec<DOT, 1, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal, fz);
+    else k_matvec<DOT, 6, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal, fz);
     c->launches++;
 }
 
@@ -459,133 +594,12 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_init(int nslot, const double *_
     if (threadIdx.x == 0) { partial[blockIdx.x] = s1; partial[nblk_max + blockIdx.x] = s2; }
 }
 
-// one block: finish reductions and update the scalars.  mode 0: init, 1: alpha, 2: beta, 3: residual check
-// stage 0: reduce the partials and update (single GPU); stage 1: reduce only, leaving the two local sums in
-// scal[SC_TMP0..1] for the NCCL allreduce; stage 2: update from the (now global) sums in scal[SC_TMP0..1].
-// stage 3 (multi-GPU with mapped mailboxes): reduce, exchange the two local sums with every rank through the
-// NVLink mailboxes (rank-ordered, deterministic sum) and update -- one launch, no NCCL in the Krylov loop.
-// The mailbox exchange always runs, also after convergence, so that all ranks keep the same sequence numbers.
-struct MailArgs { LvMailSlot *const *boxes; int nranks, rank, seq; };
-__global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nblk, int nblk_max, const double *__restrict__ partial,
-                                                    double *__restrict__ scal, double rtol, double atol, MailArgs mail) {
-    __shared__ double sm[32];
-    __shared__ double sh[2], m0[LV_MB_MAX_RANKS], m1[LV_MB_MAX_RANKS];
-    if (stage == 3) {
-        double a = 0.0, b2 = 0.0;
-        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
-        const double t1 = block_sum(a, sm);
-        const double t2 = block_sum(b2, sm);
-        if (threadIdx.x == 0) { sh[0] = t1; sh[1] = t2; }
-        __syncthreads();
-        const int q = threadIdx.x, par = mail.seq & 1;
-        if (q < mail.nranks) {
-            LvMailSlot *dst = mail.boxes[q] + par * LV_MB_MAX_RANKS + mail.rank;
-            dst->v[0] = sh[0];
-            dst->v[1] = sh[1];
-            __threadfence_system();
-            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(&dst->flag), "r"(mail.seq) : "memory");
-            LvMailSlot *src = mail.boxes[mail.rank] + par * LV_MB_MAX_RANKS + q;
-            int f;
-            do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(f) : "l"(&src->flag) : "memory"); } while (f < mail.seq);
-            m0[q] = __ldcv(&src->v[0]);
-            m1[q] = __ldcv(&src->v[1]);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double g1 = 0.0, g2 = 0.0;
-            for (int k = 0; k < mail.nranks; k++) { g1 += m0[k]; g2 += m1[k]; }
-            scal[SC_TMP0] = g1;
-            scal[SC_TMP1] = g2;
-        }
-        __syncthreads();
-        stage = 2; // fall through to the update from scal[SC_TMP0..1]
-    }
-    if (stage != 1 && mode != 0 && mode != 3 && mode != 4 && scal[SC_CONV] != 0.0) return;
-    double s1, s2;
-    if (stage != 2) {
-        double a = 0.0, b2 = 0.0;
-        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[k]; if (mode == 0 || mode == 3) b2 += partial[nblk_max + k]; }
-        s1 = block_sum(a, sm);
-        s2 = block_sum(b2, sm);
-        if (stage == 1) {
-            if (threadIdx.x == 0) { scal[SC_TMP0] = s1; scal[SC_TMP1] = s2; }
-            return;
-        }
-    } else { s1 = scal[SC_TMP0]; s2 = scal[SC_TMP1]; }
-    if (threadIdx.x != 0) return;
-    if (mode == 0) {
-        scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_BNORM2] = s2;
-        const double tol = atol + rtol * sqrt(s1); // Krylov: eps = atol + rtol*||r0||
-        scal[SC_TOL] = tol;
-        scal[SC_ITER] = 0.0;
-        scal[SC_CONV] = (sqrt(s1) <= tol) ? 1.0 : 0.0;
-    } else if (mode == 1) {
-        scal[SC_PAP] = s1;
-        scal[SC_ALPHA] = scal[SC_RR] / s1;
-    } else if (mode == 2) {
-        const double rr_old = scal[SC_RR];
-        scal[SC_BETA] = s1 / rr_old;
-        scal[SC_RR] = s1;
-        scal[SC_ITER] += 1.0;
-        if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
-    } else if (mode == 3) {
-        scal[SC_RES2] = s1; scal[SC_BNORM2] = s2;
-    } else if (mode == 4) { // MINRES init: beta1 = ||r0||
-        const double beta1 = sqrt(s1);
-        scal[MR_BETA1] = beta1; scal[MR_BETA] = beta1; scal[MR_OLDB] = 0.0; scal[MR_DBAR] = 0.0; scal[MR_EPS] = 0.0;
-        scal[MR_CS] = -1.0; scal[MR_SN] = 0.0; scal[MR_PHIBAR] = beta1; scal[MR_ANORM2] = 0.0; scal[MR_GMAX] = 0.0;
-        scal[MR_GMIN] = __longlong_as_double(0x7ff0000000000000ll); scal[MR_XENORM2] = 0.0;
-        for (int k = 0; k < 5; k++) scal[MR_ERRV + k] = 0.0;
-        scal[SC_TOL] = atol + rtol * beta1;
-        scal[SC_ITER] = 0.0;
-        scal[SC_CONV] = (beta1 == 0.0 || beta1 <= scal[SC_TOL]) ? 1.0 : 0.0;
-        scal[SC_SOLVED] = scal[SC_CONV];
-    } else if (mode == 5) { // alpha = v.y / beta ; delta = cs*dbar + sn*alpha
-        const double alpha = s1 / scal[MR_BETA];
-        scal[SC_ALPHA] = alpha;
-        scal[MR_DELTA] = scal[MR_CS] * scal[MR_DBAR] + scal[MR_SN] * alpha;
-    } else if (mode == 6) { // new beta, plane rotation
-        const double alpha = scal[SC_ALPHA], oldb = scal[MR_BETA], cs = scal[MR_CS], sn = scal[MR_SN], dbar = scal[MR_DBAR];
-        const double beta = sqrt(s1);
-        scal[MR_OLDB] = oldb; scal[MR_BETA] = beta;
-        scal[MR_ANORM2] = scal[MR_ANORM2] + alpha * alpha + oldb * oldb + beta * beta;
-        const double gbar = sn * dbar - cs * alpha;
-        scal[MR_EPS] = sn * beta;
-        scal[MR_DBAR] = -cs * beta;
-        scal[MR_ROOT] = sqrt(gbar * gbar + scal[MR_DBAR] * scal[MR_DBAR]);
-        double gamma = sqrt(gbar * gbar + beta * beta);
-        gamma = gamma > 2.220446049250313e-16 ? gamma : 2.220446049250313e-16;
-        scal[MR_GAMMA] = gamma;
-        scal[MR_CS] = gbar / gamma; scal[MR_SN] = beta / gamma;
-        scal[MR_PHI] = scal[MR_CS] * scal[MR_PHIBAR];
-        scal[MR_PHIBAR] = scal[MR_SN] * scal[MR_PHIBAR];
-    } else if (mode == 7) { // stopping tests (s1 = ||x||^2)
-        const double epsM = 2.220446049250313e-16, etol = sqrt(epsM), ctol = sqrt(epsM);
-        const int iter = (int)scal[SC_ITER] + 1;
-        scal[SC_ITER] = (double)iter;
-        const double gamma = scal[MR_GAMMA], phi = scal[MR_PHI];
-        scal[MR_ERRV + (iter % 5)] = phi;
-        double err_lbnd = 0.0;
-        if (iter >= 5) { double e2 = 0.0; for (int k = 0; k < 5; k++) e2 += scal[MR_ERRV + k] * scal[MR_ERRV + k]; err_lbnd = sqrt(e2); }
-        scal[MR_GMAX] = scal[MR_GMAX] > gamma ? scal[MR_GMAX] : gamma;
-        scal[MR_GMIN] = scal[MR_GMIN] < gamma ? scal[MR_GMIN] : gamma;
-        const double ANorm = sqrt(scal[MR_ANORM2]), xNorm = sqrt(s1), Acond = scal[MR_GMAX] / scal[MR_GMIN], rNorm = scal[MR_PHIBAR];
-        const double test1 = rNorm / (ANorm * xNorm), test2 = scal[MR_ROOT] / ANorm, tol = scal[SC_TOL];
-        scal[MR_XENORM2] = scal[MR_XENORM2] + phi * phi;
-        const bool ill = (1.0 + 1.0 / Acond <= 1.0) || (1.0 / Acond <= ctol);
-        const bool solved = (1.0 + test2 <= 1.0) || (test2 <= tol) || (1.0 + test1 <= 1.0) || (test1 <= tol) ||
-                            (iter >= 5 && err_lbnd <= etol * sqrt(scal[MR_XENORM2])) || (rNorm + 1.0 <= 1.0) || (rNorm <= tol);
-        scal[SC_RR] = rNorm * rNorm;
-        if (solved || ill || !(rNorm == rNorm)) scal[SC_CONV] = 1.0;
-        if (solved && rNorm == rNorm) scal[SC_SOLVED] = 1.0; // Krylov's stats.solved: false for the ill-conditioned and NaN exits
-    }
-}
-
 // What the host looks at between batches (CONV, ITER, RES2, BNORM2) goes to mapped pinned memory with one tiny kernel
 // per batch -- not a device->host memcpy, which would queue behind a background copy of the edge view, and not a
 // store from every scalar kernel, whose system-scope fence would stall behind that copy's PCIe traffic.
-__global__ void k_publish_scalars(const double *__restrict__ scal, double *host) {
+__global__ void k_publish_scalars(const double *__restrict__ scal, double *host, const int *dead) {
     if (threadIdx.x == 0) {
+        host[SC_DEAD] = (double)*dead;
         host[SC_CONV] = scal[SC_CONV]; host[SC_ITER] = scal[SC_ITER]; host[SC_SOLVED] = scal[SC_SOLVED];
         host[SC_RES2] = scal[SC_RES2]; host[SC_BNORM2] = scal[SC_BNORM2];
         __threadfence_system();
@@ -672,36 +686,68 @@ __global__ void __launch_bounds__(PR_BLOCK) k_axpy1(int nslot, const double *__r
 
 // r -= alpha Ap ; partial(r.r).  The x update rides along with the p update below, which reads p anyway:
 // 8 instead of 9 vector streams per iteration, same arithmetic per element.
-__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_r(int nslot, const double *__restrict__ scal, const double *__restrict__ Ap,
-                                                          double *__restrict__ r, double *__restrict__ partial) {
+template <bool FUSE>
+__global__ void __launch_bounds__(PR_BLOCK) k_cg_update_r(int nslot, double *scal, const double *__restrict__ Ap,
+                                                          double *__restrict__ r, double *__restrict__ partial, FuseArgs fz) {
     __shared__ double sm[32];
-    if (scal[SC_CONV] != 0.0) return;
+    const bool idle = scal[SC_CONV] != 0.0;
+    if (idle && !FUSE) return;
     const double alpha = scal[SC_ALPHA];
     double rr = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (idle ? 0 : nslot); i += gridDim.x * blockDim.x) {
         const double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
         rr += ri * ri;
     }
     const double s = block_sum(rr, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    if (FUSE && lv_last_block(fz.ticket)) { // mode 2: beta, iteration count, convergence test
+        cg_finish(2, fz.stage, gridDim.x, fz.nblk_max, partial, scal, fz.rtol, fz.atol, fz.mail);
+        if (threadIdx.x == 0) *fz.ticket = 0;
+    }
 }
 
 // x += alpha p ; p = r + beta p.  `iter` is this iteration's 1-based index: the iteration that converged still
 // applies its x update (and skips the p update, which nobody reads); later queued iterations are no-ops.
+// PACK (strip decomposition over peer memory): the kernel also stores the new p of every slot a neighbour needs into
+// this rank's halo outbox (only slots outside [bounds[0], bounds[1]) can be such slots, so the lookup costs nothing in
+// the interior) and its last block publishes the exchange's sequence word -- no pack / signal launches.
+template <bool PACK>
 __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xp(int nslot, int iter, const double *__restrict__ scal, const double *__restrict__ r,
-                                                           double *__restrict__ x, double *__restrict__ p) {
+                                                           double *__restrict__ x, double *__restrict__ p, LvHaloPack hp) {
     const bool conv = scal[SC_CONV] != 0.0;
-    if (conv && scal[SC_ITER] != (double)iter) return;
+    const bool idle = conv && scal[SC_ITER] != (double)iter;
+    if (idle && !PACK) return;
     const double alpha = scal[SC_ALPHA], beta = scal[SC_BETA];
-    if (conv) {
+    bool wrote = false;
+    if (idle) {
+    } else if (conv) {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) x[i] += alpha * p[i];
-        return;
+    } else {
+        const int b0 = PACK ? hp.bounds[0] : 0, b1 = PACK ? hp.bounds[1] : 0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
+            const double pi = p[i];
+            x[i] += alpha * pi;
+            const double pn = r[i] + beta * pi;
+            p[i] = pn;
+            if (PACK && (i < b0 || i >= b1)) {
+                const int s0 = hp.send_pos0[i];
+                if (s0 >= 0) {
+                    hp.outbox[s0] = pn;
+                    const int s1 = hp.send_pos1[i];
+                    if (s1 >= 0) hp.outbox[s1] = pn;
+                    wrote = true;
+                }
+            }
+        }
     }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
-        const double pi = p[i];
-        x[i] += alpha * pi;
-        p[i] = r[i] + beta * pi;
+    if (PACK) {
+        if (wrote) __threadfence_system(); // the outbox is read by other GPUs
+        if (lv_last_block(hp.ticket) && threadIdx.x == 0) {
+            __threadfence_system();
+            lv_st_release_sys(hp.flag, hp.seq);
+            *hp.ticket = 0;
+        }
     }
 }
 
@@ -734,18 +780,25 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
     double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
     const int NBMAX = 4096;
     const int nb = pr_grid(c, ns), nb_mv = mv_grid<true>(c, ns), nb_mv0 = mv_grid<false>(c, ns);
-    // finish a reduction over the partials of the kernel launched just before (mode 1: the matvec's grid): locally,
-    // or through a 2-scalar allreduce when the grid is decomposed
+    // How a reduction is finished.  Single GPU, or several GPUs with mapped mailboxes: inside the producer kernel's last
+    // block (CG modes 1 and 2) or by a one-block launch (everything else); the mailbox variant exchanges the two local sums
+    // with every rank over NVLink and adds them in rank order.  Without mailboxes: reduce / ncclAllReduce / update.
+    const bool multi = c->comm != nullptr;
+    const bool fuse = !multi || c->mailbox_ready;
+    const bool peer = multi && lv_strip_peer_mode(c); // halo values through the exchange areas (NVLink pulls)
+    auto mail_next = [&]() -> MailArgs {
+        if (multi && c->mailbox_ready) return MailArgs{(LvMailSlot *const *)c->d_mailbox_ptrs, c->nranks, c->rank, ++c->ar_seq, c->d_tickets + 7};
+        return MailArgs{nullptr, 1, 0, 0, c->d_tickets + 7};
+    };
+    auto fuse_args = [&](int ticket) -> FuseArgs { return FuseArgs{c->d_tickets + ticket, (multi && c->mailbox_ready) ? 3 : 0, NBMAX, rtol, atol, mail_next()}; };
     auto finish = [&](int mode) -> int {
         const int nb = mode == 1 ? nb_mv : pr_grid(c, ns);
-        MailArgs mail{nullptr, 1, 0, 0};
-        if (!c->comm) { k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol, mail); c->launches++; return LV_OK; }
-        if (c->mailbox_ready) {
-            mail = MailArgs{(LvMailSlot *const *)c->d_mailbox_ptrs, c->nranks, c->rank, ++c->ar_seq};
-            k_cg_scalars<<<1, 256, 0, st>>>(mode, 3, nb, NBMAX, partial, scal, rtol, atol, mail);
+        if (fuse) {
+            k_cg_scalars<<<1, 256, 0, st>>>(mode, (multi && c->mailbox_ready) ? 3 : 0, nb, NBMAX, partial, scal, rtol, atol, mail_next());
             c->launches++;
             return LV_OK;
         }
+        const MailArgs mail{nullptr, 1, 0, 0, c->d_tickets + 7};
         k_cg_scalars<<<1, 256, 0, st>>>(mode, 1, nb, NBMAX, partial, scal, rtol, atol, mail);
         LV_TRY(lv_allreduce_sum(c, scal + SC_TMP0, 2));
         k_cg_scalars<<<1, 256, 0, st>>>(mode, 2, nb, NBMAX, partial, scal, rtol, atol, mail);
@@ -756,6 +809,13 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         LvProfScope prof(c, LV_PROF_MATVEC);
         mv_launch<false>(c, nb_mv0, st, ns, in, out, nullptr, scal);
     };
+    auto publish = [&]() -> int {
+        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red, c->d_tickets + 7);
+        else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+        LV_CUDA(c, cudaStreamSynchronize(st));
+        if (c->flags_mapped && c->h_red[SC_DEAD] != 0.0) return lv_set_error(c, LV_ECUDA, "a peer GPU did not arrive at an exchange (timeout)");
+        return LV_OK;
+    };
     LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
     matvec_plain(x, Ap);
     if (!minres) {
@@ -763,45 +823,51 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
             LvProfScope prof(c, LV_PROF_VECOPS);
             k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
             c->launches++;
-            LV_TRY(lv_halo_signal(c)); // p = r is ready for the neighbours
             LV_TRY(finish(0));
+            if (peer) LV_TRY(lv_strip_halo_post(c, p, 1)); // p = r is ready for the neighbours
         }
         // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
         // flag is set, so the host only has to look at the flag between batches.  The first batch is
         // sized by the previous solve (the fixed-point passes of find_pressure! need similar counts).
+        // Launches per iteration: [halo pull] matvec (+ alpha) / r update (+ beta, convergence) / x, p update (+ halo pack and
+        // signal) -- three on one GPU, four on several.
         int done = 0;
         while (done < itmax) {
             int batch = done == 0 ? (c->cg_hint > 8 ? c->cg_hint : 8) : 8;
             const int todo = itmax - done < batch ? itmax - done : batch;
             for (int it = 0; it < todo; it++) {
-                LV_TRY(lv_halo_pull_p(c, p)); // ghost columns of the search direction, read from the neighbours' memory
+                if (peer) LV_TRY(lv_strip_halo_pull(c, p)); // ghost columns of the search direction, out of the neighbours' outboxes
+                else if (multi) LV_TRY(lv_halo_exchange(c, p, 1));
                 {
                     LvProfScope prof(c, LV_PROF_MATVEC);
-                    mv_launch<true>(c, nb_mv, st, ns, p, Ap, partial, scal);
+                    if (fuse) mv_launch<true, true>(c, nb_mv, st, ns, p, Ap, partial, scal, fuse_args(0));
+                    else mv_launch<true, false>(c, nb_mv, st, ns, p, Ap, partial, scal);
                 }
                 LvProfScope prof(c, LV_PROF_VECOPS);
-                LV_TRY(finish(1));
-                k_cg_update_r<<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial);
-                LV_TRY(finish(2));
-                k_cg_update_xp<<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p);
+                if (fuse) k_cg_update_r<true><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, fuse_args(1));
+                else {
+                    LV_TRY(finish(1));
+                    k_cg_update_r<false><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, FuseArgs());
+                    LV_TRY(finish(2));
+                }
+                if (peer) {
+                    LvHaloPack hp;
+                    LV_TRY(lv_strip_pack_args(c, &hp));
+                    k_cg_update_xp<true><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, hp);
+                } else k_cg_update_xp<false><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, LvHaloPack());
                 c->launches += 2;
-                LV_TRY(lv_halo_signal(c));
             }
             done += todo;
-            if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
-            else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
-            LV_CUDA(c, cudaStreamSynchronize(st));
+            LV_TRY(publish());
             if (c->h_red[SC_CONV] != 0.0) break;
         }
     } else {
         // MINRES (the reference's Krylov method, pressure.jl:219), warm-started: solve A dx = b - A x0, x = x0 + dx.
-        // v = r2 lives in d_vec[1], the vector the neighbours map, so the peer-memory halo serves it as well.
         double *r1 = c->d_vec[0], *r2 = c->d_vec[1], *y = c->d_vec[2], *w1 = c->d_vec[3], *w2 = c->d_vec[4], *dx = c->d_vec[5];
         {
             LvProfScope prof(c, LV_PROF_VECOPS);
             k_mr_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap /* = A x0, same buffer as y */, r1, r2, w1, w2, dx, partial);
             c->launches++;
-            LV_TRY(lv_halo_signal(c));
             LV_TRY(finish(4));
         }
         int done = 0;
@@ -810,17 +876,16 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
             const int todo = itmax - done < batch ? itmax - done : batch;
             for (int it = 0; it < todo; it++) {
                 const int iter = done + it + 1;
-                LV_TRY(lv_halo_pull_p(c, r2));
+                LV_TRY(lv_halo_exchange(c, r2, 1));
                 {
                     LvProfScope prof(c, LV_PROF_MATVEC);
-                    mv_launch<true>(c, nb_mv, st, ns, r2, y, partial, scal);
+                    mv_launch<true, false>(c, nb_mv, st, ns, r2, y, partial, scal);
                 }
                 LvProfScope prof(c, LV_PROF_VECOPS);
                 k_mr_a<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r2, r1, y, partial);
                 LV_TRY(finish(5));
                 double *wa = (iter == 1) ? w1 : w1, *wb = w2; // iter == 1 works on w2 in place, later iterations build w in w1
                 k_mr_b<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r1, r2, y, wa, wb, partial);
-                LV_TRY(lv_halo_signal(c)); // r2 (the next v) is final
                 LV_TRY(finish(6));
                 k_mr_c<<<nb, PR_BLOCK, 0, st>>>(ns, scal, iter == 1 ? w2 : w1, dx, partial);
                 LV_TRY(finish(7));
@@ -828,9 +893,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
             }
             done += todo;
-            if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
-            else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
-            LV_CUDA(c, cudaStreamSynchronize(st));
+            LV_TRY(publish());
             if (c->h_red[SC_CONV] != 0.0) break;
         }
         k_axpy1<<<nb, PR_BLOCK, 0, st>>>(ns, dx, x); // x = x0 + dx
@@ -845,9 +908,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         k_resid<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, partial, NBMAX);
         c->launches++;
         LV_TRY(finish(3));
-        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
-        else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
-        LV_CUDA(c, cudaStreamSynchronize(st));
+        LV_TRY(publish());
         const double bn = c->h_red[SC_BNORM2], rn = c->h_red[SC_RES2];
         *relres = bn > 0.0 ? sqrt(rn / bn) : sqrt(rn);
     }
@@ -866,7 +927,7 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
     double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
     const int NBMAX = 4096;
     const int nb = pr_grid(c, n);
-    const MailArgs nomail{nullptr, 1, 0, 0};
+    const MailArgs nomail{nullptr, 1, 0, 0, c->d_tickets + 7};
     double *r1 = c->d_vec[0], *r2 = c->d_vec[1], *y = c->d_vec[2], *w1 = c->d_vec[3], *w2 = c->d_vec[4];
     LV_CUDA(c, cudaMemsetAsync(y, 0, sizeof(double) * (size_t)n, st)); // A*x0 with x0 = 0
     k_mr_init<<<nb, PR_BLOCK, 0, st>>>(n, b, y, r1, r2, w1, w2, x, partial);
@@ -889,7 +950,7 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
             if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
         }
         done += todo;
-        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red);
+        if (c->flags_mapped) k_publish_scalars<<<1, 32, 0, st>>>(scal, c->h_red, c->d_tickets + 7);
         else LV_CUDA(c, cudaMemcpyAsync(c->h_red, scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
         LV_CUDA(c, cudaStreamSynchronize(st));
         if (c->h_red[SC_CONV] != 0.0) { conv = true; break; }

@@ -14,8 +14,13 @@ The reference is shared-memory only; this is the decompo
   ``sent_sel[q]`` on one side, primary slots of the ghost labels on the other).  Per remesh a rank talks to its
   strip neighbours only -- counts, ghost generators, and (peer-memory halo) one message with its slot addresses
   and CUDA IPC handles; there is no collective over the whole group;
-* inside the Krylov loop the library pulls ghost values over NVLink from the neighbours' memory and sums the dot
-  products through peer mailboxes (NCCL send/recv + allreduce as the fallback).
+* with peer memory (the default) all of this runs INSIDE the library (csrc/lv_strip.cu): ghost selection, the exchange of
+  counts and ghost generators, the halo plan and every halo exchange are kernels that pull from the neighbours' exported
+  exchange areas over NVLink; per remesh the host synchronises once for the counts and makes no torch / NCCL call.  The
+  torch.distributed path below (``exchange_ghosts`` + ``_build_halo_plan``) is the fallback when CUDA IPC is unavailable
+  and the reference for the CPU tests;
+* inside the Krylov loop ghost values are pulled out of the neighbours' halo outboxes (packed by the kernel that produces the
+  search direction) and the dot products are summed through peer mailboxes (NCCL send/recv + allreduce as the fallback).
 
 Everything in this module is plain ``torch`` + ``torch.distributed`` and works on CPU tensors with the
 ``gloo`` backend (tests) as well as on CUDA tensors with ``nccl``; the compute calls go to liblvb200.
@@ -341,6 +346,50 @@ class StripGrid:
                 self._agree_on_peer_memory(st == 0)
         self.xy_own = torch.zeros((0, 2), dtype=torch.float64, device=self.dev)
         self.lab_own = torch.zeros(0, dtype=torch.int64, device=self.dev)
+        self._strip_ready = False        # library-side strip state (lv_strip_setup) allocated and peers mapped
+        self._owned_dirty = True
+        self.capacity_factor = 1.25      # head room of the local arrays and ghost outboxes over the first owned set
+
+    def _strip_setup(self) -> None:
+        """Collective, once: size and allocate the library's strip state, exchange the CUDA IPC handles of the exchange
+        areas and map the neighbours' areas.  Capacities are fixed from here on (nothing is reallocated per remesh)."""
+        g, L, plan = self.grid, self._L, self.plan
+        peers = plan.peers()
+        n_own = int(self.xy_own.shape[0])
+        rows = max(1, min(int(plan.R[self.rank + 1]), plan.row_hi + 1) - max(int(plan.R[self.rank]), plan.row_lo))
+        est = n_own / rows * (plan.H + 3) * (2 if len(peers) == 1 else 1)          # ghosts a neighbour takes from me
+        stat = torch.tensor([float(n_own), float(est)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(stat, op=dist.ReduceOp.MAX, group=self.group)
+        n_max, est_max = (float(v) for v in stat.cpu().tolist())
+        capg = int(2.0 * self.capacity_factor * est_max) + 8192
+        cap_loc = int(self.capacity_factor * n_max) + len(peers) * capg + 4096
+        npeer = len(peers)
+        # my index in each peer's (sorted) peer list -- the strip neighbourhood is symmetric
+        idx_there = []
+        for q in peers:
+            other = StripPlan.__new__(StripPlan)
+            other.__dict__.update(plan.__dict__)
+            other.rank = q
+            idx_there.append(other.peers().index(self.rank))
+        win = [plan.window(q) for q in peers]
+        arr = lambda v: (C.c_int32 * max(npeer, 1))(*v)  # noqa: E731
+        mine = (C.c_uint8 * 64)()
+        check(L.lv_strip_setup(g._h, npeer, arr(peers), arr(idx_there), arr([w[0] for w in win]), arr([w[1] for w in win]),
+                               C.c_int64(capg), C.c_int64(cap_loc), mine), g._h)
+        ok = True
+        if self.world > 1:
+            hb = torch.tensor(list(mine), dtype=torch.uint8, device=self.dev)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+            dist.all_gather(allh, hb, group=self.group)
+            flat = []
+            for q in peers:
+                flat += allh[q].cpu().tolist()
+            st = L.lv_strip_map(g._h, (C.c_uint8 * max(64 * npeer, 1))(*flat))
+            ok = st == 0
+            self._agree_on_peer_memory(ok)
+        self._strip_ready = bool(self.use_peer_memory or self.world == 1)
+        self._capg, self._cap_loc = capg, cap_loc
 
     def _agree_on_peer_memory(self, ok: bool) -> None:
         """CUDA IPC mapping can be refused (container policy).  All ranks switch to the NCCL path together."""
@@ -360,11 +409,18 @@ class StripGrid:
         self.lab_own = torch.as_tensor(labels, dtype=torch.int64, device=self.dev).contiguous()
         if self.lab_own.numel() and int(self.lab_own.max()) >= 2 ** 30:
             raise ValueError("global labels must stay below 2^30 (the bucket sort packs key and image bit into 32 bits)")
+        self._owned_dirty = True
 
     def set_owned_from_host(self, xy_host: np.ndarray, labels_dev: torch.Tensor) -> None:
         """Owned positions from (pinned) host memory, labels already on the device (end-to-end path)."""
+        if self._strip_ready and labels_dev is self.lab_own and not self._owned_dirty:
+            # straight into the library's local arrays: one host->device copy, labels unchanged
+            n = int(xy_host.shape[0])
+            check(self._L.lv_strip_set_owned(self.grid._h, n, ptr(xy_host), 1, None), self.grid._h)
+            return
         self.xy_own = torch.from_numpy(xy_host).to(self.dev, non_blocking=True)
         self.lab_own = labels_dev
+        self._owned_dirty = True
 
     def close(self) -> None:
         """Collective teardown: unmap all peer memory, wait for every rank, then free.  Memory exported over CUDA IPC
@@ -381,9 +437,51 @@ class StripGrid:
     def migrate(self) -> None:
         """After a move: hand generators that left the strip to their new owner."""
         self.xy_own, self.lab_own = migrate_generators(self.plan, self.xy_own, self.lab_own, self.group)
+        self._owned_dirty = True
 
     # -- remesh!(grid) --------------------------------------------------------------------------------
     def remesh(self) -> None:
+        """remesh!(grid) on the strips (collective).  With peer memory everything runs inside the library; otherwise the
+        torch.distributed path below."""
+        if self.use_peer_memory or self.world == 1:
+            return self._remesh_library()
+        return self._remesh_torch()
+
+    def _remesh_library(self) -> None:
+        g, L = self.grid, self._L
+        sp = torch.cuda.current_stream(self.dev).cuda_stream
+        if sp != getattr(self, "_stream_ptr", None):   # lv_set_stream synchronises: only when the stream really changes
+            g.set_stream(sp)
+            self._stream_ptr = sp
+        if not self._strip_ready:
+            self._strip_setup()
+            if not (self.use_peer_memory or self.world == 1):   # CUDA IPC refused on some rank: all ranks fall back together
+                return self._remesh_torch()
+        if self._owned_dirty:
+            n_own = int(self.xy_own.shape[0])
+            self._key_own = self.lab_own.to(torch.int32).contiguous()
+            check(L.lv_strip_set_owned(g._h, n_own, ptr(self.xy_own) if n_own else None, 0, ptr(self._key_own) if n_own else None), g._h)
+            self._n_own = n_own
+            self._owned_dirty = False
+        counts = (C.c_int64 * 9)()
+        check(L.lv_strip_remesh(g._h, counts), g._h)
+        self.n_loc = int(counts[0])
+        g._dev_n = self.n_loc
+        peers = self.plan.peers()
+        self.halo_counts = {q: (int(counts[1 + k]), int(counts[5 + k])) for k, q in enumerate(peers)}
+        n_own = self._n_own
+        # zero-copy views of the library's local arrays (owned first, then the ghosts peer by peer)
+        self.xy_loc = self._dev_tensor(6, "<f8", torch.float64, ncomp=2)
+        self.key_loc = self._dev_tensor(7, "<i4", torch.int32)
+        self.lab_loc = self.key_loc.to(torch.int64)
+        self.mask_loc = (torch.arange(self.n_loc, device=self.dev) < n_own).to(torch.uint8)
+        ranges, pos = {}, n_own
+        for k, q in enumerate(peers):
+            ranges[q] = (pos, pos + int(counts[5 + k]))
+            pos += int(counts[5 + k])
+        self.local = LocalSet(self.xy_loc, self.lab_loc, None, n_own, ranges, {})
+
+    def _remesh_torch(self) -> None:
         g, L = self.grid, self._L
         loc = exchange_ghosts(self.plan, self.xy_own, self.lab_own, self.group)
         self.local = loc
@@ -399,20 +497,18 @@ class StripGrid:
         if self.world > 1:
             self._build_halo_plan()
 
-    def _dev_tensor(self, which: int, typestr: str, torch_dtype):
+    def _dev_tensor(self, which: int, typestr: str, torch_dtype, ncomp: int = 1):
         p, n = C.c_void_p(), C.c_int64()
         check(self._L.lv_device_array(self.grid._h, which, C.byref(p), C.byref(n)), self.grid._h)
         if n.value == 0:
-            return torch.zeros(0, dtype=torch_dtype, device=self.dev)
-        return torch.as_tensor(_DevArray(p.value, n.value, typestr), device=self.dev)
+            return torch.zeros((0, ncomp) if ncomp > 1 else 0, dtype=torch_dtype, device=self.dev)
+        return torch.as_tensor(_DevArray(p.value, n.value, typestr, shape=(n.value, ncomp) if ncomp > 1 else None), device=self.dev)
 
     def _build_halo_plan(self) -> None:
         """Ghost slots are filled from their owners.  Both sides use the order of the list the owner sent: the
         receiver's slots are the primary slots of its ghost labels (appended peer by peer in that order), the
         sender's slots are the primary slots of ``sent_sel[q]``.  Periodic-image entries of ghosts need no values
-        (edges refer to the primary slot).  For the peer-memory halo one neighbour-only message per peer carries
-        the sender's slots -- the addresses the receiver will load from -- and the CUDA IPC handles of its vector:
-        no collective over the whole group per remesh."""
+        (edges refer to the primary slot).  (NCCL fallback path; with peer memory the library builds the plan itself.)"""
         g, L, loc = self.grid, self._L, self.local
         prim = self._dev_tensor(1, "<i4", torch.int32)                             # primary slot of every local label
         peers = self.plan.peers()
@@ -435,27 +531,6 @@ class StripGrid:
         check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(s_all) if s_all.numel() else None, rc,
                              ptr(r_all) if r_all.numel() else None), g._h)
         self.halo_counts = {q: (int(send_slots[q].numel()), int(recv_slots[q].numel())) for q in peers}
-        if self.use_peer_memory and npeer:
-            # message to peer q: [16 words of IPC handles | my primary slots of what I sent it]; sizes are known on both sides
-            mine = (C.c_uint8 * 128)()
-            check(L.lv_peer_export(g._h, mine), g._h)
-            if bytes(mine) != getattr(self, "_handle_bytes", None):
-                self._handle_bytes = bytes(mine)
-                self._handle_words = torch.frombuffer(bytearray(self._handle_bytes), dtype=torch.int64).to(self.dev)
-            msgs = {q: torch.cat([self._handle_words, send_slots[q].to(torch.int64)]).unsqueeze(1) for q in peers}
-            sizes = {q: 16 + int(recv_slots[q].numel()) for q in peers}
-            got = exchange_with_peers(msgs, peers, self.dev, torch.int64, 1, self.group, counts_in=sizes)
-            remote = torch.cat([got[q][16:, 0] for q in peers]).to(torch.int32).contiguous()
-            hw = torch.cat([got[q][:16, 0] for q in peers]).cpu().numpy().tobytes()   # one sync; also orders the stream
-            harr = (C.c_uint8 * (128 * npeer)).from_buffer_copy(hw)
-            self._remote_keep = remote
-            torch.cuda.current_stream(self.dev).synchronize()
-            st = L.lv_peer_plan(g._h, npeer, harr, ptr(remote) if remote.numel() else None)
-            if not getattr(self, "_peer_agreed", False):
-                self._agree_on_peer_memory(st == 0)  # collective, first plan only: mapping either works on this box or not
-                self._peer_agreed = True
-            else:
-                check(st, g._h)
 
     # -- results --------------------------------------------------------------------------------------
     def owned_index(self) -> torch.Tensor:

@@ -268,8 +268,10 @@ def test_gresho_vortex_on_the_gpu(lv, oracle):
 
 
 def test_sedov_blast_on_the_gpu(lv, oracle):
-    """examples/sedov.jl (BASELINE config) at N = 40, every operator of the step on the GPU (CG pressure solve): same
-    comparison with the reference's semi-analytic profile as tests/test_oracle.py runs on the restatement."""
+    """examples/sedov.jl (BASELINE config) at N = 40, every operator of the step on the GPU, pressure solve by the
+    reference's Krylov method (MINRES, reference tolerances): same comparison with the reference's semi-analytic profile as
+    tests/test_oracle.py runs on the restatement.  (At atol = rtol = 1e-6 the stopping point -- hence the noisy wake --
+    depends on the Krylov method: CG gives a wake error of 13 % on the GPU and on the CPU restatement alike, MINRES 8 %.)"""
     from . import sedov_case as C
     S = lv.stepping
     N = 40
@@ -284,7 +286,7 @@ def test_sedov_blast_on_the_gpu(lv, oracle):
         getattr(g, k)[...] = val
     E0 = (g.mass * g.e).sum()
     S.to_device(g)
-    solver = lv.PressureSolver(g)
+    solver = lv.PressureSolver(g, solver="minres")
     for dt in C.time_steps(dr):
         S.move(g, dt)
         S.ideal_eos(g, C.GAMMA, C.P0)
