@@ -220,8 +220,8 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
 int lv_pr_ensure(LvContext *c);
 int lv_pr_assemble(LvContext *c, double dt);
 int lv_pr_matvec(LvContext *c, const double *x, double *y); // slot-order device vectors
-int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall);
-int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres);
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done);
+int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres, bool pre_init);
 int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver,
                         const double *vbc_wall, int32_t *iters_out, double *relres_out);
 int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *, double *)> &apply, const double *b, double *x,

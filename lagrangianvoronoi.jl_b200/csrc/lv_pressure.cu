@@ -501,44 +501,118 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned c
     GP[i] = make_double2(gx / mi, gy / mi);
 }
 
+// Later passes, sweep 1 fused with the first matvec of the solve: both gather P_j over the same row, so
+// GP_i (pressure.jl:178,185) and (A P)_i (pressure.jl:119-130, the A x0 of the warm-started Krylov solve) come out of
+// one CSR walk.  (A P)_i is accumulated exactly like k_matvec does (diagonal first, neighbours in edge order).
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp_mv(int nslot, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
+                                                        const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mx_in,
+                                                        const double *__restrict__ w, const double *__restrict__ diag,
+                                                        const double *__restrict__ mass, const double *__restrict__ P,
+                                                        double2 *__restrict__ GP, double *__restrict__ AP) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    const double Pi = P[i];
+    if (!own[i]) { GP[i] = make_double2(0.0, 0.0); AP[i] = diag[i] * Pi; return; }
+    const int r0 = rowptr[i], d = rdeg[i];
+    int cj[RH_U];
+    double lr[RH_U], pj[RH_U], wk[RH_U];
+    double2 mm[RH_U];
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) {
+        cj[k] = k < d ? col[r0 + k] : -1;
+        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+        wk[k] = k < d ? w[r0 + k] : 0.0;
+        mm[k] = k < d ? mx_in[r0 + k] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) pj[k] = cj[k] >= 0 ? P[cj[k]] : Pi;
+    double gx = 0.0, gy = 0.0, yi = diag[i] * Pi;
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) {
+        if (k < d) yi += wk[k] * (Pi - pj[k]);
+        if (k < d && cj[k] >= 0) {
+            const double s = lr[k] * (Pi - pj[k]);
+            gx -= s * mm[k].x;
+            gy -= s * mm[k].y;
+        }
+    }
+    for (int k = RH_U; k < d; k++) {
+        const int j = col[r0 + k];
+        const double pv = j >= 0 ? P[j] : Pi;
+        yi += w[r0 + k] * (Pi - pv);
+        if (j < 0) continue;
+        const double s = lrr_in[r0 + k] * (Pi - pv);
+        const double2 m = mx_in[r0 + k];
+        gx -= s * m.x;
+        gy -= s * m.y;
+    }
+    const double mi = mass[i];
+    GP[i] = make_double2(gx / mi, gy / mi);
+    AP[i] = yi;
+}
+
 // Later passes, sweep 2: b_i = A_i P_i/(rho c2 dt^2) + bvel_i + sum lrr (GP_i - GP_j).(m - z)   pressure.jl:171,189-202
-__global__ void __launch_bounds__(PR_BLOCK, 8) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
+// INIT: the kernel is also the CG initialisation (k_cg_init): r = b - A x0 with A x0 from k_rhs_gp_mv, p = r and the block
+// partials of r.r and b.b -- grid-stride with k_cg_init's grid and accumulation order, so the sums are bit-identical to it.
+template <bool INIT>
+__global__ void __launch_bounds__(PR_BLOCK, INIT ? 4 : 8) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
                                                        const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mz_in,
                                                        const double *__restrict__ area, const double *__restrict__ rho,
                                                        const double *__restrict__ c2, const double *__restrict__ P,
                                                        const double *__restrict__ bvel, const double2 *__restrict__ GP,
-                                                       double *__restrict__ b) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nslot) return;
-    if (!own[i]) { b[i] = 0.0; return; }
-    const double2 gi = GP[i];
-    double bi = (area[i] * P[i]) / ((rho[i] * c2[i]) * (dt * dt)) + bvel[i];
-    const int r0 = rowptr[i], d = rdeg[i];
-    int cj[RH_U];
-    double lr[RH_U];
-    double2 mm[RH_U], gj[RH_U];
+                                                       double *__restrict__ b, const double *__restrict__ AP, double *__restrict__ r,
+                                                       double *__restrict__ p, double *__restrict__ partial, int nblk_max) {
+    __shared__ double sm[32];
+    double rr = 0.0, bb = 0.0;
+    const int stride = INIT ? gridDim.x * blockDim.x : nslot;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += stride) {
+        double bi = 0.0;
+        if (own[i]) {
+            const double2 gi = GP[i];
+            bi = (area[i] * P[i]) / ((rho[i] * c2[i]) * (dt * dt)) + bvel[i];
+            const int r0 = rowptr[i], d = rdeg[i];
+            int cj[RH_U];
+            double lr[RH_U];
+            double2 mm[RH_U], gj[RH_U];
 #pragma unroll
-    for (int k = 0; k < RH_U; k++) {
-        cj[k] = k < d ? col[r0 + k] : -1;
-        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
-        mm[k] = k < d ? mz_in[r0 + k] : make_double2(0.0, 0.0);
+            for (int k = 0; k < RH_U; k++) {
+                cj[k] = k < d ? col[r0 + k] : -1;
+                lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+                mm[k] = k < d ? mz_in[r0 + k] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < RH_U; k++) gj[k] = cj[k] >= 0 ? GP[cj[k]] : gi;
+#pragma unroll
+            for (int k = 0; k < RH_U; k++)
+                if (k < d && cj[k] >= 0) bi += lr[k] * ((gi.x - gj[k].x) * mm[k].x + (gi.y - gj[k].y) * mm[k].y); // :198
+            for (int k = RH_U; k < d; k++) {
+                const int j = col[r0 + k];
+                if (j < 0) continue;
+                const double2 g2 = GP[j], m = mz_in[r0 + k];
+                bi += lrr_in[r0 + k] * ((gi.x - g2.x) * m.x + (gi.y - g2.y) * m.y);
+            }
+        }
+        b[i] = bi;
+        if (INIT) {
+            const double ri = bi - AP[i];
+            r[i] = ri;
+            p[i] = ri;
+            rr += ri * ri;
+            bb += bi * bi;
+        }
     }
-#pragma unroll
-    for (int k = 0; k < RH_U; k++) gj[k] = cj[k] >= 0 ? GP[cj[k]] : gi;
-#pragma unroll
-    for (int k = 0; k < RH_U; k++)
-        if (k < d && cj[k] >= 0) bi += lr[k] * ((gi.x - gj[k].x) * mm[k].x + (gi.y - gj[k].y) * mm[k].y); // :198
-    for (int k = RH_U; k < d; k++) {
-        const int j = col[r0 + k];
-        if (j < 0) continue;
-        const double2 g2 = GP[j], m = mz_in[r0 + k];
-        bi += lrr_in[r0 + k] * ((gi.x - g2.x) * m.x + (gi.y - g2.y) * m.y);
+    if (INIT) {
+        const double s1 = block_sum(rr, sm);
+        const double s2 = block_sum(bb, sm);
+        if (threadIdx.x == 0) { partial[blockIdx.x] = s1; partial[nblk_max + blockIdx.x] = s2; }
     }
-    b[i] = bi;
 }
 
-int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
+static inline int pr_grid(const LvContext *c, int64_t n);
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done) {
+    if (init_done) *init_done = false;
     LV_TRY(lv_pr_ensure(c));
     if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
     if (!c->assembled || c->asm_dt != dt) LV_TRY(lv_pr_assemble(c, dt)); // the per-edge factors come from the assembly
@@ -560,14 +634,24 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall) {
         c->bvel_valid = true;
     }
     if (gp_step) {
+        // fused with the start of the CG solve (its first matvec and k_cg_init) when the caller is find_pressure!
+        const bool fused = fuse_init && !first;
         if (!first) {
-            k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
-                                                     c->d_GP);
+            if (fused) k_rhs_gp_mv<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_w, c->d_diag,
+                                                                   c->d_mass, c->d_P, c->d_GP, c->d_vec[2]);
+            else k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
+                                                          c->d_GP);
             c->launches++;
         }
         LV_TRY(lv_halo_exchange(c, (double *)c->d_GP, 2));
-        k_rhs_corr<<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
-                                                   c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b);
+        if (fused) {
+            k_rhs_corr<true><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area,
+                                                                         c->d_rho, c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, c->d_vec[2],
+                                                                         c->d_vec[0], c->d_vec[1], c->d_red + SC_COUNT, 4096);
+            if (init_done) *init_done = true;
+        } else
+            k_rhs_corr<false><<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
+                                                              c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, nullptr, nullptr, nullptr, nullptr, 4096);
         c->launches++;
     }
     LV_CUDA(c, cudaGetLastError());
@@ -638,16 +722,19 @@ __global__ void __launch_bounds__(PR_BLOCK) k_mr_a(int nslot, int iter, const do
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 // y -= (alpha/beta) r2; w update; r1 = r2; r2 = y; partial(r2.r2)
+// `own` (nullable): rows this rank owns.  Ghost slots of v = r2 hold the neighbours' values after the halo exchange; they
+// must not enter the recurrences or the norms, so they are read as zero (and left zero for the next exchange to refill).
 __global__ void __launch_bounds__(PR_BLOCK) k_mr_b(int nslot, int iter, const double *__restrict__ scal, double *__restrict__ r1,
                                                    double *__restrict__ r2, const double *__restrict__ y, double *__restrict__ wa /* w1 */,
-                                                   double *__restrict__ wb /* w2 */, double *__restrict__ partial) {
+                                                   double *__restrict__ wb /* w2 */, double *__restrict__ partial,
+                                                   const unsigned char *__restrict__ own) {
     __shared__ double sm[32];
     if (scal[SC_CONV] != 0.0) return;
     const double beta = scal[MR_BETA], alpha = scal[SC_ALPHA], eps_old = scal[MR_EPS], delta = scal[MR_DELTA];
     const double c2 = -alpha / beta, ib = 1.0 / beta;
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
-        const double vi = r2[i];
+        const double vi = (own == nullptr || own[i]) ? r2[i] : 0.0;
         const double yi = y[i] + c2 * vi;
         if (iter == 1) wb[i] = wb[i] + ib * vi;
         else {
@@ -767,7 +854,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_resid(int nslot, const double *__r
 }
 
 // A x = b with x = c->d_P (initial guess in, solution out), b = c->d_b
-int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres) {
+int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres, bool pre_init) {
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     if (solver != LV_SOLVER_CG && solver != LV_SOLVER_MINRES) return lv_set_error(c, LV_EINVAL, "unknown solver %d", solver);
     const bool minres = solver == LV_SOLVER_MINRES;
@@ -816,13 +903,18 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         if (c->flags_mapped && c->h_red[SC_DEAD] != 0.0) return lv_set_error(c, LV_ECUDA, "a peer GPU did not arrive at an exchange (timeout)");
         return LV_OK;
     };
-    LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
-    matvec_plain(x, Ap);
+    if (pre_init && minres) return lv_set_error(c, LV_EINVAL, "pre-initialised solves are CG only");
+    if (!pre_init) {
+        LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
+        matvec_plain(x, Ap);
+    }
     if (!minres) {
         {
             LvProfScope prof(c, LV_PROF_VECOPS);
-            k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
-            c->launches++;
+            if (!pre_init) { // otherwise the right-hand-side kernels left r, p and the partial sums behind (lv_pr_rhs)
+                k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
+                c->launches++;
+            }
             LV_TRY(finish(0));
             if (peer) LV_TRY(lv_strip_halo_post(c, p, 1)); // p = r is ready for the neighbours
         }
@@ -885,7 +977,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                 k_mr_a<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r2, r1, y, partial);
                 LV_TRY(finish(5));
                 double *wa = (iter == 1) ? w1 : w1, *wb = w2; // iter == 1 works on w2 in place, later iterations build w in w1
-                k_mr_b<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r1, r2, y, wa, wb, partial);
+                k_mr_b<<<nb, PR_BLOCK, 0, st>>>(ns, iter, scal, r1, r2, y, wa, wb, partial, multi ? c->d_own : nullptr);
                 LV_TRY(finish(6));
                 k_mr_c<<<nb, PR_BLOCK, 0, st>>>(ns, scal, iter == 1 ? w2 : w1, dx, partial);
                 LV_TRY(finish(7));
@@ -942,7 +1034,7 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
             LV_TRY(apply(r2, y));
             k_mr_a<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r2, r1, y, partial);
             k_cg_scalars<<<1, 256, 0, st>>>(5, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
-            k_mr_b<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r1, r2, y, w1, w2, partial);
+            k_mr_b<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r1, r2, y, w1, w2, partial, nullptr);
             k_cg_scalars<<<1, 256, 0, st>>>(6, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
             k_mr_c<<<nb, PR_BLOCK, 0, st>>>(n, scal, iter == 1 ? w2 : w1, x, partial);
             k_cg_scalars<<<1, 256, 0, st>>>(7, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
@@ -966,10 +1058,11 @@ int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double 
                         int32_t *iters_out, double *relres_out) {
     LV_TRY(lv_pr_assemble(c, dt));
     for (int it = 1; it <= niter; it++) {
-        LV_TRY(lv_pr_rhs(c, dt, it > 1, vbc_wall));
+        bool init_done = false;
+        LV_TRY(lv_pr_rhs(c, dt, it > 1, vbc_wall, solver == LV_SOLVER_CG, &init_done));
         int iters = 0;
         double relres = 0.0;
-        LV_TRY(lv_pr_solve(c, solver, rtol, atol, itmax, &iters, relres_out ? &relres : nullptr));
+        LV_TRY(lv_pr_solve(c, solver, rtol, atol, itmax, &iters, relres_out ? &relres : nullptr, init_done));
         if (iters_out) iters_out[it - 1] = iters;
         if (relres_out) relres_out[it - 1] = relres;
     }
@@ -1180,7 +1273,7 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
 int32_t lv_pressure_rhs(LvHandle c, double dt, int32_t gp_step, const double *vbc_wall, double *b, double *GP) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
-    LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall));
+    LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall, false, nullptr));
     if (b) LV_TRY(download_slots(c, c->d_b, b, 1));
     if (GP) LV_TRY(download_slots(c, (const double *)c->d_GP, GP, 2));
     return LV_OK;
@@ -1221,7 +1314,7 @@ int32_t lv_pressure_solve(LvHandle c, int32_t solver, const double *b, double *x
         if (st == LV_OK) st = lv_gather_to_slots(c, (const double *)stage, dsts[k], 1, 0.0);
         cudaStreamSynchronize(c->stream);
     }
-    if (st == LV_OK) st = lv_pr_solve(c, solver, rtol, atol, itmax, iters, relres);
+    if (st == LV_OK) st = lv_pr_solve(c, solver, rtol, atol, itmax, iters, relres, false);
     if (st == LV_OK) st = download_slots(c, c->d_P, x, 1);
     return st;
 }
