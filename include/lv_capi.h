@@ -131,19 +131,29 @@ int32_t lv_pressure_operator(LvHandle h, int64_t *rowptr, int64_t *col, double *
                              double *diag);
 /* mul!(y, A, x) (pressure.jl:119-130), x and y in label order */
 int32_t lv_pressure_matvec(LvHandle h, const double *x, double *y);
+/* boundaries(p) (iterators.jl:50-57) of the whole mesh, numbered polygon by polygon in label order and, inside a polygon,
+ * in edge order: *count, and for every boundary edge its midpoint (2 doubles), wall label (-1..-4) and 1-based polygon
+ * (any array may be NULL; cap = capacity in edges).  This is what a host needs to evaluate the reference's closures
+ * boundary_velocity(midpoint(e), e.label) (pressure.jl:182), vDirichlet(m) and charfun(m) (diffusion.jl:64-70) per edge. */
+int32_t lv_boundary_edges(LvHandle h, int64_t *count, double *midpoint, int64_t *label, int64_t *polygon, int64_t cap);
+/* boundary velocity per boundary edge (2 doubles each, numbering of lv_boundary_edges), used by every right-hand side built
+ * from now on until the next remesh; NULL returns to the four per-wall constants vbc_wall */
+int32_t lv_set_boundary_velocity(LvHandle h, const double *vbc_edge, int64_t n_edge);
 /* refresh!(solver, dt, gp_step, boundary_velocity) (pressure.jl:162-203).  vbc_wall[4][2] is
- * the boundary velocity per wall code (row -label-1), NULL = zero_vbc (pressure.jl:205).
- * Outputs b[n], GP[2n] in label order (either may be NULL). */
+ * the boundary velocity per wall code (row -label-1), NULL = zero_vbc (pressure.jl:205); per-edge values set with
+ * lv_set_boundary_velocity take precedence.  Outputs b[n], GP[2n] in label order (either may be NULL). */
 int32_t lv_pressure_rhs(LvHandle h, double dt, int32_t gp_step, const double *vbc_wall, double *b,
                         double *GP);
 /* find_pressure!(solver, dt, niter; boundary_velocity) (pressure.jl:215-225).
  * Reference defaults: niter 10, rtol = atol = 1e-6, itmax 1000 (pressure.jl:219).
  * Host form gathers the fields, solves and writes P_out[n]; iters_out[niter] and
- * relres_out[niter] (true relative residual ||b - A P|| / ||b|| after each pass) may be NULL. */
+ * relres_out[niter] (true relative residual ||b - A P|| / ||b|| after each pass) may be NULL.
+ * vbc_edge (nullable): boundary_velocity evaluated by the caller per boundary edge (2 doubles each, n_vbc_edge edges in
+ * the numbering of lv_boundary_edges); NULL = the four per-wall constants vbc_wall (exact for the reference's examples). */
 int32_t lv_find_pressure(LvHandle h, double dt, int32_t niter, double rtol, double atol, int32_t itmax,
                          int32_t solver, const double *mass, const double *rho, const double *c2,
-                         const double *P_in, const double *v, const double *vbc_wall, double *P_out,
-                         int32_t *iters_out, double *relres_out);
+                         const double *P_in, const double *v, const double *vbc_wall, const double *vbc_edge,
+                         int64_t n_vbc_edge, double *P_out, int32_t *iters_out, double *relres_out);
 /* Device-resident form on the fields uploaded with lv_fields_upload*; P stays resident. */
 int32_t lv_find_pressure_dev(LvHandle h, double dt, int32_t niter, double rtol, double atol,
                              int32_t itmax, int32_t solver, const double *vbc_wall, int32_t *iters_out,
@@ -172,6 +182,11 @@ int32_t lv_step_viscous_step(LvHandle h, double dt, int32_t artificial_viscosity
 /* bdary_friction!(grid, vDirichlet, dt) diffusion.jl:64-80; vwall[4][2] = the closure's value on the walls UP, RIGHT, DOWN, LEFT
  * (NULL = all walls at rest), charfun = everywhere */
 int32_t lv_step_bdary_friction(LvHandle h, double dt, const double *vwall);
+/* general form: wall_on[4] (nullable = all) switches whole walls off (charfun constant per wall, e.g. examples/bubble.jl);
+ * v_edge (2 doubles) / on_edge (1 byte) per boundary edge in the numbering of lv_boundary_edges carry vDirichlet(m) and
+ * charfun(m) evaluated by the host at every boundary-edge midpoint (diffusion.jl:64-80); NULL falls back to vwall / on */
+int32_t lv_step_bdary_friction_ex(LvHandle h, double dt, const double *vwall, const uint8_t *wall_on, const double *v_edge,
+                                  const uint8_t *on_edge, int64_t n_edge);
 int32_t lv_step_find_dv(LvHandle h, double dt, double alpha);          /* find_dv!                 relaxation.jl:10-25 */
 int32_t lv_step_relaxation_step(LvHandle h, double dt, int32_t rusanov); /* relaxation_step!       relaxation.jl:36-73 (remeshes) */
 /* multiphase_projection!(solver) (relaxation.jl:179-206; MultiphaseProjector mul! :91-123, refresh! :162-177).  Reference

@@ -132,16 +132,31 @@ function remesh_b200!(grid::VoronoiGrid)
 end
 
 # ---- find_pressure!  src/pressure.jl:215-225 ---------------------------------------------------
-# boundary_velocity(midpoint, label) is a Julia closure (pressure.jl:182); no callback crosses the C
-# ABI, so it is evaluated here once per wall code at the wall's mid point (exact for the per-wall
-# constants the examples use, examples/piston.jl:122-127).
+# boundary_velocity(midpoint(e), e.label) is a Julia closure (pressure.jl:182); no callback crosses the C ABI, so it
+# is evaluated HERE for every boundary edge, in the order boundaries(p) yields them polygon by polygon (= the numbering
+# of lv_boundary_edges: the edge view is already on the host after remesh!).  When the values are constant along every
+# wall (all the reference's examples, e.g. examples/piston.jl:122-127) the four per-wall constants go down and the per-edge
+# array stays empty; otherwise the per-edge values do.
 function wall_velocities(grid::VoronoiGrid, boundary_velocity)
-    b = grid.boundary_rect
-    mids = (RealVector(0.5(b.xmin[1] + b.xmax[1]), b.xmax[2]),   # UP    = -1
-            RealVector(b.xmax[1], 0.5(b.xmin[2] + b.xmax[2])),   # RIGHT = -2
-            RealVector(0.5(b.xmin[1] + b.xmax[1]), b.xmin[2]),   # DOWN  = -3
-            RealVector(b.xmin[1], 0.5(b.xmin[2] + b.xmax[2])))   # LEFT  = -4
-    return RealVector[boundary_velocity(mids[k], -k) for k in 1:4]
+    wall = fill(VEC0, 4)
+    seen = falses(4)
+    constant = true
+    edge = RealVector[]
+    for p in grid.polygons, e in LagrangianVoronoi.boundaries(p)
+        vbc = boundary_velocity(LagrangianVoronoi.midpoint(e), e.label)
+        push!(edge, vbc)
+        k = -e.label
+        if 1 <= k <= 4
+            if !seen[k]
+                wall[k] = vbc; seen[k] = true
+            elseif wall[k] != vbc
+                constant = false
+            end
+        else
+            constant = false
+        end
+    end
+    return constant ? (wall, RealVector[]) : (wall, edge)
 end
 
 function staging(ctx::DeviceContext, name::Symbol, ::Type{T}, n::Int) where T
@@ -166,13 +181,14 @@ function find_pressure_b200!(solver::PressureSolver, dt::Float64, niter::Int64 =
             mass[i] = p.mass; rho[i] = p.rho; c2[i] = p.c2; P[i] = p.P; v[i] = p.v
         end
     end
-    vbc = wall_velocities(grid, boundary_velocity)
+    vbc, vbc_edge = wall_velocities(grid, boundary_velocity)
     iters = Vector{Int32}(undef, niter)
     relres = Vector{Float64}(undef, niter)
     check(ctx, ccall((:lv_find_pressure, LIB), Int32,
                      (Ptr{Cvoid}, Float64, Int32, Float64, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                      Ptr{Float64}, Ptr{RealVector}, Ptr{RealVector}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
-                     ctx.handle, dt, niter, rtol, atol, itmax, krylov, mass, rho, c2, P, v, vbc, P, iters,
+                      Ptr{Float64}, Ptr{RealVector}, Ptr{RealVector}, Ptr{RealVector}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+                     ctx.handle, dt, niter, rtol, atol, itmax, krylov, mass, rho, c2, P, v, vbc,
+                     isempty(vbc_edge) ? C_NULL : pointer(vbc_edge), length(vbc_edge), P, iters,
                      solver.verbose ? pointer(relres) : C_NULL))
     Threads.@threads for i in 1:n
         @inbounds grid.polygons[i].P = P[i]      # pressure.jl:221-223

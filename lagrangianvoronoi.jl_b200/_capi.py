@@ -20,14 +20,14 @@ PROF_SLOTS = {"cells": 0, "clip": 1, "assemble": 2, "matvec": 3, "vecops": 4}
 # every symbol include/lv_capi.h declares; tests check the library exports all of them
 SYMBOLS = [
     "lv_create", "lv_destroy", "lv_last_error", "lv_set_rects", "lv_grid_info", "lv_magic_path", "lv_set_stream",
-    "lv_sync", "lv_remesh", "lv_remesh_dev", "lv_mesh_nnz", "lv_mesh_download", "lv_mesh_faces", "lv_mesh_hash", "lv_clip_info", "lv_set_async_edges", "lv_mesh_wait",
+    "lv_sync", "lv_remesh", "lv_remesh_dev", "lv_mesh_nnz", "lv_mesh_download", "lv_mesh_faces", "lv_mesh_hash", "lv_boundary_edges", "lv_set_boundary_velocity", "lv_clip_info", "lv_set_async_edges", "lv_mesh_wait",
     "lv_pressure_create", "lv_pressure_destroy", "lv_fields_upload", "lv_fields_upload_dev", "lv_pressure_download",
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
     "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
     "lv_halo_plan", "lv_halo_exchange_dev", "lv_strip_setup", "lv_strip_map", "lv_strip_set_owned", "lv_strip_remesh", "lv_mailbox_export", "lv_mailbox_plan", "lv_peer_disable", "lv_peer_close",
     "lv_state_set", "lv_state_get", "lv_state_ptr", "lv_state_remesh", "lv_step_move", "lv_step_eos", "lv_step_find_pressure",
-    "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_bdary_friction", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection", "lv_step_multiphase_apply",
+    "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_bdary_friction", "lv_step_bdary_friction_ex", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection", "lv_step_multiphase_apply",
 ]
 
 
@@ -101,7 +101,10 @@ def load_library() -> C.CDLL:
     L.lv_pressure_matvec.argtypes = [vp, vp, vp]
     L.lv_pressure_rhs.argtypes = [vp, C.c_double, C.c_int32, vp, vp, vp]
     L.lv_find_pressure.argtypes = [vp, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32,
-                                   vp, vp, vp, vp, vp, vp, vp, i32p, dp]
+                                   vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, i32p, dp]
+    L.lv_boundary_edges.argtypes = [vp, ip, vp, vp, vp, C.c_int64]
+    L.lv_set_boundary_velocity.argtypes = [vp, vp, C.c_int64]
+    L.lv_step_bdary_friction_ex.argtypes = [vp, C.c_double, vp, vp, vp, vp, C.c_int64]
     L.lv_find_pressure_dev.argtypes = [vp, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                        vp, i32p, dp]
     L.lv_pressure_solve.argtypes = [vp, C.c_int32, vp, vp, C.c_double, C.c_double, C.c_int32, i32p, dp]

@@ -216,7 +216,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
-                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_tickets, c->d_scratch,
+                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_tickets, c->d_bdry_ptr, c->d_vbc_edge, c->d_bf_on, c->d_scratch,
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1], c->d_io_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
@@ -312,6 +312,8 @@ int lv_remesh_common(LvContext *c, int64_t n) {
     // permuted garbage now, so the "fields not uploaded" guards of lv_pr_assemble / lv_pr_rhs must fire again
     c->pr_valid = false;
     c->bvel_valid = false;
+    c->bdry_valid = false;   // boundary-edge numbering and per-edge wall data belong to the old mesh
+    c->vbc_edge_on = false;
     c->n = n;
     LV_TRY(lv_cells_build(c));
     LV_TRY(lv_clip_run(c));
@@ -594,6 +596,109 @@ extern "C" int32_t lv_mesh_hash(LvHandle c, const int32_t *global_label_dev, uin
     c->launches++;
     LV_CUDA(c, cudaMemcpyAsync(out, d, 48, cudaMemcpyDeviceToHost, c->stream));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+// ---- boundary edges (boundaries(p), iterators.jl:50-57) numbered in CSR order ------------------------------------
+__global__ void __launch_bounds__(256) k_bdry_count(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+                                                    const unsigned char *__restrict__ rdeg, const int *__restrict__ col, int *__restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = prim[i];
+    int d = 0;
+    if (s >= 0)
+        for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) d += col[k] < 0;
+    cnt[i] = d;
+}
+__global__ void __launch_bounds__(256) k_bdry_list(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
+                                                   const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                   const double2 *__restrict__ v1, const double2 *__restrict__ v2, const int *__restrict__ bptr,
+                                                   double2 *__restrict__ mid, long long *__restrict__ label, long long *__restrict__ poly) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = prim[i];
+    if (s < 0) return;
+    int o = bptr[i];
+    for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) {
+        const int cc = col[k];
+        if (cc >= 0) continue;
+        const double2 a = v1[k], b = v2[k];
+        if (mid) mid[o] = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y)); // midpoint(e)  geometry.jl:145-147
+        if (label) label[o] = cc;
+        if (poly) poly[o] = i + 1;
+        o++;
+    }
+}
+
+int lv_bdry_index(LvContext *c) {
+    if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
+    if (c->bdry_valid) return LV_OK;
+    const int64_t n = c->n;
+    c->n_bedge = 0;
+    if (n > 0) {
+        int64_t cap = c->cap_bdry;
+        LV_TRY(lv_ensure(c, (void **)&c->d_bdry_ptr, &cap, 2 * (c->cap_n > n ? c->cap_n : n) + 8, sizeof(int)));
+        c->cap_bdry = cap;
+        int *cnt = c->d_bdry_ptr + (cap / 2);
+        k_bdry_count<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, c->d_col, cnt);
+        c->launches++;
+        LV_TRY(lv_exclusive_scan_i32(c, cnt, c->d_bdry_ptr, n));
+        int total = 0;
+        LV_CUDA(c, cudaMemcpyAsync(&total, c->d_bdry_ptr + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->n_bedge = total;
+    }
+    c->bdry_valid = true;
+    return LV_OK;
+}
+
+extern "C" int32_t lv_boundary_edges(LvHandle c, int64_t *count, double *midpoint, int64_t *label, int64_t *polygon, int64_t cap) {
+    if (!c || !count) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(lv_bdry_index(c));
+    *count = c->n_bedge;
+    if (!midpoint && !label && !polygon) return LV_OK;
+    if (cap < c->n_bedge) return lv_set_error(c, LV_ECAPACITY, "boundary-edge buffer too small: %lld > %lld", (long long)c->n_bedge, (long long)cap);
+    const int64_t m = c->n_bedge;
+    if (m == 0) return LV_OK;
+    void *stage = nullptr;
+    LV_TRY(lv_alloc(c, &stage, (size_t)m * 32));
+    double2 *mid = (double2 *)stage;
+    long long *lab = (long long *)((char *)stage + (size_t)m * 16), *pol = lab + m;
+    k_bdry_list<<<(int)((c->n + 255) / 256), 256, 0, c->stream>>>(c->n, c->d_prim_of_label, c->d_rowptr, c->d_deg, c->d_col, c->d_v1, c->d_v2,
+                                                                c->d_bdry_ptr, mid, lab, pol);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && midpoint) e = cudaMemcpyAsync(midpoint, mid, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && label) e = cudaMemcpyAsync(label, lab, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && polygon) e = cudaMemcpyAsync(polygon, pol, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream);
+    lv_free(c, stage, (size_t)m * 32);
+    if (e != cudaSuccess) return lv_set_error(c, LV_ECUDA, "boundary-edge download failed: %s", cudaGetErrorString(e));
+    return LV_OK;
+}
+
+// boundary_velocity per boundary edge (order of lv_boundary_edges), used by every right-hand side until the next remesh;
+// NULL returns to the four per-wall constants
+extern "C" int32_t lv_set_boundary_velocity(LvHandle c, const double *vbc_edge, int64_t n_edge) {
+    if (!c) return LV_EINVAL;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    c->bvel_valid = false;
+    if (!vbc_edge) { c->vbc_edge_on = false; return LV_OK; }
+    LV_TRY(lv_bdry_index(c));
+    if (n_edge != c->n_bedge) return lv_set_error(c, LV_EINVAL, "boundary velocity for %lld edges, the mesh has %lld boundary edges", (long long)n_edge, (long long)c->n_bedge);
+    if (n_edge > c->cap_bedge || !c->d_vbc_edge) {
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_vbc_edge) cudaFree(c->d_vbc_edge);
+        if (c->d_bf_on) cudaFree(c->d_bf_on);
+        c->cap_bedge = n_edge + n_edge / 8 + 64;
+        LV_CUDA(c, cudaMalloc((void **)&c->d_vbc_edge, sizeof(double2) * (size_t)c->cap_bedge));
+        LV_CUDA(c, cudaMalloc((void **)&c->d_bf_on, (size_t)c->cap_bedge));
+    }
+    if (n_edge > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_vbc_edge, vbc_edge, sizeof(double2) * (size_t)n_edge, cudaMemcpyHostToDevice, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->vbc_edge_on = true;
     return LV_OK;
 }
 

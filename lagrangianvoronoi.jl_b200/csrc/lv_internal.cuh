@@ -105,6 +105,15 @@ struct LvContext {
     double *d_bvel = nullptr;                 // [nslot] P-independent part of the right-hand side
     bool bvel_valid = false;
     double asm_dt = 0.0;
+    // per-boundary-edge data (pressure.jl:182 boundary_velocity(midpoint(e), e.label) evaluated by the host per edge):
+    // boundary edges are numbered polygon by polygon in label order, inside a polygon in edge order
+    int *d_bdry_ptr = nullptr;   // [n+1] first boundary-edge number of every label
+    int64_t cap_bdry = 0, n_bedge = 0;
+    bool bdry_valid = false;
+    double2 *d_vbc_edge = nullptr; // [n_bedge] wall velocity per boundary edge, or unused
+    unsigned char *d_bf_on = nullptr; // [n_bedge] bdary_friction! charfun(m) per boundary edge
+    int64_t cap_bedge = 0;
+    bool vbc_edge_on = false;
     double last_vbc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t cap_w = 0;
     double *d_b = nullptr;
@@ -253,6 +262,7 @@ struct LvHaloPack { // what a producer kernel needs to pack its freshly written 
 };
 int lv_strip_pack_args(LvContext *c, LvHaloPack *out); // advances the exchange sequence
 int lv_remesh_common(LvContext *c, int64_t n);
+int lv_bdry_index(LvContext *c); // numbers the boundary edges of the current mesh (d_bdry_ptr, n_bedge)
 
 // ---- device helpers shared by kernels ---------------------------------------------------------
 #define LV_WAIT_TIMEOUT_CYCLES 40000000000ll // ~20 s: only a dead peer gets there

@@ -413,10 +413,12 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
                                                         const double *__restrict__ mass, const double *__restrict__ rho,
                                                         const double *__restrict__ c2, const double *__restrict__ P,
                                                         const double2 *__restrict__ v, double *__restrict__ b, double *__restrict__ bvel,
-                                                        double2 *__restrict__ GP) {
+                                                        double2 *__restrict__ GP, const unsigned *__restrict__ ent_label,
+                                                        const int *__restrict__ bptr, const double2 *__restrict__ vbc_edge) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
     if (!own[i]) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
+    int be = vbc_edge ? bptr[ent_label[i] & ~LV_IMAGE_BIT] : 0; // number of this polygon's first boundary edge
     const double2 x = ent_xy[i];
     const double Pi = P[i];
     const double2 vi = v[i];
@@ -446,7 +448,8 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
         const double2 a = v1[k], c = v2[k];
         const double sx = a.y - c.y, sy = c.x - a.x; // dS  :181
         const int wl = -j - 1;
-        const double bx = wl < 4 ? vbc.w[2 * wl] : 0.0, by = wl < 4 ? vbc.w[2 * wl + 1] : 0.0;
+        double bx = wl < 4 ? vbc.w[2 * wl] : 0.0, by = wl < 4 ? vbc.w[2 * wl + 1] : 0.0;
+        if (vbc_edge) { const double2 ve = vbc_edge[be++]; bx = ve.x; by = ve.y; } // boundary_velocity(midpoint(e), e.label)  :182
         const double t = (sx * (bx - vi.x) + sy * (by - vi.y)) / dt; // :183
         bi -= t;
         bv -= t;
@@ -628,7 +631,7 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool
     if (first) {
         k_rhs_first<<<nb, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, vbc, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg, c->d_col, c->d_v1,
                                                     c->d_v2, c->d_lrr, c->d_mx, c->d_area, c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_b,
-                                                    c->d_bvel, c->d_GP);
+                                                    c->d_bvel, c->d_GP, c->d_ent_label, c->d_bdry_ptr, c->vbc_edge_on ? c->d_vbc_edge : nullptr);
         c->launches++;
         for (int k = 0; k < 8; k++) c->last_vbc[k] = vbc.w[k];
         c->bvel_valid = true;
@@ -1288,9 +1291,11 @@ int32_t lv_find_pressure_dev(LvHandle c, double dt, int32_t niter, double rtol, 
 
 int32_t lv_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
                          const double *mass, const double *rho, const double *c2, const double *P_in, const double *v,
-                         const double *vbc_wall, double *P_out, int32_t *iters_out, double *relres_out) {
+                         const double *vbc_wall, const double *vbc_edge, int64_t n_vbc_edge, double *P_out, int32_t *iters_out,
+                         double *relres_out) {
     if (!c || !mass || !rho || !c2 || !P_in || !v || !P_out) return lv_set_error(c, LV_EINVAL, "null argument");
     LV_CUDA(c, cudaSetDevice(c->device));
+    LV_TRY(lv_set_boundary_velocity(c, vbc_edge, n_vbc_edge)); // NULL: the four per-wall constants
     LV_TRY(upload_fields(c, mass, rho, c2, P_in, v, false));
     LV_TRY(lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out));
     return download_slots(c, c->d_P, P_out, 1);

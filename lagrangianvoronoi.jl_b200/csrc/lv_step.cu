@@ -94,8 +94,11 @@ __global__ void __launch_bounds__(ST_BLOCK) k_move(StepView S, double dt, double
 // ---- bdary_friction!  diffusion.jl:64-80 ---------------------------------------------------------------------
 // vDirichlet is a closure in the reference; the ABI takes the per-wall constants the examples use (cavity.jl:41-44),
 // indexed by -label-1 = UP, RIGHT, DOWN, LEFT.  Only the polygon's own fields are touched.
-struct WallVel { double v[8]; };
-__global__ void __launch_bounds__(ST_BLOCK) k_bdary_friction(StepView S, double dt, WallVel w) {
+// Per-edge form (lv_step_bdary_friction_ex): v_edge[e] = vDirichlet(m) and on_edge[e] = charfun(m) evaluated by the host at
+// the midpoint of boundary edge number e (numbering of lv_boundary_edges); wall_on switches whole walls off.
+struct WallVel { double v[8]; unsigned char on[4]; };
+__global__ void __launch_bounds__(ST_BLOCK) k_bdary_friction(StepView S, double dt, WallVel w, const int *__restrict__ bptr,
+                                                             const double2 *__restrict__ v_edge, const unsigned char *__restrict__ on_edge) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.n) return;
     const int s = S.prim[i];
@@ -105,9 +108,14 @@ __global__ void __launch_bounds__(ST_BLOCK) k_bdary_friction(StepView S, double 
     const double mu = S.mu[i], mass = S.mass[i];
     double e = S.e[i], tmp = 1.0;
     const int r0 = S.rowptr[s], d = S.rdeg[s];
+    int be = bptr ? bptr[i] : 0;
     for (int k = r0; k < r0 + d; k++) {
         const int lab = S.col[k];
         if (lab >= 0) continue; // boundaries(p): wall codes are negative
+        const int e_no = be++;
+        const int wk0 = (lab >= -4) ? -lab - 1 : -1;
+        if (wk0 >= 0 && !w.on[wk0]) continue;            // if !charfun(m) continue end  diffusion.jl:69
+        if (on_edge && !on_edge[e_no]) continue;
         const double2 a = S.v1[k], b = S.v2[k];
         const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y);
         double nx = a.y - b.y, ny = b.x - a.x; // normal_vector  polygon.jl:153-156
@@ -117,7 +125,8 @@ __global__ void __launch_bounds__(ST_BLOCK) k_bdary_friction(StepView S, double 
         const double lrr = sqrt(ex * ex + ey * ey) / fabs((mx - x.x) * nx + (my - x.y) * ny);
         const double c = mu * lrr;
         const int wk = (lab >= -4) ? -lab - 1 : -1;
-        const double vdx = wk >= 0 ? w.v[2 * wk] : 0.0, vdy = wk >= 0 ? w.v[2 * wk + 1] : 0.0;
+        double vdx = wk >= 0 ? w.v[2 * wk] : 0.0, vdy = wk >= 0 ? w.v[2 * wk + 1] : 0.0;
+        if (v_edge) { vdx = v_edge[e_no].x; vdy = v_edge[e_no].y; }
         const double fx = (c * vdx) / mass, fy = (c * vdy) / mass;
         tmp += ((dt * mu) * lrr) / mass;
         e += dt * (fx * v.x + fy * v.y);
@@ -573,16 +582,43 @@ int32_t lv_step_viscous_step(LvHandle c, double dt, int32_t artificial_viscosity
     return LV_OK;
 }
 
-int32_t lv_step_bdary_friction(LvHandle c, double dt, const double *vwall) { // bdary_friction!  diffusion.jl:64-80
+int32_t lv_step_bdary_friction_ex(LvHandle c, double dt, const double *vwall, const uint8_t *wall_on, const double *v_edge,
+                                  const uint8_t *on_edge, int64_t n_edge) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     WallVel w;
     for (int k = 0; k < 8; k++) w.v[k] = vwall ? vwall[k] : 0.0;
-    if (S.n > 0) { k_bdary_friction<<<GRID(S.n)>>>(S, dt, w); c->launches++; }
+    for (int k = 0; k < 4; k++) w.on[k] = wall_on ? (wall_on[k] != 0) : 1;
+    const bool per_edge = v_edge || on_edge;
+    if (per_edge) {
+        LV_TRY(lv_bdry_index(c));
+        if (n_edge != c->n_bedge) return lv_set_error(c, LV_EINVAL, "wall data for %lld edges, the mesh has %lld boundary edges", (long long)n_edge, (long long)c->n_bedge);
+        if (n_edge > c->cap_bedge || !c->d_vbc_edge) {
+            LV_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (c->d_vbc_edge) cudaFree(c->d_vbc_edge);
+            if (c->d_bf_on) cudaFree(c->d_bf_on);
+            c->cap_bedge = n_edge + n_edge / 8 + 64;
+            LV_CUDA(c, cudaMalloc((void **)&c->d_vbc_edge, sizeof(double2) * (size_t)c->cap_bedge));
+            LV_CUDA(c, cudaMalloc((void **)&c->d_bf_on, (size_t)c->cap_bedge));
+            c->vbc_edge_on = false;
+            c->bvel_valid = false;
+        }
+        // the per-edge velocity buffer is shared with lv_set_boundary_velocity: a later right-hand side must be given its own
+        if (v_edge && n_edge > 0) { LV_CUDA(c, cudaMemcpyAsync(c->d_vbc_edge, v_edge, sizeof(double2) * (size_t)n_edge, cudaMemcpyHostToDevice, c->stream)); c->vbc_edge_on = false; c->bvel_valid = false; }
+        if (on_edge && n_edge > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_bf_on, on_edge, (size_t)n_edge, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (S.n > 0) {
+        k_bdary_friction<<<GRID(S.n)>>>(S, dt, w, per_edge ? c->d_bdry_ptr : nullptr, v_edge ? c->d_vbc_edge : nullptr, on_edge ? c->d_bf_on : nullptr);
+        c->launches++;
+    }
     LV_CUDA(c, cudaGetLastError());
+    if (per_edge) LV_CUDA(c, cudaStreamSynchronize(c->stream)); // the host arrays may be reused
     return LV_OK;
+}
+int32_t lv_step_bdary_friction(LvHandle c, double dt, const double *vwall) { // per-wall constants, charfun = everywhere
+    return lv_step_bdary_friction_ex(c, dt, vwall, nullptr, nullptr, nullptr, 0);
 }
 
 int32_t lv_step_find_dv(LvHandle c, double dt, double alpha) { // find_dv!(grid, dt, alpha)  relaxation.jl:10-25

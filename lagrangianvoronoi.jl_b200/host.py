@@ -303,11 +303,18 @@ class PressureSolver:
         m = int(rowptr[-1])
         return rowptr, col[:m], w[:m], diag
 
-    def rhs(self, dt: float, gp_step: bool = False, vbc_wall=None):
+    def set_boundary_velocity(self, vbc_edge=None):
+        """Per-boundary-edge wall velocities (order of ``boundary_edges``) for the following right-hand sides; None clears."""
+        g = self.grid
+        ve = None if vbc_edge is None else np.ascontiguousarray(vbc_edge, np.float64).reshape(-1, 2)
+        check(g._L.lv_set_boundary_velocity(g._h, ptr(ve), 0 if ve is None else int(ve.shape[0])), g._h)
+
+    def rhs(self, dt: float, gp_step: bool = False, vbc_wall=None, vbc_edge=None):
         g = self.grid
         n = g.n if g.n else getattr(g, "_dev_n", 0)
         b, GP = np.zeros(n), np.zeros((n, 2))
         vw = None if vbc_wall is None else np.ascontiguousarray(vbc_wall, np.float64).reshape(4, 2)
+        self.set_boundary_velocity(vbc_edge)
         check(g._L.lv_pressure_rhs(g._h, float(dt), int(gp_step), ptr(vw), ptr(b), ptr(GP)), g._h)
         return b, GP
 
@@ -340,22 +347,46 @@ class PressureSolver:
         return out
 
 
+def boundary_edges(grid: VoronoiGrid):
+    """(midpoint[nb, 2], label[nb], polygon[nb]) of every boundary edge -- boundaries(p) (iterators.jl:50-57) over the whole
+    mesh, polygon by polygon in label order, edges in p.edges order.  ``polygon`` is 1-based like the reference's indices."""
+    L = grid._L
+    cnt = C.c_int64()
+    check(L.lv_boundary_edges(grid._h, C.byref(cnt), None, None, None, 0), grid._h)
+    nb = cnt.value
+    mid, lab, pol = np.zeros((nb, 2)), np.zeros(nb, np.int64), np.zeros(nb, np.int64)
+    if nb:
+        check(L.lv_boundary_edges(grid._h, C.byref(cnt), ptr(mid), ptr(lab), ptr(pol), nb), grid._h)
+    return mid, lab, pol
+
+
 def _wall_velocities(grid: VoronoiGrid, boundary_velocity):
-    """The reference passes a closure boundary_velocity(midpoint, label) (pressure.jl:182).  No
-    callback crosses the C ABI: the closure is evaluated here once per wall code at the wall's
-    mid point, which is exact for the per-wall constants the examples use
-    (examples/piston.jl:122-127); an explicit (4,2) array is also accepted."""
+    """The reference passes a closure boundary_velocity(midpoint(e), e.label) (pressure.jl:182).  No callback crosses the
+    C ABI: the closure is evaluated HERE at the midpoint of every boundary edge.  Returns (vbc_wall, vbc_edge): when the
+    values are constant along every wall (what all the reference's examples do, e.g. examples/piston.jl:122-127) the four
+    per-wall constants and None -- the fast path; otherwise None and the per-edge array.  An explicit (4, 2) array of wall
+    constants or an (nb, 2) array of per-edge values is accepted as well."""
     if boundary_velocity is None:
-        return None
-    if callable(boundary_velocity):
-        (x0, y0), (x1, y1) = grid.boundary_rect.xmin, grid.boundary_rect.xmax
-        mids = {BDARY_UP: (0.5 * (x0 + x1), y1), BDARY_RIGHT: (x1, 0.5 * (y0 + y1)),
-                BDARY_DOWN: (0.5 * (x0 + x1), y0), BDARY_LEFT: (x0, 0.5 * (y0 + y1))}
-        out = np.zeros((4, 2))
-        for code, m in mids.items():
-            out[-code - 1] = np.asarray(boundary_velocity(np.asarray(m), code), np.float64)
-        return out
-    return np.ascontiguousarray(boundary_velocity, np.float64).reshape(4, 2)
+        return None, None
+    if not callable(boundary_velocity):
+        a = np.ascontiguousarray(boundary_velocity, np.float64)
+        if a.shape == (4, 2) or a.size == 8:
+            return a.reshape(4, 2), None
+        return None, a.reshape(-1, 2)
+    mid, lab, _ = boundary_edges(grid)
+    if len(lab) == 0:
+        return None, None
+    vals = np.array([np.asarray(boundary_velocity(m, int(l)), np.float64).reshape(2) for m, l in zip(mid, lab)])
+    wall = np.zeros((4, 2))
+    constant = True
+    for code in (BDARY_UP, BDARY_RIGHT, BDARY_DOWN, BDARY_LEFT):
+        sel = lab == code
+        if sel.any():
+            wall[-code - 1] = vals[sel][0]
+            constant &= bool((vals[sel] == vals[sel][0]).all())
+    if constant and np.isin(lab, (-1, -2, -3, -4)).all():
+        return wall, None
+    return None, np.ascontiguousarray(vals)
 
 
 def find_pressure(solver: PressureSolver, dt: float, niter: int = 10, boundary_velocity=None) -> None:
@@ -367,11 +398,12 @@ def find_pressure(solver: PressureSolver, dt: float, niter: int = 10, boundary_v
     n = g.n
     iters = np.zeros(niter, np.int32)
     relres = np.zeros(niter) if solver.verbose else None
-    vw = _wall_velocities(g, boundary_velocity)
+    vw, ve = _wall_velocities(g, boundary_velocity)
     kind = LV_SOLVER_MINRES if solver.solver == "minres" else LV_SOLVER_CG
     P_out = g.P
     check(g._L.lv_find_pressure(g._h, float(dt), int(niter), solver.rtol, solver.atol, int(solver.itmax), kind,
-                                ptr(g.mass), ptr(g.rho), ptr(g.c2), ptr(g.P), ptr(g.v), ptr(vw), ptr(P_out),
+                                ptr(g.mass), ptr(g.rho), ptr(g.c2), ptr(g.P), ptr(g.v), ptr(vw), ptr(ve),
+                                0 if ve is None else int(ve.shape[0]), ptr(P_out),
                                 iters.ctypes.data_as(C.POINTER(C.c_int32)),
                                 None if relres is None else relres.ctypes.data_as(C.POINTER(C.c_double))), g._h)
     solver.iters, solver.relres = iters, relres

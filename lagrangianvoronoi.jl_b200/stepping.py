@@ -84,7 +84,8 @@ def find_pressure_resident(solver: PressureSolver, dt: float, niter: int = 10, b
     g = solver.grid
     iters = np.zeros(niter, np.int32)
     relres = np.zeros(niter) if solver.verbose else None
-    vw = _wall_velocities(g, boundary_velocity)
+    vw, ve = _wall_velocities(g, boundary_velocity)
+    check(g._L.lv_set_boundary_velocity(g._h, ptr(ve), 0 if ve is None else int(ve.shape[0])), g._h)
     kind = LV_SOLVER_MINRES if solver.solver == "minres" else LV_SOLVER_CG
     check(g._L.lv_step_find_pressure(g._h, float(dt), int(niter), solver.rtol, solver.atol, int(solver.itmax), kind, ptr(vw),
                                      iters.ctypes.data_as(C.POINTER(C.c_int32)),
@@ -108,13 +109,31 @@ def viscous_step(grid: VoronoiGrid, dt: float, artificial_viscosity: bool = True
     check(grid._L.lv_step_viscous_step(grid._h, float(dt), int(artificial_viscosity)), grid._h)
 
 
-def bdary_friction(grid: VoronoiGrid, dt: float, vwall=None) -> None:
-    """bdary_friction!(grid, vDirichlet, dt)  diffusion.jl:64-80.  ``vwall[4][2]``: the Dirichlet velocity on the walls
-    UP, RIGHT, DOWN, LEFT (the reference's closure evaluated per wall, e.g. the lid of examples/cavity.jl:41-44)."""
-    vw = np.ascontiguousarray(np.zeros((4, 2)) if vwall is None else vwall, dtype=np.float64)
-    if vw.shape != (4, 2):
-        raise ValueError("vwall must have shape (4, 2)")
-    check(grid._L.lv_step_bdary_friction(grid._h, float(dt), vw.ctypes.data), grid._h)
+def bdary_friction(grid: VoronoiGrid, dt: float, vwall=None, charfun=None) -> None:
+    """bdary_friction!(grid, vDirichlet, dt; charfun)  diffusion.jl:64-80.
+
+    ``vwall``: the reference's closure ``vDirichlet(m)`` (evaluated here at the midpoint of every boundary edge), or the four
+    per-wall constants ``vwall[4][2]`` for UP, RIGHT, DOWN, LEFT (what examples/cavity.jl:41-44 amounts to).  ``charfun``: the
+    reference's ``charfun(m)`` closure (e.g. top_and_bottom of examples/bubble.jl), or four per-wall flags; None = everywhere."""
+    from .host import boundary_edges
+    per_edge_v = callable(vwall)
+    per_edge_c = callable(charfun)
+    v_edge = on_edge = wall_on = None
+    vw = np.zeros((4, 2))
+    if per_edge_v or per_edge_c:
+        mid, lab, _ = boundary_edges(grid)
+        if per_edge_v:
+            v_edge = np.ascontiguousarray([np.asarray(vwall(m), np.float64).reshape(2) for m in mid]).reshape(-1, 2)
+        if per_edge_c:
+            on_edge = np.ascontiguousarray([1 if charfun(m) else 0 for m in mid], dtype=np.uint8)
+    if vwall is not None and not per_edge_v:
+        vw = np.ascontiguousarray(vwall, dtype=np.float64)
+        if vw.shape != (4, 2):
+            raise ValueError("vwall must have shape (4, 2)")
+    if charfun is not None and not per_edge_c:
+        wall_on = np.ascontiguousarray(charfun, dtype=np.uint8).reshape(4)
+    n_edge = 0 if (v_edge is None and on_edge is None) else int(len(v_edge) if v_edge is not None else len(on_edge))
+    check(grid._L.lv_step_bdary_friction_ex(grid._h, float(dt), ptr(vw), ptr(wall_on), ptr(v_edge), ptr(on_edge), n_edge), grid._h)
 
 
 def find_dv(grid: VoronoiGrid, dt: float, alpha: float = 1.0) -> None:

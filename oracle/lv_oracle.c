@@ -126,6 +126,9 @@ struct lvo_grid {
     int64_t A_n;
     double *b, *Psol;
     vec2 *GP;
+    /* per-boundary-edge wall velocities: boundary_velocity(midpoint(e), e.label) evaluated by the caller (pressure.jl:182) */
+    double *vbc_edge;
+    int64_t n_vbc_edge;
 };
 
 static int g_threads = 0;
@@ -223,6 +226,7 @@ static void free_pressure(lvo_grid *g) {
 }
 
 void lvo_grid_destroy(lvo_grid *g) {
+    if (g) free(g->vbc_edge);
     if (!g) return;
     free_pressure(g);
     free_polygons(g);
@@ -639,14 +643,55 @@ void lvo_pressure_matvec(const lvo_grid *g, const double *x, double *y) { /* pre
 
 static const double ZERO_VBC[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* pressure.jl:205-207 */
 
+/* boundaries(p) (iterators.jl:50-57) over the whole grid, polygon by polygon, edges in storage order: first[i] = number of
+ * the first boundary edge of polygon i (first has n+1 entries); returns the total */
+static int64_t bdry_first(const lvo_grid *g, int64_t *first) {
+    int64_t tot = 0;
+    for (int64_t i = 0; i < g->n; i++) {
+        first[i] = tot;
+        const poly_t *p = g->polygons[i];
+        for (int64_t k = 0; k < p->edges.last; k++) tot += (p->edges.data[k].label <= 0);
+    }
+    first[g->n] = tot;
+    return tot;
+}
+int64_t lvo_boundary_edges(const lvo_grid *g, double *mid, int64_t *label, int64_t *polygon) {
+    int64_t o = 0;
+    for (int64_t i = 0; i < g->n; i++) {
+        const poly_t *p = g->polygons[i];
+        for (int64_t k = 0; k < p->edges.last; k++) {
+            edge_t e = p->edges.data[k];
+            if (!(e.label <= 0)) continue;
+            if (mid) { vec2 m = midpoint_e(e); mid[2 * o] = m.x; mid[2 * o + 1] = m.y; }
+            if (label) label[o] = e.label;
+            if (polygon) polygon[o] = i + 1;
+            o++;
+        }
+    }
+    return o;
+}
+void lvo_set_vbc_edge(lvo_grid *g, const double *v, int64_t n) { /* NULL: back to the per-wall constants */
+    free(g->vbc_edge);
+    g->vbc_edge = NULL;
+    g->n_vbc_edge = 0;
+    if (v && n > 0) {
+        g->vbc_edge = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+        memcpy(g->vbc_edge, v, sizeof(double) * 2 * (size_t)n);
+        g->n_vbc_edge = n;
+    }
+}
+
 static void rhs_refresh(lvo_grid *g, double dt, int gp_step, const double *vbc_wall) { /* pressure.jl:162-203 */
     double *b = g->b, *P = g->Psol;
     vec2 *GP = g->GP;
     if (!vbc_wall) vbc_wall = ZERO_VBC;
+    int64_t *bfirst = NULL;
+    if (g->vbc_edge) { bfirst = (int64_t *)malloc(sizeof(int64_t) * (size_t)(g->n + 1)); bdry_first(g, bfirst); }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < g->n; i++) {
         const poly_t *p = g->polygons[i];
         double A = poly_area(p);
+        int64_t be = bfirst ? bfirst[i] : 0;
         double bi = (A * p->P) / ((p->rho * p->c2) * (dt * dt));
         P[i] = p->P;
         vec2 gp = V(0.0, 0.0);
@@ -664,11 +709,13 @@ static void rhs_refresh(lvo_grid *g, double dt, int gp_step, const double *vbc_w
             vec2 dS = V(e.v1.y - e.v2.y, e.v2.x - e.v1.x);
             vec2 vbc = V(0.0, 0.0);
             if (e.label < 0 && e.label >= -4) vbc = V(vbc_wall[2 * (-e.label - 1)], vbc_wall[2 * (-e.label - 1) + 1]);
+            if (bfirst) { vbc = V(g->vbc_edge[2 * be], g->vbc_edge[2 * be + 1]); be++; } /* boundary_velocity(midpoint(e), e.label) */
             bi -= vdot(dS, vsub(vbc, p->v)) / dt;
         }
         GP[i] = V(gp.x / p->mass, gp.y / p->mass);
         b[i] = bi;
     }
+    free(bfirst);
     if (gp_step) {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < g->n; i++) {
@@ -1069,19 +1116,32 @@ void lvo_viscous_step(lvo_grid *g, double dt, int artificial_viscosity) { /* dif
 /* diffusion.jl:55-80 bdary_friction!: viscous drag of the walls (Dirichlet condition for a tangential wall velocity).
  * vDirichlet is a closure in the reference; here it is the per-wall constant vwall[-label-1] (what examples/cavity.jl:41-44
  * evaluates to), charfun = everywhere. */
-void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall) {
+void lvo_bdary_friction_ex(lvo_grid *g, double dt, const double *vwall, const unsigned char *wall_on, const double *v_edge,
+                           const unsigned char *on_edge);
+void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall) { lvo_bdary_friction_ex(g, dt, vwall, NULL, NULL, NULL); }
+/* general form: v_edge[2e], on_edge[e] = vDirichlet(m), charfun(m) evaluated by the caller at the midpoint of boundary edge
+ * number e (numbering of lvo_boundary_edges); wall_on[4] switches whole walls off */
+void lvo_bdary_friction_ex(lvo_grid *g, double dt, const double *vwall, const unsigned char *wall_on, const double *v_edge,
+                           const unsigned char *on_edge) {
+    int64_t *bfirst = NULL;
+    if (v_edge || on_edge) { bfirst = (int64_t *)malloc(sizeof(int64_t) * (size_t)(g->n + 1)); bdry_first(g, bfirst); }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < g->n; i++) {
         poly_t *p = g->polygons[i];
         double tmp = 1.0;
+        int64_t be = bfirst ? bfirst[i] : 0;
         for (int64_t k = 0; k < p->edges.last; k++) { /* boundaries(p): iterators.jl:50-57 */
             edge_t e = p->edges.data[k];
             if (!(e.label <= 0)) continue;
+            const int64_t e_no = be++;
+            if (wall_on && e.label < 0 && e.label >= -4 && !wall_on[-e.label - 1]) continue; /* if !charfun(m) continue end */
+            if (on_edge && !on_edge[e_no]) continue;
             vec2 m = vscale(0.5, vadd(e.v1, e.v2));
             vec2 nv = normal_vector(e);
             double lrr = len_e(e) / fabs(vdot(vsub(m, p->x), nv));
             vec2 vd = V(0.0, 0.0);
             if (vwall && e.label < 0 && e.label >= -4) vd = V(vwall[2 * (-e.label - 1)], vwall[2 * (-e.label - 1) + 1]);
+            if (v_edge) vd = V(v_edge[2 * e_no], v_edge[2 * e_no + 1]);
             double c = p->mu * lrr;
             vec2 f = V((c * vd.x) / p->mass, (c * vd.y) / p->mass);
             tmp += ((dt * p->mu) * lrr) / p->mass;
@@ -1090,6 +1150,7 @@ void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall) {
         }
         p->v = V(p->v.x / tmp, p->v.y / tmp);
     }
+    free(bfirst);
 }
 
 /* ------------------------------------------------------------------ relaxation.jl:10-73 */

@@ -92,6 +92,11 @@ void lvo_pressure_step(lvo_grid *g, double dt);                   /* pressure.jl
 void lvo_find_D(lvo_grid *g);                                     /* diffusion.jl:8-19 */
 void lvo_viscous_step(lvo_grid *g, double dt, int artificial_viscosity); /* diffusion.jl:39-53 */
 void lvo_bdary_friction(lvo_grid *g, double dt, const double *vwall); /* diffusion.jl:64-80; vwall[4][2] by -label-1 */
+/* the reference's closures evaluated per boundary edge by the caller: boundaries(p) numbered polygon by polygon */
+int64_t lvo_boundary_edges(const lvo_grid *g, double *mid, int64_t *label, int64_t *polygon);
+void lvo_set_vbc_edge(lvo_grid *g, const double *v, int64_t n); /* boundary_velocity per edge for the RHS (pressure.jl:182); NULL clears */
+void lvo_bdary_friction_ex(lvo_grid *g, double dt, const double *vwall, const unsigned char *wall_on, const double *v_edge,
+                           const unsigned char *on_edge); /* vDirichlet(m), charfun(m) per edge (diffusion.jl:64-80) */
 void lvo_find_dv(lvo_grid *g, double dt, double alpha);           /* relaxation.jl:10-25 */
 int lvo_relaxation_step(lvo_grid *g, double dt, int rusanov);     /* relaxation.jl:36-73 */
 

@@ -70,6 +70,10 @@ def lib() -> C.CDLL:
         L.lvo_find_D.argtypes = [vp]
         L.lvo_viscous_step.argtypes = [vp, C.c_double, C.c_int]
         L.lvo_bdary_friction.argtypes = [vp, C.c_double, C.c_void_p]
+        L.lvo_boundary_edges.restype = C.c_int64
+        L.lvo_boundary_edges.argtypes = [vp, dp, ip, ip]
+        L.lvo_set_vbc_edge.argtypes = [vp, dp, C.c_int64]
+        L.lvo_bdary_friction_ex.argtypes = [vp, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvo_find_dv.argtypes = [vp, C.c_double, C.c_double]
         L.lvo_relaxation_step.argtypes = [vp, C.c_double, C.c_int]
         L.lvo_multiphase_projection.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -261,6 +265,29 @@ class OracleGrid:
         """diffusion.jl:64-80 with per-wall constant Dirichlet velocities vwall[4][2] (UP, RIGHT, DOWN, LEFT)."""
         vw = np.ascontiguousarray(np.zeros((4, 2)) if vwall is None else vwall, dtype=np.float64)
         lib().lvo_bdary_friction(self._g, float(dt), vw.ctypes.data)
+
+    def boundary_edges(self):
+        """(midpoint[nb,2], label[nb], polygon[nb] 1-based) of boundaries(p) over the grid, polygon by polygon."""
+        nb = int(lib().lvo_boundary_edges(self._g, None, None, None))
+        mid, lab, pol = np.zeros((nb, 2)), np.zeros(nb, np.int64), np.zeros(nb, np.int64)
+        if nb:
+            lib().lvo_boundary_edges(self._g, _dp(mid), _ip(lab), _ip(pol))
+        return mid, lab, pol
+
+    def set_vbc_edge(self, v=None):
+        """boundary_velocity(midpoint(e), e.label) per boundary edge (pressure.jl:182), or None for the per-wall constants."""
+        if v is None:
+            lib().lvo_set_vbc_edge(self._g, None, 0)
+        else:
+            v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 2)
+            lib().lvo_set_vbc_edge(self._g, _dp(v), v.shape[0])
+
+    def bdary_friction_ex(self, dt, vwall=None, wall_on=None, v_edge=None, on_edge=None):
+        """diffusion.jl:64-80 with vDirichlet(m) / charfun(m) given per boundary edge (or per wall)."""
+        def p(a, dt_):
+            return None if a is None else np.ascontiguousarray(a, dtype=dt_)
+        vw, wo, ve, oe = p(vwall, np.float64), p(wall_on, np.uint8), p(v_edge, np.float64), p(on_edge, np.uint8)
+        lib().lvo_bdary_friction_ex(self._g, float(dt), *(None if a is None else a.ctypes.data for a in (vw, wo, ve, oe)))
 
     def find_dv(self, dt, alpha=1.0):
         lib().lvo_find_dv(self._g, float(dt), float(alpha))

@@ -300,3 +300,42 @@ def test_gresho_vortex_stays_steady_and_converges(oracle):
         assert abs((og.get("mass") * og.get("e")).sum() - E0) < 1e-11 * abs(E0)
         errs.append(G.l2_error(og.get("x"), og.get("v"), og.get("mass")))
     assert errs[0] < 0.09 and errs[1] < 0.06 and errs[1] < 0.8 * errs[0], errs
+
+
+def test_per_edge_wall_data_reduces_to_the_per_wall_constants(oracle):
+    """The per-boundary-edge forms of the right-hand side (pressure.jl:180-184) and of bdary_friction! (diffusion.jl:64-80)
+    are the closures of the reference evaluated edge by edge: with values that are constant along each wall they must
+    reproduce the per-wall paths bit for bit, and the numbering must follow boundaries(p) polygon by polygon."""
+    from .conftest import make_points
+    xy, dr, bmin, bmax = make_points("poisson", 24, 3)
+    og = oracle.OracleGrid(bmin, bmax, dr)
+    og.set_points(xy); assert og.remesh() == 0
+    n = len(xy)
+    rng = np.random.default_rng(0)
+    for k, val in (("rho", 1.0), ("mass", og.area()), ("c2", 50.0), ("v", rng.standard_normal((n, 2))), ("P", rng.standard_normal(n)),
+                   ("mu", 0.01), ("e", 1.0)):
+        og.set(k, val)
+    mid, lab, pol = og.boundary_edges()
+    rowptr, edges = og.mesh()
+    assert len(lab) == int((edges["label"] <= 0).sum()) and (np.diff(pol) >= 0).all()
+    k = 0
+    for i in range(n):                                                    # numbering = polygons in order, edges in storage order
+        for e in edges[rowptr[i]:rowptr[i + 1]]:
+            if e["label"] <= 0:
+                assert pol[k] == i + 1 and lab[k] == e["label"] and np.array_equal(mid[k], 0.5 * (e["v1"] + e["v2"]))
+                k += 1
+    vw = np.array([[0.3, 0.0], [0.0, -0.2], [0.1, 0.1], [0.0, 0.4]])
+    og.assemble(0.01)
+    b0, _, _ = og.rhs(0.01, True, vw)
+    og.set_vbc_edge(vw[-lab - 1])
+    b1, _, _ = og.rhs(0.01, True, None)
+    og.set_vbc_edge(None)
+    assert np.array_equal(b0, b1)
+    v_before = og.get("v").copy()
+    og.bdary_friction(0.01, vw); va = og.get("v").copy(); ea = og.get("e").copy()
+    og.set("v", v_before); og.set("e", 1.0)
+    og.bdary_friction_ex(0.01, v_edge=vw[-lab - 1], on_edge=np.ones(len(lab), np.uint8))
+    assert np.array_equal(va, og.get("v")) and np.array_equal(ea, og.get("e"))
+    og.set("v", v_before)
+    og.bdary_friction_ex(0.01, vwall=vw, wall_on=np.zeros(4, np.uint8))          # every wall switched off: nothing happens
+    assert np.array_equal(og.get("v"), v_before)

@@ -162,3 +162,47 @@ def test_find_pressure_minres_reference_defaults(lv, oracle):
     assert np.abs(s.iters - iters_ref).max() <= 3, (s.iters, iters_ref)
     P_ref = og.get("P")
     assert np.abs(g.P - P_ref).max() <= 1e-6 * np.abs(P_ref).max()
+
+
+def test_position_dependent_boundary_velocity(lv, oracle):
+    """boundary_velocity(midpoint(e), e.label) (pressure.jl:182) that VARIES along the walls: the host mirror evaluates the
+    closure at every boundary-edge midpoint and the per-edge values reach the right-hand side; same numbering, same b,
+    same converged pressure as the restatement.  Per-wall constants keep using the 4-constant fast path."""
+    from lvb200 import host
+    g, og, xy, dr = _setup(lv, oracle, "poisson", 48, False, False, 6, 10.0)
+    dt = 0.1 * dr
+
+    def lid(m, label):                                                     # a lid whose speed varies along the wall + a leaky side
+        if label == host.BDARY_UP:
+            return np.array([np.sin(np.pi * m[0]) ** 2, 0.0])
+        if label == host.BDARY_LEFT:
+            return np.array([0.05 * m[1], 0.0])
+        return np.zeros(2)
+
+    mid, lab, pol = host.boundary_edges(g)
+    mid0, lab0, pol0 = og.boundary_edges()
+    assert np.array_equal(lab, lab0) and np.array_equal(pol, pol0) and mid.tobytes() == mid0.tobytes()
+    assert set(np.unique(lab)) == {-1, -2, -3, -4} and len(lab) > 100
+    vw, ve = host._wall_velocities(g, lid)
+    assert vw is None and ve.shape == (len(lab), 2)
+    og.set_vbc_edge(np.array([lid(m, l) for m, l in zip(mid0, lab0)]))
+    s = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    s.upload_fields(g.mass, g.rho, g.c2, g.P, g.v)
+    s.assemble(dt); og.assemble(dt)
+    for gp_step in (False, True):
+        b, GP = s.rhs(dt, gp_step, None, vbc_edge=ve)
+        b0, _, GP0 = og.rhs(dt, gp_step, None)
+        assert np.allclose(b, b0, rtol=1e-12, atol=1e-12 * np.abs(b0).max())
+    b_const, _ = s.rhs(dt, False, np.zeros((4, 2)))
+    assert np.abs(b - b_const).max() > 1e-3 * np.abs(b0).max()              # the lid really enters b
+    lv.find_pressure(s, dt, 3, boundary_velocity=lid)
+    og.find_pressure(dt, 3, rtol=1e-12, atol=0.0, itmax=20000, solver="cg")
+    Pref = og.get("P")
+    assert np.abs(g.P - Pref).max() <= 1e-8 * np.abs(Pref).max()
+    # closures that are constant along every wall take the fast path and give the same answer as the explicit constants
+    const = lambda m, label: np.array([0.3, 0.0]) if label == host.BDARY_UP else np.zeros(2)   # noqa: E731
+    vw, ve = host._wall_velocities(g, const)
+    assert ve is None and np.array_equal(vw, [[0.3, 0.0], [0, 0], [0, 0], [0, 0]])
+    # a wrong number of per-edge values is refused
+    with pytest.raises(lv.LvError):
+        s.set_boundary_velocity(np.zeros((len(lab) - 1, 2)))

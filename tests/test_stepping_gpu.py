@@ -71,6 +71,32 @@ def test_explicit_sweeps_match_oracle(lv, oracle, kind, n_side, xper, yper):
     assert np.array_equal(rowptr, r0) and edges.tobytes() == e0.tobytes()
 
 
+def test_bdary_friction_closures(lv, oracle):
+    """bdary_friction!(grid, vDirichlet, dt; charfun) (diffusion.jl:64-80) with the reference's closures: a lid velocity that
+    varies along the wall and charfun = top_and_bottom (examples/bubble.jl) -- side walls get NO drag, not zero-velocity drag."""
+    S = lv.stepping
+    g, og, dr = _pair(lv, oracle, "poisson", 40, False, False, 9)
+    dt = 0.3 * dr
+    mu = np.full(g.n, 2.0e-2)
+    og.set("mu", mu); S.state_set(g, "mu", mu)
+    vD = lambda m: np.array([np.sin(np.pi * m[0]) ** 2, 0.1 * m[1]])       # noqa: E731
+    top_and_bottom = lambda m: (m[1] > 1.0 - 1e-9) or (m[1] < 1e-9)          # noqa: E731
+    mid, lab, _ = og.boundary_edges()
+    v0 = og.get("v").copy()
+    S.bdary_friction(g, dt, vD, charfun=top_and_bottom)
+    og.bdary_friction_ex(dt, v_edge=np.array([vD(m) for m in mid]), on_edge=np.array([top_and_bottom(m) for m in mid], dtype=np.uint8))
+    _compare(lv, g, og, ["v", "e"])
+    v1 = og.get("v")
+    x = og.get("x")
+    side_only = ((x[:, 0] < 0.5 * dr) | (x[:, 0] > 1 - 0.5 * dr)) & (x[:, 1] > 3 * dr) & (x[:, 1] < 1 - 3 * dr)
+    assert side_only.any() and np.array_equal(v1[side_only], v0[side_only])   # cells touching only a side wall are untouched
+    assert np.abs(v1 - v0).max() > 0
+    # per-wall flags: the same charfun as four switches (UP, RIGHT, DOWN, LEFT)
+    S.bdary_friction(g, dt, np.array([[1.0, 0.0], [0, 0], [0, 0], [0, 0]]), charfun=[1, 0, 1, 0])
+    og.bdary_friction_ex(dt, vwall=np.array([[1.0, 0.0], [0, 0], [0, 0], [0, 0]]), wall_on=np.array([1, 0, 1, 0], dtype=np.uint8))
+    _compare(lv, g, og, ["v", "e"])
+
+
 def test_walls_stop_escaping_generators(lv, oracle):
     """move! projects the velocity of cells that would leave the box and zeroes it if that fails (move.jl:9-21)."""
     S = lv.stepping
