@@ -85,8 +85,7 @@ int lv_pr_ensure(LvContext *c) {
         c->pr_valid = false;
     }
     if (c->cap_w < c->cap_nnz || !c->d_w) {
-        int64_t c1 = c->cap_w, c2 = c->cap_w, c3 = c->cap_w, c4 = c->cap_w, c5 = c->cap_w;
-        LV_TRY(lv_ensure(c, (void **)&c->d_colk, &c5, c->cap_nnz, sizeof(int)));
+        int64_t c1 = c->cap_w, c2 = c->cap_w, c3 = c->cap_w, c4 = c->cap_w;
         LV_TRY(lv_ensure(c, (void **)&c->d_w, &c1, c->cap_nnz, sizeof(double)));
         LV_TRY(lv_ensure(c, (void **)&c->d_lrr, &c2, c->cap_nnz, sizeof(double)));
         LV_TRY(lv_ensure(c, (void **)&c->d_mx, &c3, c->cap_nnz, sizeof(double2)));
@@ -98,87 +97,38 @@ int lv_pr_ensure(LvContext *c) {
     return LV_OK;
 }
 
-// ---- k-major warp tiles --------------------------------------------------------------------------------------
-// The per-edge arrays of the pressure system (colk, w, lrr, mx, mz) are stored, per tile of 32 consecutive slots (one
-// warp), "k-major": first edge 0 of every row of the tile that has one, then the edges 1, and so on.  A tile occupies the
-// same range of the edge arrays as its rows do in the mesh's row-major CSR -- it starts at rowptr of the tile's first slot,
-// because both clipping kernels place the rows of a warp contiguously in slot order -- so the loads a warp issues for
-// edge k hit consecutive addresses (one or two 128-byte lines instead of up to 32) and no per-row rowptr is read.  Per-row
-// sums keep the edge order, hence every bit of the results.
-__device__ __forceinline__ unsigned km_lanemask_lt() {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
-struct KmIter { int run; };
-__device__ __forceinline__ KmIter km_begin(const int *__restrict__ rowptr, int i) {
-    KmIter it;
-    it.run = rowptr[i & ~31];
-    return it;
-}
-// position of this lane's edge k (meaningful when `has`), then advance to k + 1; all 32 lanes of the warp must call it
-__device__ __forceinline__ int km_next(KmIter &it, bool has) {
-    const unsigned m = __ballot_sync(0xffffffffu, has);
-    const int pos = it.run + __popc(m & km_lanemask_lt());
-    it.run += __popc(m);
-    return pos;
-}
-// the same position computed by one thread alone (download paths): sum_l min(d_l, k) + #{l < lane: d_l > k}
-__device__ __forceinline__ int km_pos_slow(const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg, int nslot, int s, int k) {
-    const int t0 = s & ~31, lane = s & 31;
-    int pos = rowptr[t0];
-    for (int l = 0; l < 32 && t0 + l < nslot; l++) {
-        const int dl = rdeg[t0 + l];
-        pos += (dl < k ? dl : k) + ((l < lane && dl > k) ? 1 : 0);
-    }
-    return pos;
-}
-#define KM_FULL 0xffffffffu
-
 // ---- K3: operator assembly  pressure.jl:104-117 ------------------------------------------------
 // Besides A.diagonal and the weights w = lrr*(0.5/rho_i + 0.5/rho_j) the kernel keeps, per edge, the three
 // geometric factors every later sweep of find_pressure! needs -- lrr = lr_ratio(p.x - y, e) (polygon.jl:228),
 // m - p.x and m - z (pressure.jl:176,178,196,198) -- so that the 10 fixed-point passes neither repeat the
-// FP64 divide/sqrt nor re-gather the neighbour positions.  Values are the reference's expressions.  Reads the mesh
-// row-major, writes the k-major tiles (coalesced stores).
+// FP64 divide/sqrt nor re-gather the neighbour positions.  Values are the reference's expressions.
 __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot, double dt, const unsigned char *__restrict__ own,
                                                        const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                        const int *__restrict__ col, const double2 *__restrict__ v1,
                                                        const double2 *__restrict__ v2, const double *__restrict__ mass,
                                                        const double *__restrict__ rho, const double *__restrict__ c2,
-                                                       double *__restrict__ diag, int *__restrict__ colk, double *__restrict__ w, double *__restrict__ lrr_out,
+                                                       double *__restrict__ diag, double *__restrict__ w, double *__restrict__ lrr_out,
                                                        double2 *__restrict__ mx_out, double2 *__restrict__ mz_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i & ~31) >= nslot) return; // warp-uniform: the lanes of a partial last tile stay for the ballots
-    const bool mine = i < nslot && own[i];
-    double ri = 1.0;
-    double2 x = make_double2(0.0, 0.0);
-    int r0 = 0, d = 0;
-    if (mine) {
-        ri = rho[i];
-        diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
-        x = ent_xy[i];
-        r0 = rowptr[i];
-        d = rdeg[i];
-    } else if (i < nslot) diag[i] = 0.0;
-    KmIter it = km_begin(rowptr, i);
-    for (int k = 0; __any_sync(KM_FULL, k < d); k++) {
-        const bool has = k < d;
-        const int pos = km_next(it, has);
-        if (!has) continue;
-        const int j = col[r0 + k];
-        const double2 a = v1[r0 + k], b = v2[r0 + k];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (!own[i]) { diag[i] = 0.0; return; }
+    const double ri = rho[i];
+    diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
+    const double2 x = ent_xy[i];
+    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
+    for (int k = r0; k < r1; k++) {
+        const int j = col[k];
+        const double2 a = v1[k], b = v2[k];
         const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y); // midpoint(e)  geometry.jl:145-147
-        colk[pos] = j;
-        mx_out[pos] = make_double2(mx - x.x, my - x.y);
-        if (j < 0) { w[pos] = 0.0; lrr_out[pos] = 0.0; mz_out[pos] = make_double2(0.0, 0.0); continue; } // wall edge: not in neighbors(p, grid)
+        mx_out[k] = make_double2(mx - x.x, my - x.y);
+        if (j < 0) { w[k] = 0.0; lrr_out[k] = 0.0; mz_out[k] = make_double2(0.0, 0.0); continue; } // wall edge: not in neighbors(p, grid)
         const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
         const double ex = a.x - b.x, ey = a.y - b.y, dx = x.x - y.x, dy = x.y - y.y;
         const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy)); // lr_ratio  polygon.jl:228-232
-        lrr_out[pos] = lrr;
-        w[pos] = lrr * (0.5 / ri + 0.5 / rho[j]);                           // pressure.jl:113
+        lrr_out[k] = lrr;
+        w[k] = lrr * (0.5 / ri + 0.5 / rho[j]);                             // pressure.jl:113
         const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);        // midpoint(p.x, y)  pressure.jl:196
-        mz_out[pos] = make_double2(mx - zx, my - zy);
+        mz_out[k] = make_double2(mx - zx, my - zy);
     }
 }
 
@@ -190,7 +140,7 @@ int lv_pr_assemble(LvContext *c, double dt) {
     if (ns > 0) {
         k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                              c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
-                                                                             c->d_diag, c->d_colk, c->d_w, c->d_lrr, c->d_mx, c->d_mz);
+                                                                             c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz);
         c->launches++;
         LV_CUDA(c, cudaGetLastError());
     }
@@ -347,14 +297,16 @@ __global__ void __launch_bounds__(256) k_cg_scalars(int mode, int stage, int nbl
 struct FuseArgs { int *ticket; int stage, nblk_max; double rtol, atol; MailArgs mail; };
 
 // ---- K4: matvec  pressure.jl:119-130, with optional fused dot(x, y) partial ----------------------
-// One thread per row, grid-stride by warps over the k-major tiles: the col / w loads of edge k of a warp's 32 rows are
-// consecutive, x[j] gathers hit L1/L2 (slot order is a spatial order).  The per-row sum keeps the reference's order:
-// diagonal first, then the neighbours in edge order.  All loads of the first MV_U edges are issued before the first use
-// (the kernel is latency bound, not bandwidth bound, when the loads of a row are chained).
+// One thread per row, grid-stride.  Rows are in bucket (slot) order and the rows of 32 consecutive
+// slots are contiguous in the edge arrays, so a warp's col / w reads fall into a handful of lines
+// that stay in L1 over the ~6 iterations of the row loop and x[j] gathers hit L1/L2.  The per-row sum
+// keeps the reference's order: diagonal first, then the neighbours in edge order.
+// (A variant that staged each warp tile's col / w through shared memory measured 1.7x slower on
+// B200 -- three dependent memory round trips per tile instead of one -- and was dropped.)
 #define MV_U 8
 template <bool DOT, int MINB, bool FUSE>
 __global__ void __launch_bounds__(PR_BLOCK, MINB) k_matvec(int nslot, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
-                                                     const int *__restrict__ colk, const double *__restrict__ w,
+                                                     const int *__restrict__ col, const double *__restrict__ w,
                                                      const double *__restrict__ diag, const double *__restrict__ x,
                                                      double *__restrict__ y, double *__restrict__ partial,
                                                      double *scal, FuseArgs fz) {
@@ -362,36 +314,30 @@ __global__ void __launch_bounds__(PR_BLOCK, MINB) k_matvec(int nslot, const int 
     const bool idle = DOT && scal[SC_CONV] != 0.0; // converged: queued launches are no-ops (the fused finish still runs
     if (idle && !FUSE) return;                     // so that all ranks keep the same mailbox sequence numbers)
     double acc = 0.0;
-    const int nend = idle ? 0 : nslot;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < nend; i += gridDim.x * blockDim.x) { // warp-uniform bound
-        const bool valid = i < nslot;
-        const double xi = valid ? x[i] : 0.0;
-        const int d = valid ? rdeg[i] : 0;
-        double yi = valid ? diag[i] * xi : 0.0;
-        KmIter it = km_begin(rowptr, i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (idle ? 0 : nslot); i += gridDim.x * blockDim.x) {
+        const double xi = x[i];
+        double yi = diag[i] * xi;
+        const int r0 = rowptr[i], d = rdeg[i];
+        // all loads of the first MV_U edges are issued before the first use (memory-level parallelism:
+        // the kernel is latency bound, not bandwidth bound, when the loads of a row are chained)
         int cj[MV_U];
         double wk[MV_U], xj[MV_U];
 #pragma unroll
         for (int k = 0; k < MV_U; k++) {
-            const bool has = k < d;
-            const int pos = km_next(it, has);
-            cj[k] = has ? colk[pos] : -1;
-            wk[k] = has ? w[pos] : 0.0;
+            cj[k] = k < d ? col[r0 + k] : -1;
+            wk[k] = k < d ? w[r0 + k] : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < MV_U; k++) xj[k] = cj[k] >= 0 ? x[cj[k]] : xi;
 #pragma unroll
         for (int k = 0; k < MV_U; k++)
             if (k < d) yi += wk[k] * (xi - xj[k]);
-        for (int k = MV_U; __any_sync(KM_FULL, k < d); k++) {
-            const bool has = k < d;
-            const int pos = km_next(it, has);
-            if (!has) continue;
-            const int j = colk[pos];
+        for (int k = MV_U; k < d; k++) {
+            const int j = col[r0 + k];
             const double xv = j >= 0 ? x[j] : xi;
-            yi += w[pos] * (xi - xv);
+            yi += w[r0 + k] * (xi - xv);
         }
-        if (valid) y[i] = yi;
+        y[i] = yi;
         if (DOT) acc += xi * yi;
     }
     if (DOT) {
@@ -418,7 +364,7 @@ static inline int pr_grid(const LvContext *c, int64_t n) {
 // LV_MV_MINB=1 selects the uncapped build, LV_MV_GRID=legacy the old grid (A/B switches for the bench).
 static int mv_minb() {
     static int v = 0;
-    if (v == 0) { const char *e = getenv("LV_MV_MINB"); v = (e && e[0] == '1') ? 1 : ((e && e[0] == '5') ? 5 : 6); }
+    if (v == 0) { const char *e = getenv("LV_MV_MINB"); v = (e && e[0] == '1') ? 1 : 6; }
     return v;
 }
 template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
@@ -427,8 +373,7 @@ template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
         const char *e = getenv("LV_MV_GRID");
         int occ = 0;
         cudaError_t st = mv_minb() == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 1, DOT>, PR_BLOCK, 0)
-                         : mv_minb() == 5 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 5, DOT>, PR_BLOCK, 0)
-                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 6, DOT>, PR_BLOCK, 0);
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec<DOT, 6, DOT>, PR_BLOCK, 0);
         if ((e && !strcmp(e, "legacy")) || st != cudaSuccess || occ < 1) occ = 8;
         per_sm = occ;
     }
@@ -439,9 +384,8 @@ template <bool DOT> static int mv_grid(const LvContext *c, int64_t n) {
 template <bool DOT, bool FUSE = false>
 static void mv_launch(LvContext *c, int grid, cudaStream_t st, int ns, const double *x, double *y, double *partial, double *scal,
                       const FuseArgs &fz = FuseArgs()) {
-    if (mv_minb() == 1) k_matvec<DOT, 1, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_colk, c->d_w, c->d_diag, x, y, partial, scal, fz);
-    else if (mv_minb() == 5) k_matvec<DOT, 5, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_colk, c->d_w, c->d_diag, x, y, partial, scal, fz);
-    else k_matvec<DOT, 6, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_colk, c->d_w, c->d_diag, x, y, partial, scal, fz);
+    if (mv_minb() == 1) k_matvec<DOT, 1, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal, fz);
+    else k_matvec<DOT, 6, FUSE><<<grid, PR_BLOCK, 0, st>>>(ns, c->d_rowptr, c->d_deg, c->d_col, c->d_w, c->d_diag, x, y, partial, scal, fz);
     c->launches++;
 }
 
@@ -460,7 +404,7 @@ struct Vbc { double w[8]; };
 
 // First pass of find_pressure! (gp_step = false): b, the initial GP and -- kept for the later passes --
 // bvel, the part of b that does not depend on P (velocity divergence + wall terms, pressure.jl:177,180-184).
-// b itself is accumulated in the reference's order.  Mesh arrays (col, v1, v2) are row-major, lrr / m - p.x k-major.
+// b itself is accumulated in the reference's order.
 __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslot, double dt, Vbc vbc, const unsigned char *__restrict__ own,
                                                         const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                         const int *__restrict__ col, const double2 *__restrict__ v1,
@@ -471,32 +415,24 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
                                                         const double2 *__restrict__ v, double *__restrict__ b, double *__restrict__ bvel,
                                                         double2 *__restrict__ GP, const unsigned *__restrict__ ent_label,
                                                         const int *__restrict__ bptr, const double2 *__restrict__ vbc_edge) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i & ~31) >= nslot) return;
-    const bool mine = i < nslot && own[i];
-    if (i < nslot && !mine) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); }
-    double2 x = make_double2(0.0, 0.0), vi = x;
-    double Pi = 0.0, bi = 0.0, bv = 0.0, gx = 0.0, gy = 0.0;
-    int r0 = 0, d = 0;
-    if (mine) {
-        x = ent_xy[i];
-        Pi = P[i];
-        vi = v[i];
-        bi = (area[i] * Pi) / ((rho[i] * c2[i]) * (dt * dt)); // pressure.jl:171
-        r0 = rowptr[i];
-        d = rdeg[i];
-    }
-    KmIter it = km_begin(rowptr, i);
-    for (int k = 0; __any_sync(KM_FULL, k < d); k++) { // neighbors(p, grid)
-        const bool has = k < d;
-        const int pos = km_next(it, has);
-        if (!has) continue;
-        const int j = col[r0 + k];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (!own[i]) { b[i] = 0.0; bvel[i] = 0.0; GP[i] = make_double2(0.0, 0.0); return; }
+    int be = vbc_edge ? bptr[ent_label[i] & ~LV_IMAGE_BIT] : 0; // number of this polygon's first boundary edge
+    const double2 x = ent_xy[i];
+    const double Pi = P[i];
+    const double2 vi = v[i];
+    double bi = (area[i] * Pi) / ((rho[i] * c2[i]) * (dt * dt)); // pressure.jl:171
+    double bv = 0.0;
+    double gx = 0.0, gy = 0.0;
+    const int r0 = rowptr[i], r1 = r0 + rdeg[i];
+    for (int k = r0; k < r1; k++) { // neighbors(p, grid)
+        const int j = col[k];
         if (j < 0) continue;
         const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
-        const double2 m = mx_in[pos]; // m - p.x
-        const double lrr = lrr_in[pos];
-        const double2 a = v1[r0 + k], c = v2[r0 + k];
+        const double2 m = mx_in[k]; // m - p.x
+        const double lrr = lrr_in[k];
+        const double2 a = v1[k], c = v2[k];
         const double mx = 0.5 * (a.x + c.x), my = 0.5 * (a.y + c.y);
         const double2 vj = v[j];
         const double t = (lrr / dt) * ((vi.x - vj.x) * (mx - y.x) + (vi.y - vj.y) * (my - y.y)); // :177
@@ -506,9 +442,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
         gx -= s * m.x; // :178
         gy -= s * m.y;
     }
-    if (!mine) return;
-    int be = vbc_edge ? bptr[ent_label[i] & ~LV_IMAGE_BIT] : 0; // number of this polygon's first boundary edge
-    for (int k = r0; k < r0 + d; k++) { // boundaries(p)
+    for (int k = r0; k < r1; k++) { // boundaries(p)
         const int j = col[k];
         if (j >= 0) continue;
         const double2 a = v1[k], c = v2[k];
@@ -528,72 +462,105 @@ __global__ void __launch_bounds__(PR_BLOCK) k_rhs_first(LvGridParams g, int nslo
 
 #define RH_U 8 // edges whose loads are issued before first use (same latency argument as k_matvec)
 
-// Later passes, sweep 1: GP_i = -sum lrr (P_i - P_j)(m - p.x) / mass_i   pressure.jl:178,185.  MV: fused with the first
-// matvec of the solve -- both gather P_j over the same row, so GP_i and (A P)_i (pressure.jl:119-130, the A x0 of the
-// warm-started Krylov solve) come out of one CSR walk; (A P)_i is accumulated exactly like k_matvec does.
-template <bool MV>
+// Later passes, sweep 1: GP_i = -sum lrr (P_i - P_j)(m - p.x) / mass_i   pressure.jl:178,185
 __global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp(int nslot, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
-                                                     const unsigned char *__restrict__ rdeg, const int *__restrict__ colk,
+                                                     const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                      const double *__restrict__ lrr_in, const double2 *__restrict__ mx_in,
-                                                     const double *__restrict__ w, const double *__restrict__ diag,
                                                      const double *__restrict__ mass, const double *__restrict__ P,
-                                                     double2 *__restrict__ GP, double *__restrict__ AP) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((i & ~31) >= nslot) return;
-    const bool valid = i < nslot, mine = valid && own[i];
-    const double Pi = valid ? P[i] : 0.0;
-    const int d = mine ? rdeg[i] : 0;
-    KmIter it = km_begin(rowptr, i);
+                                                     double2 *__restrict__ GP) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    if (!own[i]) { GP[i] = make_double2(0.0, 0.0); return; }
+    const double Pi = P[i];
+    const int r0 = rowptr[i], d = rdeg[i];
+    int cj[RH_U];
+    double lr[RH_U], pj[RH_U];
+    double2 mm[RH_U];
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) {
+        cj[k] = k < d ? col[r0 + k] : -1;
+        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+        mm[k] = k < d ? mx_in[r0 + k] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < RH_U; k++) pj[k] = cj[k] >= 0 ? P[cj[k]] : Pi;
+    double gx = 0.0, gy = 0.0;
+#pragma unroll
+    for (int k = 0; k < RH_U; k++)
+        if (k < d && cj[k] >= 0) {
+            const double s = lr[k] * (Pi - pj[k]);
+            gx -= s * mm[k].x;
+            gy -= s * mm[k].y;
+        }
+    for (int k = RH_U; k < d; k++) {
+        const int j = col[r0 + k];
+        if (j < 0) continue;
+        const double s = lrr_in[r0 + k] * (Pi - P[j]);
+        const double2 m = mx_in[r0 + k];
+        gx -= s * m.x;
+        gy -= s * m.y;
+    }
+    const double mi = mass[i];
+    GP[i] = make_double2(gx / mi, gy / mi);
+}
+
+// Later passes, sweep 1 fused with the first matvec of the solve: both gather P_j over the same row, so
+// GP_i (pressure.jl:178,185) and (A P)_i (pressure.jl:119-130, the A x0 of the warm-started Krylov solve) come out of
+// one CSR walk.  (A P)_i is accumulated exactly like k_matvec does (diagonal first, neighbours in edge order).
+__global__ void __launch_bounds__(PR_BLOCK) k_rhs_gp_mv(int nslot, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
+                                                        const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
+                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mx_in,
+                                                        const double *__restrict__ w, const double *__restrict__ diag,
+                                                        const double *__restrict__ mass, const double *__restrict__ P,
+                                                        double2 *__restrict__ GP, double *__restrict__ AP) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    const double Pi = P[i];
+    if (!own[i]) { GP[i] = make_double2(0.0, 0.0); AP[i] = diag[i] * Pi; return; }
+    const int r0 = rowptr[i], d = rdeg[i];
     int cj[RH_U];
     double lr[RH_U], pj[RH_U], wk[RH_U];
     double2 mm[RH_U];
 #pragma unroll
     for (int k = 0; k < RH_U; k++) {
-        const bool has = k < d;
-        const int pos = km_next(it, has);
-        cj[k] = has ? colk[pos] : -1;
-        lr[k] = has ? lrr_in[pos] : 0.0;
-        if (MV) wk[k] = has ? w[pos] : 0.0;
-        mm[k] = has ? mx_in[pos] : make_double2(0.0, 0.0);
+        cj[k] = k < d ? col[r0 + k] : -1;
+        lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+        wk[k] = k < d ? w[r0 + k] : 0.0;
+        mm[k] = k < d ? mx_in[r0 + k] : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int k = 0; k < RH_U; k++) pj[k] = cj[k] >= 0 ? P[cj[k]] : Pi;
-    double gx = 0.0, gy = 0.0, yi = (MV && valid) ? diag[i] * Pi : 0.0;
+    double gx = 0.0, gy = 0.0, yi = diag[i] * Pi;
 #pragma unroll
     for (int k = 0; k < RH_U; k++) {
-        if (MV && k < d) yi += wk[k] * (Pi - pj[k]);
+        if (k < d) yi += wk[k] * (Pi - pj[k]);
         if (k < d && cj[k] >= 0) {
             const double s = lr[k] * (Pi - pj[k]);
             gx -= s * mm[k].x;
             gy -= s * mm[k].y;
         }
     }
-    for (int k = RH_U; __any_sync(KM_FULL, k < d); k++) {
-        const bool has = k < d;
-        const int pos = km_next(it, has);
-        if (!has) continue;
-        const int j = colk[pos];
+    for (int k = RH_U; k < d; k++) {
+        const int j = col[r0 + k];
         const double pv = j >= 0 ? P[j] : Pi;
-        if (MV) yi += w[pos] * (Pi - pv);
+        yi += w[r0 + k] * (Pi - pv);
         if (j < 0) continue;
-        const double s = lrr_in[pos] * (Pi - pv);
-        const double2 m = mx_in[pos];
+        const double s = lrr_in[r0 + k] * (Pi - pv);
+        const double2 m = mx_in[r0 + k];
         gx -= s * m.x;
         gy -= s * m.y;
     }
-    if (!valid) return;
-    if (MV) AP[i] = yi;
-    if (!mine) { GP[i] = make_double2(0.0, 0.0); return; }
     const double mi = mass[i];
     GP[i] = make_double2(gx / mi, gy / mi);
+    AP[i] = yi;
 }
 
 // Later passes, sweep 2: b_i = A_i P_i/(rho c2 dt^2) + bvel_i + sum lrr (GP_i - GP_j).(m - z)   pressure.jl:171,189-202
-// INIT: the kernel is also the CG initialisation (k_cg_init): r = b - A x0 with A x0 from k_rhs_gp<true>, p = r and the block
+// INIT: the kernel is also the CG initialisation (k_cg_init): r = b - A x0 with A x0 from k_rhs_gp_mv, p = r and the block
 // partials of r.r and b.b -- grid-stride with k_cg_init's grid and accumulation order, so the sums are bit-identical to it.
 template <bool INIT>
-__global__ void __launch_bounds__(PR_BLOCK, 3) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
-                                                       const unsigned char *__restrict__ rdeg, const int *__restrict__ colk,
+__global__ void __launch_bounds__(PR_BLOCK, INIT ? 4 : 8) k_rhs_corr(int nslot, double dt, const unsigned char *__restrict__ own, const int *__restrict__ rowptr,
+                                                       const unsigned char *__restrict__ rdeg, const int *__restrict__ col,
                                                        const double *__restrict__ lrr_in, const double2 *__restrict__ mz_in,
                                                        const double *__restrict__ area, const double *__restrict__ rho,
                                                        const double *__restrict__ c2, const double *__restrict__ P,
@@ -602,44 +569,34 @@ __global__ void __launch_bounds__(PR_BLOCK, 3) k_rhs_corr(int nslot, double dt, 
                                                        double *__restrict__ p, double *__restrict__ partial, int nblk_max) {
     __shared__ double sm[32];
     double rr = 0.0, bb = 0.0;
-    const int stride = INIT ? gridDim.x * blockDim.x : (nslot + 32);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31) < nslot; i += stride) {
-        const bool valid = i < nslot, mine = valid && own[i];
+    const int stride = INIT ? gridDim.x * blockDim.x : nslot;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += stride) {
         double bi = 0.0;
-        double2 gi = make_double2(0.0, 0.0);
-        int d = 0;
-        if (mine) {
-            gi = GP[i];
+        if (own[i]) {
+            const double2 gi = GP[i];
             bi = (area[i] * P[i]) / ((rho[i] * c2[i]) * (dt * dt)) + bvel[i];
-            d = rdeg[i];
-        }
-        KmIter it = km_begin(rowptr, i);
-        int cj[RH_U];
-        double lr[RH_U];
-        double2 mm[RH_U], gj[RH_U];
+            const int r0 = rowptr[i], d = rdeg[i];
+            int cj[RH_U];
+            double lr[RH_U];
+            double2 mm[RH_U], gj[RH_U];
 #pragma unroll
-        for (int k = 0; k < RH_U; k++) {
-            const bool has = k < d;
-            const int pos = km_next(it, has);
-            cj[k] = has ? colk[pos] : -1;
-            lr[k] = has ? lrr_in[pos] : 0.0;
-            mm[k] = has ? mz_in[pos] : make_double2(0.0, 0.0);
-        }
+            for (int k = 0; k < RH_U; k++) {
+                cj[k] = k < d ? col[r0 + k] : -1;
+                lr[k] = k < d ? lrr_in[r0 + k] : 0.0;
+                mm[k] = k < d ? mz_in[r0 + k] : make_double2(0.0, 0.0);
+            }
 #pragma unroll
-        for (int k = 0; k < RH_U; k++) gj[k] = cj[k] >= 0 ? GP[cj[k]] : gi;
+            for (int k = 0; k < RH_U; k++) gj[k] = cj[k] >= 0 ? GP[cj[k]] : gi;
 #pragma unroll
-        for (int k = 0; k < RH_U; k++)
-            if (k < d && cj[k] >= 0) bi += lr[k] * ((gi.x - gj[k].x) * mm[k].x + (gi.y - gj[k].y) * mm[k].y); // :198
-        for (int k = RH_U; __any_sync(KM_FULL, k < d); k++) {
-            const bool has = k < d;
-            const int pos = km_next(it, has);
-            if (!has) continue;
-            const int j = colk[pos];
-            if (j < 0) continue;
-            const double2 g2 = GP[j], m = mz_in[pos];
-            bi += lrr_in[pos] * ((gi.x - g2.x) * m.x + (gi.y - g2.y) * m.y);
+            for (int k = 0; k < RH_U; k++)
+                if (k < d && cj[k] >= 0) bi += lr[k] * ((gi.x - gj[k].x) * mm[k].x + (gi.y - gj[k].y) * mm[k].y); // :198
+            for (int k = RH_U; k < d; k++) {
+                const int j = col[r0 + k];
+                if (j < 0) continue;
+                const double2 g2 = GP[j], m = mz_in[r0 + k];
+                bi += lrr_in[r0 + k] * ((gi.x - g2.x) * m.x + (gi.y - g2.y) * m.y);
+            }
         }
-        if (!valid) continue;
         b[i] = bi;
         if (INIT) {
             const double ri = bi - AP[i];
@@ -683,20 +640,20 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool
         // fused with the start of the CG solve (its first matvec and k_cg_init) when the caller is find_pressure!
         const bool fused = fuse_init && !first;
         if (!first) {
-            if (fused) k_rhs_gp<true><<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_colk, c->d_lrr, c->d_mx, c->d_w, c->d_diag,
-                                                                      c->d_mass, c->d_P, c->d_GP, c->d_vec[2]);
-            else k_rhs_gp<false><<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_colk, c->d_lrr, c->d_mx, c->d_w, c->d_diag,
-                                                                 c->d_mass, c->d_P, c->d_GP, nullptr);
+            if (fused) k_rhs_gp_mv<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_w, c->d_diag,
+                                                                   c->d_mass, c->d_P, c->d_GP, c->d_vec[2]);
+            else k_rhs_gp<<<nb, PR_BLOCK, 0, c->stream>>>(ns, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mx, c->d_mass, c->d_P,
+                                                          c->d_GP);
             c->launches++;
         }
         LV_TRY(lv_halo_exchange(c, (double *)c->d_GP, 2));
         if (fused) {
-            k_rhs_corr<true><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_colk, c->d_lrr, c->d_mz, c->d_area,
+            k_rhs_corr<true><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area,
                                                                          c->d_rho, c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, c->d_vec[2],
                                                                          c->d_vec[0], c->d_vec[1], c->d_red + SC_COUNT, 4096);
             if (init_done) *init_done = true;
         } else
-            k_rhs_corr<false><<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_colk, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
+            k_rhs_corr<false><<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
                                                               c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, nullptr, nullptr, nullptr, nullptr, 4096);
         c->launches++;
     }
@@ -1131,7 +1088,6 @@ int32_t lv_pressure_destroy(LvHandle c) {
                       &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
     for (double **p : one) { lv_free(c, *p, sizeof(double) * (size_t)c->pr_cap); *p = nullptr; }
     lv_free(c, c->d_lrr, sizeof(double) * (size_t)c->cap_w); c->d_lrr = nullptr;
-    lv_free(c, c->d_colk, sizeof(int) * (size_t)c->cap_w); c->d_colk = nullptr;
     lv_free(c, c->d_mx, sizeof(double2) * (size_t)c->cap_w); c->d_mx = nullptr;
     lv_free(c, c->d_mz, sizeof(double2) * (size_t)c->cap_w); c->d_mz = nullptr;
     lv_free(c, c->d_v, sizeof(double2) * (size_t)c->pr_cap); c->d_v = nullptr;
@@ -1225,7 +1181,7 @@ int32_t lv_pressure_assemble(LvHandle c, double dt) {
     return lv_pr_assemble(c, dt);
 }
 
-__global__ void __launch_bounds__(256) k_op_copy(int64_t n, int nslot, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
+__global__ void __launch_bounds__(256) k_op_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
                                                  const int *__restrict__ rowptr_l, const int *__restrict__ col, const double *__restrict__ w,
                                                  const double *__restrict__ diag, const unsigned *__restrict__ ent_label,
                                                  long long *__restrict__ col_l, double *__restrict__ w_l, double *__restrict__ diag_l) {
@@ -1235,11 +1191,11 @@ __global__ void __launch_bounds__(256) k_op_copy(int64_t n, int nslot, const int
     if (s < 0) { diag_l[i] = 0.0; return; }
     diag_l[i] = diag[s];
     int o = rowptr_l[i];
-    for (int k = 0; k < rdeg[s]; k++) {
-        const int j = col[rowptr[s] + k];
+    for (int k = rowptr[s]; k < rowptr[s] + rdeg[s]; k++) {
+        const int j = col[k];
         if (j < 0) continue;
         col_l[o] = (long long)(ent_label[j] & ~LV_IMAGE_BIT) + 1;
-        w_l[o] = w[km_pos_slow(rowptr, rdeg, nslot, s, k)]; // the weights live in the k-major tiles
+        w_l[o] = w[k];
         o++;
     }
 }
@@ -1275,7 +1231,7 @@ int32_t lv_pressure_operator(LvHandle c, int64_t *rowptr, int64_t *col, double *
         k_op_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, c->d_col, deg);
         c->launches++;
         if ((st = lv_exclusive_scan_i32(c, deg, rl, n)) != LV_OK) break;
-        k_op_copy<<<nb, 256, 0, c->stream>>>(n, (int)c->nslot, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_w, c->d_diag, c->d_ent_label, col_l, w_l, d_l);
+        k_op_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_w, c->d_diag, c->d_ent_label, col_l, w_l, d_l);
         c->launches++;
         int *h_rl = (int *)malloc(sizeof(int) * (size_t)(n + 1));
         cudaError_t e = cudaMemcpyAsync(h_rl, rl, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
