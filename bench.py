@@ -268,11 +268,11 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
 
         def step_e2e():
             # host buffers in, host buffers out: positions / fields go up, rowptr + edges + areas + centroids + P come back.
-            # The edge view is downloaded lazily (second stream) so that it overlaps the pressure solve; the step ends
-            # only when every byte is in host memory.
+            # Every mesh output (rowptr, areas, centroids, edge records) is downloaded lazily on a second stream so that
+            # it overlaps the next remesh and the pressure solve; the step ends only when every byte is in host memory.
             g.P = p_in.pop() if p_in else g.P
-            lv.remesh(g, lazy=True)
-            lv.remesh(g, lazy=True)
+            lv.remesh(g, lazy="all")
+            lv.remesh(g, lazy="all")
             lv.find_pressure(solver, dt, args.niter)
             lv.wait_edges(g)
             return int(solver.iters.sum())

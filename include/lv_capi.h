@@ -96,6 +96,9 @@ int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap
  * While such a copy is in flight the copy engine is busy, so rowptr / area / centroid (lv_remesh) and P (lv_find_pressure,
  * lv_pressure_download) are written straight into the caller's buffers by the conversion kernels when those buffers are
  * pinned (cudaHostAlloc / cudaHostRegister: mapped under UVA); pageable buffers take the ordinary cudaMemcpy path.
+ * on = 2 ("everything lazy"): rowptr, areas and centroids travel in the background too, ahead of the edge records on the
+ * same copy stream; lv_remesh returns as soon as the device-side conversion is queued and NO output buffer may be read
+ * before lv_mesh_wait.  For callers that launch the next device call (a second remesh, find_pressure!) straight away.
  * Environment switches (diagnostics): LV_DIRECT_STORE=0 disables the direct stores, LV_FLAG_MODE=memcpy reads status
  * words with cudaMemcpy instead of mapped memory. */
 int32_t lv_set_async_edges(LvHandle h, int32_t on);

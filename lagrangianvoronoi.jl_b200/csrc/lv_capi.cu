@@ -432,7 +432,10 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
     // stores them straight into host memory instead: coalesced 256-512 B per warp, concurrent with the DMA.
     long long *r64_out = r64; double *area_out = area_l; double2 *cen_out = cen_l;
     bool direct_r = false, direct_a = false, direct_c = false;
-    if (c->async_edges) {
+    // async_all (lv_set_async_edges(h, 2)): the per-cell arrays travel in the background as well, ahead of the edge records on
+    // the copy stream; nothing on the caller's critical path touches PCIe and lv_mesh_wait orders the host against all of it
+    const bool all_lazy = c->async_edges && c->async_all && edges;
+    if (c->async_edges && !all_lazy) {
         direct_r = rowptr && (r64_out = (long long *)lv_mapped_alias(rowptr)) != nullptr;
         direct_a = area && (area_out = (double *)lv_mapped_alias(area)) != nullptr;
         direct_c = centroid && (cen_out = (double2 *)lv_mapped_alias(centroid)) != nullptr;
@@ -449,15 +452,21 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
                                                 area ? area_out : nullptr, centroid ? cen_out : nullptr);
         c->launches++;
         cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess && rowptr && !direct_r) e = cudaMemcpyAsync(rowptr, r64, sizeof(long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && area && !direct_a) e = cudaMemcpyAsync(area, area_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && centroid && !direct_c) e = cudaMemcpyAsync(centroid, cen_l, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        cudaStream_t cell_stream = c->stream;
+        if (all_lazy) {
+            e = cudaEventRecord(c->ev_conv_done, c->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_conv_done, 0);
+            cell_stream = c->copy_stream;
+        }
+        if (e == cudaSuccess && rowptr && !direct_r) e = cudaMemcpyAsync(rowptr, r64, sizeof(long long) * (size_t)(n + 1), cudaMemcpyDeviceToHost, cell_stream);
+        if (e == cudaSuccess && area && !direct_a) e = cudaMemcpyAsync(area, area_l, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, cell_stream);
+        if (e == cudaSuccess && centroid && !direct_c) e = cudaMemcpyAsync(centroid, cen_l, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, cell_stream);
         if (e == cudaSuccess && edges) {
             if (c->async_edges) {
                 // the 40 B/edge view is the bulk of the device->host traffic: copy it on a second stream so that it
                 // overlaps whatever the caller runs next (lv_mesh_wait orders the host against it)
-                e = cudaEventRecord(c->ev_conv_done, c->stream);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_conv_done, 0);
+                if (!all_lazy) e = cudaEventRecord(c->ev_conv_done, c->stream);
+                if (e == cudaSuccess && !all_lazy) e = cudaStreamWaitEvent(c->copy_stream, c->ev_conv_done, 0);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(edges, e_l, sizeof(LvEdge) * (size_t)nnz, cudaMemcpyDeviceToHost, c->copy_stream);
                 if (e == cudaSuccess) e = cudaEventRecord(c->ev_stage_done[sb], c->copy_stream);
                 c->stage_pending[sb] = (e == cudaSuccess);
@@ -486,6 +495,7 @@ int32_t lv_set_async_edges(LvHandle c, int32_t on) {
     }
     if (!on) LV_TRY(lv_mesh_wait(c));
     c->async_edges = on != 0;
+    c->async_all = on == 2;
     return LV_OK;
 }
 int32_t lv_mesh_wait(LvHandle c) {

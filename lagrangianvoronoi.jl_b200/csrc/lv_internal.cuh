@@ -91,7 +91,7 @@ struct LvContext {
     int64_t cap_io_stage = 0;                  // persistent because cudaFree would wait for the background edge copies
     cudaStream_t copy_stream = nullptr; // background device->host copy of the edge view (lv_set_async_edges)
     cudaEvent_t ev_conv_done = nullptr, ev_stage_done[2] = {nullptr, nullptr};
-    bool async_edges = false, stage_pending[2] = {false, false};
+    bool async_edges = false, async_all = false, stage_pending[2] = {false, false};
     int stage_cur = 0;
     bool flags_mapped = true; // status words via mapped pinned memory (default) or cudaMemcpyAsync (LV_FLAG_MODE=memcpy)
     // pressure (slot order)

@@ -207,7 +207,8 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
     """remesh!(grid)  voronoigrid.jl:89-108.
 
     ``lazy=True`` returns once ``rowptr``, areas and centroids are back and lets the edge records (40 B each, the bulk
-    of the traffic) arrive in the background; call ``wait_edges(grid)`` before reading ``grid.edges``.
+    of the traffic) arrive in the background; call ``wait_edges(grid)`` before reading ``grid.edges``.  ``lazy="all"``
+    sends rowptr, areas and centroids in the background as well: nothing may be read before ``wait_edges(grid)``.
 
     Gathers ``grid.x``, runs the cell-list build and the clipping kernel on the GPU and leaves
     ``grid.rowptr`` / ``grid.edges`` (the flat ``p.edges`` view), areas and centroids on the host.
@@ -225,9 +226,10 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
                           ptr(grid._centroid)), grid._h)
         grid.edges = None
         return
-    if bool(lazy) != getattr(grid, "_lazy_edges", False):
-        check(L.lv_set_async_edges(grid._h, int(bool(lazy))), grid._h)
-        grid._lazy_edges = bool(lazy)
+    mode = 2 if lazy == "all" else int(bool(lazy))
+    if mode != getattr(grid, "_lazy_edges", 0):
+        check(L.lv_set_async_edges(grid._h, mode), grid._h)
+        grid._lazy_edges = mode
     buf = getattr(grid, "_edge_buf", None)
     if buf is None or buf.shape[0] < 6 * n + 64:  # grow-only pinned buffer: page-locking GBs per call would dominate
         wait_edges(grid)  # a background copy of the previous lazy remesh may still be writing into the old buffer

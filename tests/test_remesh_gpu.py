@@ -183,6 +183,16 @@ def test_lazy_edge_download_is_identical(lv):
     assert g.edges.tobytes() == ref[1].tobytes()
     lv.remesh(g)                                            # back to the synchronous mode
     assert g.edges.tobytes() == ref[1].tobytes()
+    # everything lazy: rowptr, areas and centroids arrive in the background too
+    area_ref, cen_ref = lv.area(g).copy(), lv.centroid(g).copy()
+    g.edges[...] = 0; g.rowptr[...] = 0; g._area[...] = 0; g._centroid[...] = 0
+    for _ in range(3):
+        lv.remesh(g, lazy="all")
+    lv.wait_edges(g)
+    assert np.array_equal(g.rowptr, ref[0]) and g.edges.tobytes() == ref[1].tobytes()
+    assert np.array_equal(lv.area(g), area_ref) and np.array_equal(lv.centroid(g), cen_ref)
+    lv.remesh(g)
+    assert g.edges.tobytes() == ref[1].tobytes()
 
 
 def _degenerate_sets(seed):
