@@ -3,8 +3,8 @@
 Mirrors IO.jl:14-72 and the output part of simulation.jl:35-94: ``export_grid`` writes the Voronoi polygons as
 PolyData polys (the chain of ``v1`` vertices of every polygon, IO.jl:18-26) with per-polygon cell data,
 ``export_points`` the generators as a vertex cloud, ``run`` is the fixed-dt loop with frame cadence, ``cells.pvd`` /
-``points.pvd`` collections and ``simdata.csv``.  Files are plain (ascii) VTK XML that ParaView reads; the reference
-writes the same data model through WriteVTK.jl (compressed binary).
+``points.pvd`` collections and ``simdata.csv``.  Files are VTK XML PolyData with appended raw binary data (optionally zlib
+compressed) -- the container WriteVTK.jl produces for the reference -- written straight from the numpy buffers.
 """
 from __future__ import annotations
 
@@ -13,60 +13,146 @@ import os
 import numpy as np
 
 
-def _data_array(name, arr, ncomp=1, dtype="Float64"):
-    a = np.asarray(arr)
-    fmt = "%.17g" if dtype.startswith("Float") else "%d"
-    body = "\n".join(" ".join(fmt % v for v in row) for row in a.reshape(-1, ncomp if ncomp > 1 else 1))
-    nc = f' NumberOfComponents="{ncomp}"' if ncomp > 1 else ""
-    return f'<DataArray type="{dtype}" Name="{name}"{nc} format="ascii">\n{body}\n</DataArray>\n'
+_VTK_TYPES = {np.dtype("float64"): "Float64", np.dtype("int64"): "Int64", np.dtype("int32"): "Int32", np.dtype("float32"): "Float32"}
+
+
+class _VtpWriter:
+    """VTK XML PolyData with APPENDED RAW data (what WriteVTK.jl's ``vtk_grid`` writes by default: ``append = true``), optionally
+    zlib-compressed per block like WriteVTK's ``compress = true``.  Arrays are written straight from their numpy buffers --
+    no per-number formatting -- so a 16M-cell frame costs a few seconds of memcpy / file I/O instead of 10^8 ``%`` operations.
+    ``ascii=True`` keeps the old plain-text form (small files, debugging)."""
+
+    BLOCK = 1 << 22  # uncompressed bytes per zlib block
+
+    def __init__(self, ascii: bool = False, compress: bool = False):
+        self.ascii, self.compress = ascii, compress
+        self.blobs, self.offset = [], 0
+
+    def array(self, name, arr, ncomp=1):
+        a = np.ascontiguousarray(arr)
+        if a.dtype not in _VTK_TYPES:
+            a = a.astype(np.float64 if a.dtype.kind == "f" else np.int64)
+        typ = _VTK_TYPES[a.dtype]
+        nc = f' NumberOfComponents="{ncomp}"' if ncomp > 1 else ""
+        if self.ascii:
+            flat = a.reshape(-1, ncomp if ncomp > 1 else 1)
+            fmt = "%.17g" if a.dtype.kind == "f" else "%d"
+            body = "\n".join(" ".join(fmt % v for v in row) for row in flat)
+            return f'<DataArray type="{typ}" Name="{name}"{nc} format="ascii">\n{body}\n</DataArray>\n'
+        raw = memoryview(a).cast("B")
+        if self.compress:
+            import zlib
+            nb = max(1, (len(raw) + self.BLOCK - 1) // self.BLOCK)
+            parts = [zlib.compress(raw[k * self.BLOCK:(k + 1) * self.BLOCK], 1) for k in range(nb)]
+            last = len(raw) - (nb - 1) * self.BLOCK
+            head = np.array([nb, self.BLOCK, 0 if last == self.BLOCK else last] + [len(q) for q in parts], dtype="<u8").tobytes()
+            chunk = [head] + parts
+        else:
+            chunk = [np.array([len(raw)], dtype="<u8").tobytes(), raw]
+        off = self.offset
+        self.blobs += chunk
+        self.offset += sum(len(q) for q in chunk)
+        return f'<DataArray type="{typ}" Name="{name}"{nc} format="appended" offset="{off}"/>\n'
+
+    def header(self):
+        comp = ' compressor="vtkZLibDataCompressor"' if (self.compress and not self.ascii) else ""
+        return f'<?xml version="1.0"?>\n<VTKFile type="PolyData" version="1.0" byte_order="LittleEndian" header_type="UInt64"{comp}>\n'
+
+    def write(self, filename, body):
+        with open(filename, "wb") as f:
+            f.write((self.header() + body).encode())
+            if not self.ascii:
+                f.write(b'<AppendedData encoding="raw">\n_')
+                for q in self.blobs:
+                    f.write(q)
+                f.write(b"\n</AppendedData>\n")
+            f.write(b"</VTKFile>\n")
 
 
 def _vec3(a):
     a = np.asarray(a, dtype=np.float64).reshape(-1, 2)
-    return np.concatenate([a, np.zeros((a.shape[0], 1))], axis=1)  # Vec3  IO.jl:1-3
+    out = np.zeros((a.shape[0], 3))
+    out[:, :2] = a
+    return out  # Vec3  IO.jl:1-3
 
 
-def _datasets(grid, names):
+def _datasets(w, grid, names):
     out = ""
     for nm in names:
         if not hasattr(grid, nm):
             raise ValueError(f"Cannot export variable {nm} because it does not exist.")  # IO.jl:65-67
         a = np.asarray(getattr(grid, nm))
-        out += _data_array(nm, _vec3(a), 3) if a.ndim == 2 else _data_array(nm, a)
+        out += w.array(nm, _vec3(a), 3) if a.ndim == 2 else w.array(nm, a.astype(np.float64, copy=False))
     return out
 
 
-def export_grid(grid, filename: str, *variables) -> str:
+def export_grid(grid, filename: str, *variables, ascii: bool = False, compress: bool = False) -> str:
     """export_grid(grid, filename, vars...)  IO.jl:14-33"""
     if not filename.endswith(".vtp"):
         filename += ".vtp"
     rowptr, edges = grid.rowptr, grid.edges
     pts = _vec3(edges["v1"])                                   # one vertex per edge, in chain order
     n, m = len(rowptr) - 1, pts.shape[0]
-    xml = ('<?xml version="1.0"?>\n<VTKFile type="PolyData" version="1.0" byte_order="LittleEndian">\n<PolyData>\n'
-           f'<Piece NumberOfPoints="{m}" NumberOfVerts="0" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="{n}">\n'
-           "<Points>\n" + _data_array("Points", pts, 3) + "</Points>\n<Polys>\n"
-           + _data_array("connectivity", np.arange(m), 1, "Int64") + _data_array("offsets", rowptr[1:], 1, "Int64")
-           + "</Polys>\n<CellData>\n" + _datasets(grid, variables) + "</CellData>\n</Piece>\n</PolyData>\n</VTKFile>\n")
-    with open(filename, "w") as f:
-        f.write(xml)
+    w = _VtpWriter(ascii, compress)
+    body = ("<PolyData>\n"
+            f'<Piece NumberOfPoints="{m}" NumberOfVerts="0" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="{n}">\n'
+            "<Points>\n" + w.array("Points", pts, 3) + "</Points>\n<Polys>\n"
+            + w.array("connectivity", np.arange(m, dtype=np.int64)) + w.array("offsets", np.asarray(rowptr[1:], dtype=np.int64))
+            + "</Polys>\n<CellData>\n" + _datasets(w, grid, variables) + "</CellData>\n</Piece>\n</PolyData>\n")
+    w.write(filename, body)
     return filename
 
 
-def export_points(grid, filename: str, *variables) -> str:
+def export_points(grid, filename: str, *variables, ascii: bool = False, compress: bool = False) -> str:
     """export_points(grid, filename, vars...)  IO.jl:50-57"""
     if not filename.endswith(".vtp"):
         filename += ".vtp"
     pts = _vec3(grid.x)
     n = pts.shape[0]
-    xml = ('<?xml version="1.0"?>\n<VTKFile type="PolyData" version="1.0" byte_order="LittleEndian">\n<PolyData>\n'
-           f'<Piece NumberOfPoints="{n}" NumberOfVerts="{n}" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="0">\n'
-           "<Points>\n" + _data_array("Points", pts, 3) + "</Points>\n<Verts>\n"
-           + _data_array("connectivity", np.arange(n), 1, "Int64") + _data_array("offsets", np.arange(1, n + 1), 1, "Int64")
-           + "</Verts>\n<PointData>\n" + _datasets(grid, variables) + "</PointData>\n</Piece>\n</PolyData>\n</VTKFile>\n")
-    with open(filename, "w") as f:
-        f.write(xml)
+    w = _VtpWriter(ascii, compress)
+    body = ("<PolyData>\n"
+            f'<Piece NumberOfPoints="{n}" NumberOfVerts="{n}" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="0">\n'
+            "<Points>\n" + w.array("Points", pts, 3) + "</Points>\n<Verts>\n"
+            + w.array("connectivity", np.arange(n, dtype=np.int64)) + w.array("offsets", np.arange(1, n + 1, dtype=np.int64))
+            + "</Verts>\n<PointData>\n" + _datasets(w, grid, variables) + "</PointData>\n</Piece>\n</PolyData>\n")
+    w.write(filename, body)
     return filename
+
+
+def read_vtp(filename: str) -> dict:
+    """Minimal reader of the files written above (tests, post-processing): {array name: numpy array} plus the piece counts."""
+    import re
+    import zlib
+    blob = open(filename, "rb").read()
+    k = blob.find(b'<AppendedData encoding="raw">')
+    xml = blob if k < 0 else blob[:k]
+    text = xml.decode()
+    data0 = None if k < 0 else blob.index(b"_", k) + 1
+    compressed = "vtkZLibDataCompressor" in text
+    out = {"_counts": {m.group(1): int(m.group(2)) for m in re.finditer(r'NumberOf(\w+)="(\d+)"', text)}}
+    types = {v: k2 for k2, v in _VTK_TYPES.items()}
+    for m in re.finditer(r'<DataArray type="(\w+)" Name="(\w+)"(?: NumberOfComponents="(\d+)")? format="(\w+)"(?: offset="(\d+)")?\s*(/>|>)', text):
+        typ, name, nc, fmt, off = m.group(1), m.group(2), int(m.group(3) or 1), m.group(4), m.group(5)
+        dt = types[typ]
+        if fmt == "ascii":
+            end = text.index("</DataArray>", m.end())
+            a = np.array(text[m.end():end].split(), dtype=dt)
+        else:
+            p = data0 + int(off)
+            if compressed:
+                nb, bs, last = (int(v) for v in np.frombuffer(blob, "<u8", 3, p))
+                sizes = np.frombuffer(blob, "<u8", nb, p + 24)
+                q = p + 24 + 8 * nb
+                parts = []
+                for sz in sizes:
+                    parts.append(zlib.decompress(blob[q:q + int(sz)]))
+                    q += int(sz)
+                a = np.frombuffer(b"".join(parts), dtype=dt)
+            else:
+                nbytes = int(np.frombuffer(blob, "<u8", 1, p)[0])
+                a = np.frombuffer(blob, dtype=dt, count=nbytes // dt.itemsize, offset=p + 8)
+        out[name] = a.reshape(-1, nc) if nc > 1 else a
+    return out
 
 
 class _Pvd:

@@ -961,6 +961,102 @@ int lvo_populate_hex(lvo_grid *g) {
     return lvo_remesh(g);
 }
 
+/* ------------------------------------------------------------------ populate.jl:18-145 (the other seeding strategies)
+ * charfun = everywhere; ic! is the caller's business.  Julia's ranges are evaluated in twice precision (StepRangeLen),
+ * i.e. element k of a:s:b is the correctly rounded a + k*s: long double arithmetic reproduces that on x86. */
+static int inside_rect(const lvo_grid *g, double x1, double x2) { /* isinside  geometry.jl:127-129 */
+    return (g->bmin.x <= x1 && x1 <= g->bmax.x) && (g->bmin.y <= x2 && x2 <= g->bmax.y);
+}
+static double corner_rmax(const lvo_grid *g, double cx, double cy) { /* maximum(norm(x - center) for x in verts(rect)) */
+    double r = 0.0;
+    const double xs[2] = {g->bmin.x, g->bmax.x}, ys[2] = {g->bmin.y, g->bmax.y};
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            double dx = xs[a] - cx, dy = ys[b] - cy, d = sqrt(dx * dx + dy * dy);
+            if (d > r) r = d;
+        }
+    return r;
+}
+typedef struct { double *xy; int64_t n, cap; } ptbuf;
+static void pt_push(ptbuf *b, double x1, double x2) {
+    if (b->n == b->cap) { b->cap = b->cap ? 2 * b->cap : 1024; b->xy = (double *)realloc(b->xy, sizeof(double) * 2 * (size_t)b->cap); }
+    b->xy[2 * b->n] = x1; b->xy[2 * b->n + 1] = x2; b->n++;
+}
+int lvo_populate_circ(lvo_grid *g, double cx, double cy) { /* populate.jl:18-35 */
+    double r_max = corner_rmax(g, cx, cy);
+    ptbuf b = {NULL, 0, 0};
+    /* for r in (0.5*dr):dr:r_max -- floor((r_max - 0.5dr)/dr) + 1 elements, the end point included when it is hit */
+    int64_t nring = r_max >= 0.5 * g->dr ? (int64_t)floor((r_max - 0.5 * g->dr) / g->dr * (1.0 + 4e-16)) + 1 : 0;
+    for (int64_t k = 0; k < nring; k++) {
+        double r = (double)(0.5L * (long double)g->dr + (long double)k * (long double)g->dr);
+        int64_t k_max = (int64_t)nearbyint(2.0 * M_PI * r / g->dr); /* round(Int, .): ties to even, like Julia */
+        for (int64_t q = 1; q <= k_max; q++) {
+            double theta = 2.0 * M_PI * (double)q / (double)k_max;
+            double x1 = cx + r * cos(theta), x2 = cy + r * sin(theta);
+            if (inside_rect(g, x1, x2)) pt_push(&b, x1, x2);
+        }
+    }
+    lvo_set_points(g, b.n, b.xy);
+    free(b.xy);
+    return lvo_remesh(g);
+}
+int lvo_populate_rect(lvo_grid *g) { /* populate.jl:46-66 */
+    int64_t N = (int64_t)nearbyint((g->bmax.x - g->bmin.x) / g->dr), M = (int64_t)nearbyint((g->bmax.y - g->bmin.y) / g->dr);
+    ptbuf b = {NULL, 0, 0};
+    for (int64_t i = 0; i < N; i++) {     /* range(x1_min, x1_max, N): N points, both ends included */
+        long double t1 = N > 1 ? (long double)i / (long double)(N - 1) : 0.0L;
+        double x1 = (double)((long double)g->bmin.x + t1 * ((long double)g->bmax.x - (long double)g->bmin.x));
+        for (int64_t j = 0; j < M; j++) {
+            long double t2 = M > 1 ? (long double)j / (long double)(M - 1) : 0.0L;
+            double x2 = (double)((long double)g->bmin.y + t2 * ((long double)g->bmax.y - (long double)g->bmin.y));
+            double p1 = x1 + 0.5 * g->dr, p2 = x2 + 0.5 * g->dr;
+            if (inside_rect(g, p1, p2)) pt_push(&b, p1, p2);
+        }
+    }
+    lvo_set_points(g, b.n, b.xy);
+    free(b.xy);
+    return lvo_remesh(g);
+}
+int lvo_populate_vogel(lvo_grid *g, double cx, double cy) { /* populate.jl:105-121 */
+    double r_max = corner_rmax(g, cx, cy);
+    int64_t N = (int64_t)nearbyint(M_PI * r_max * r_max / (g->dr * g->dr));
+    ptbuf b = {NULL, 0, 0};
+    for (int64_t i = 1; i <= N; i++) {
+        double r = r_max * sqrt((double)i / (double)N);
+        double theta = 2.39996322972865332 * (double)i;
+        double x1 = cx + r * cos(theta), x2 = cy + r * sin(theta);
+        if (inside_rect(g, x1, x2)) pt_push(&b, x1, x2);
+    }
+    lvo_set_points(g, b.n, b.xy);
+    free(b.xy);
+    return lvo_remesh(g);
+}
+/* populate_rand!  populate.jl:76-95 with the uniform samples (s1, s2 per point) supplied by the caller instead of Julia's
+ * global RNG; ns = number of sample pairs available (>= N = round(area/dr^2)) */
+int lvo_populate_rand(lvo_grid *g, const double *s, int64_t ns) {
+    int64_t N = (int64_t)nearbyint(fabs(g->bmax.x - g->bmin.x) * fabs(g->bmax.y - g->bmin.y) / (g->dr * g->dr));
+    if (N > ns) return LVO_EINVAL;
+    ptbuf b = {NULL, 0, 0};
+    for (int64_t i = 0; i < N; i++) {
+        double s1 = s[2 * i], s2 = s[2 * i + 1];
+        double x1 = s1 * g->bmax.x + (1 - s1) * g->bmin.x, x2 = s2 * g->bmax.y + (1 - s2) * g->bmin.y;
+        if (inside_rect(g, x1, x2)) pt_push(&b, x1, x2);
+    }
+    lvo_set_points(g, b.n, b.xy);
+    free(b.xy);
+    return lvo_remesh(g);
+}
+/* the relaxation loop of populate_lloyd!  populate.jl:132-145: niter x (remesh!; p.x = centroid(p)), then remesh! */
+int lvo_lloyd(lvo_grid *g, int niter) {
+    for (int it = 0; it < niter; it++) {
+        int st = lvo_remesh(g);
+        if (st != LVO_OK) return st;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < g->n; i++) g->polygons[i]->x = poly_centroid(g->polygons[i]);
+    }
+    return lvo_remesh(g);
+}
+
 /* ------------------------------------------------------------------ move.jl */
 static double least_positive_residue(double x, double d) { return fmod(fmod(x, d) + d, d); } /* voronoigrid.jl:181-183 */
 static vec2 periodic_wrap(const lvo_grid *g, vec2 x) { /* voronoigrid.jl:187-192 */

@@ -85,6 +85,12 @@ int lvo_cg(const lvo_grid *g, const double *b, double *x, double rtol, double at
 /* callers either side of the hot path, needed to pin the oracle with
  * the reference's own Taylor-Green thresholds */
 int lvo_populate_hex(lvo_grid *g);                                /* populate.jl:149-174 (no ic!) */
+/* the other seeding strategies (charfun = everywhere, no ic!) and the relaxation loop of populate_lloyd! */
+int lvo_populate_circ(lvo_grid *g, double cx, double cy);        /* populate.jl:18-35 */
+int lvo_populate_rect(lvo_grid *g);                               /* populate.jl:46-66 */
+int lvo_populate_vogel(lvo_grid *g, double cx, double cy);       /* populate.jl:105-121 */
+int lvo_populate_rand(lvo_grid *g, const double *s, int64_t ns); /* populate.jl:76-95, uniform samples from the caller */
+int lvo_lloyd(lvo_grid *g, int niter);                            /* populate.jl:132-145 */
 int lvo_move(lvo_grid *g, double dt);                             /* move.jl:9-33 */
 void lvo_stiffened_eos(lvo_grid *g, double gamma, double P0);     /* pressure.jl:64-70 */
 void lvo_ideal_eos(lvo_grid *g, double gamma, double Pmin);       /* pressure.jl:49-55 */

@@ -63,6 +63,11 @@ def lib() -> C.CDLL:
         L.lvo_minres.argtypes = [vp, dp, dp, C.c_double, C.c_double, C.c_int, C.c_int]
         L.lvo_cg.argtypes = [vp, dp, dp, C.c_double, C.c_double, C.c_int]
         L.lvo_populate_hex.argtypes = [vp]
+        L.lvo_populate_circ.argtypes = [vp, C.c_double, C.c_double]
+        L.lvo_populate_rect.argtypes = [vp]
+        L.lvo_populate_vogel.argtypes = [vp, C.c_double, C.c_double]
+        L.lvo_populate_rand.argtypes = [vp, dp, C.c_int64]
+        L.lvo_lloyd.argtypes = [vp, C.c_int]
         L.lvo_move.argtypes = [vp, C.c_double]
         L.lvo_stiffened_eos.argtypes = [vp, C.c_double, C.c_double]
         L.lvo_ideal_eos.argtypes = [vp, C.c_double, C.c_double]
@@ -242,6 +247,24 @@ class OracleGrid:
     # -- callers either side of the hot path
     def populate_hex(self) -> int:
         return int(lib().lvo_populate_hex(self._g))
+
+    def populate_circ(self, center=(0.0, 0.0)) -> int:
+        return int(lib().lvo_populate_circ(self._g, float(center[0]), float(center[1])))
+
+    def populate_rect(self) -> int:
+        return int(lib().lvo_populate_rect(self._g))
+
+    def populate_vogel(self, center=(0.0, 0.0)) -> int:
+        return int(lib().lvo_populate_vogel(self._g, float(center[0]), float(center[1])))
+
+    def populate_rand(self, samples) -> int:
+        """populate_rand! with the caller's uniform samples [[s1, s2], ...] in place of Julia's global RNG."""
+        s = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, 2)
+        return int(lib().lvo_populate_rand(self._g, _dp(s), s.shape[0]))
+
+    def lloyd(self, niterations=100) -> int:
+        """The relaxation loop of populate_lloyd! (populate.jl:132-145) on the current generators."""
+        return int(lib().lvo_lloyd(self._g, int(niterations)))
 
     def move(self, dt) -> int:
         return int(lib().lvo_move(self._g, float(dt)))

@@ -19,20 +19,122 @@ def test_vtp_writers_roundtrip(lv, tmp_path):
     g.edges["v1"] = [[0, 0], [0, 1], [1, 0], [1, 1], [1, 0], [0, 1]]
     g.x = np.array([[0.3, 0.3], [0.7, 0.7]])
     g.P = np.array([1.5, -2.0]); g.v = np.array([[1.0, 2.0], [3.0, 4.0]])
-    f = lv.io.export_grid(g, str(tmp_path / "c"), "P", "v")
-    root = ET.parse(f).getroot()
-    piece = root.find("PolyData/Piece")
-    assert piece.get("NumberOfPoints") == "6" and piece.get("NumberOfPolys") == "2"
-    offs = [int(t) for t in piece.find("Polys/DataArray[@Name='offsets']").text.split()]
-    assert offs == [3, 6]
-    P = [float(t) for t in piece.find("CellData/DataArray[@Name='P']").text.split()]
-    assert P == [1.5, -2.0]
-    v = piece.find("CellData/DataArray[@Name='v']")
-    assert v.get("NumberOfComponents") == "3"
-    f2 = lv.io.export_points(g, str(tmp_path / "p"), "P")
-    assert ET.parse(f2).getroot().find("PolyData/Piece").get("NumberOfVerts") == "2"
+    for mode, kw in (("ascii", {"ascii": True}), ("raw", {}), ("zlib", {"compress": True})):
+        f = lv.io.export_grid(g, str(tmp_path / ("c" + mode)), "P", "v", **kw)
+        d = lv.io.read_vtp(f)
+        assert d["_counts"]["Points"] == 6 and d["_counts"]["Polys"] == 2
+        assert d["offsets"].tolist() == [3, 6] and d["connectivity"].tolist() == list(range(6))
+        assert np.array_equal(d["Points"], np.column_stack([g.edges["v1"], np.zeros(6)]))
+        assert d["P"].tolist() == [1.5, -2.0]
+        assert np.array_equal(d["v"], [[1.0, 2.0, 0.0], [3.0, 4.0, 0.0]])           # Vec3  IO.jl:1-3
+        f2 = lv.io.export_points(g, str(tmp_path / ("p" + mode)), "P", **kw)
+        assert lv.io.read_vtp(f2)["_counts"]["Verts"] == 2
+        if mode == "ascii":                                                          # the ascii form is plain XML
+            piece = ET.parse(f).getroot().find("PolyData/Piece")
+            assert piece.get("NumberOfPoints") == "6" and piece.find("CellData/DataArray[@Name='v']").get("NumberOfComponents") == "3"
+        else:                                                                        # the XML part parses once the raw block is cut out
+            blob = open(f, "rb").read()
+            head = blob[:blob.index(b"<AppendedData")] + b"</VTKFile>"
+            assert ET.fromstring(head).find("PolyData/Piece/Points/DataArray").get("format") == "appended"
+    # a large frame goes through without per-number formatting: 2M edge records in well under a second of CPU
+    import time
+    big = _FakeGrid()
+    m = 2_000_000
+    big.rowptr = np.arange(0, m + 1, 4)
+    big.edges = np.zeros(m, lv.EDGE_DTYPE)
+    big.edges["v1"] = np.random.default_rng(0).random((m, 2))
+    big.P = np.zeros(m // 4)
+    t0 = time.perf_counter()
+    fb = lv.io.export_grid(big, str(tmp_path / "big"), "P")
+    assert time.perf_counter() - t0 < 5.0
+    assert np.array_equal(lv.io.read_vtp(fb)["Points"][:, :2], big.edges["v1"])
     with pytest.raises(ValueError, match="does not exist"):                      # IO.jl:65-67
         lv.io.export_grid(g, str(tmp_path / "bad"), "nope")
+
+
+def _host_points(lv, name, dom, dr, **kw):
+    """The generator set a populate_* strategy of the host mirror produces, without touching the GPU."""
+    class Dummy:                                                            # stands in for VoronoiGrid: only geometry is read
+        boundary_rect, n = dom, 0
+    d = Dummy(); d.dr = dr
+    got = {}
+    orig = lv.populate._finish
+    lv.populate._finish = lambda grid, pts, charfun, ic, edges=True: got.setdefault("pts", _inside(np.asarray(pts, float).reshape(-1, 2), dom))
+    try:
+        getattr(lv.populate, "populate_" + name)(d, **kw)
+    finally:
+        lv.populate._finish = orig
+    return got["pts"]
+
+
+def _inside(p, dom):
+    (x0, y0), (x1, y1) = dom.xmin, dom.xmax
+    return p[(p[:, 0] >= x0) & (p[:, 0] <= x1) & (p[:, 1] >= y0) & (p[:, 1] <= y1)]
+
+
+@pytest.mark.parametrize("dom,dr", [(((0.0, 0.0), (1.0, 1.0)), 1 / 40), (((-0.5, 0.25), (1.5, 1.25)), 1 / 37), (((-1.0, -1.0), (1.0, 1.0)), 0.0625)])
+def test_seeding_strategies_match_the_oracle_restatement(lv, oracle, dom, dr):
+    """populate_rect! / hex! / circ! / vogel! / rand! (populate.jl:18-174): the host mirror and the C restatement generate the
+    same generators in the same order (labels are positions in that order).  rect and hex are exact; circ and vogel go
+    through libm's sin / cos on both sides and agree to the last few ulps."""
+    rect = lv.Rectangle(*dom)
+    centre = (0.5 * (dom[0][0] + dom[1][0]) + 0.013, 0.5 * (dom[0][1] + dom[1][1]) - 0.02)
+    samples = np.random.default_rng(5).random((int(round((dom[1][0] - dom[0][0]) * (dom[1][1] - dom[0][1]) / dr ** 2)), 2))
+    cases = {"rect": ({}, lambda og: og.populate_rect(), 0.0), "hex": ({}, lambda og: og.populate_hex(), 0.0),
+             "circ": ({"center": centre}, lambda og: og.populate_circ(centre), 4e-16),
+             "vogel": ({"center": centre}, lambda og: og.populate_vogel(centre), 4e-16),
+             "rand": ({"samples": samples}, lambda og: og.populate_rand(samples), 0.0)}
+    for name, (kw, run, tol) in cases.items():
+        og = oracle.OracleGrid(dom[0], dom[1], dr)
+        assert run(og) == 0, name
+        a, b = _host_points(lv, name, rect, dr, **kw), og.get("x")
+        assert a.shape == b.shape and len(a) > 100, (name, a.shape, b.shape)
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() <= tol * scale, (name, np.abs(a - b).max())
+
+
+def test_lloyd_relaxation_on_the_restatement(oracle):
+    """populate_lloyd! (populate.jl:132-145) through the restatement: the cells even out (area spread shrinks), the domain
+    stays tiled, generators converge towards their centroids."""
+    dr = 1 / 24
+    og = oracle.OracleGrid((0.0, 0.0), (1.0, 1.0), dr)
+    s = np.random.default_rng(3).random((576, 2))
+    assert og.populate_rand(s) == 0
+    a0 = og.area().std()
+    assert og.lloyd(30) == 0
+    assert og.area().std() < 0.35 * a0 and abs(og.area().sum() - 1.0) < 1e-12
+    assert np.abs(og.get("x") - og.centroid()).max() < 0.05 * dr
+
+
+@pytest.mark.gpu
+def test_seeding_and_lloyd_parity_with_the_oracle(lv, oracle):
+    """f3 parity: every seeding strategy gives the oracle's mesh byte for byte on the oracle's generators, and the device-side
+    Lloyd loop (lv_step_lloyd: 100 x (remesh!; x = centroid)) lands on the restatement's positions bit for bit -- every
+    iteration clips the same polygons and computes the same centroids."""
+    dom = ((0.0, 0.0), (1.0, 1.0))
+    dr = 1 / 32
+    centre = (0.47, 0.52)
+    samples = np.random.default_rng(8).random((1024, 2))
+    runs = {"rect": lambda og: og.populate_rect(), "hex": lambda og: og.populate_hex(), "circ": lambda og: og.populate_circ(centre),
+            "vogel": lambda og: og.populate_vogel(centre), "rand": lambda og: og.populate_rand(samples)}
+    for name, run in runs.items():
+        og = oracle.OracleGrid(dom[0], dom[1], dr)
+        assert run(og) == 0
+        g = lv.VoronoiGrid(lv.Rectangle(*dom), dr)
+        g.set_points(og.get("x"))
+        lv.remesh(g)
+        r0, e0 = og.mesh()
+        assert np.array_equal(g.rowptr, r0) and g.edges.tobytes() == e0.tobytes(), name
+        assert np.array_equal(lv.centroid(g), og.centroid()) and np.array_equal(lv.area(g), og.area()), name
+    # Lloyd from the same random seeding, 100 iterations like the reference's default
+    og = oracle.OracleGrid(dom[0], dom[1], dr)
+    assert og.populate_rand(samples) == 0
+    g = lv.VoronoiGrid(lv.Rectangle(*dom), dr)
+    lv.populate.populate_lloyd(g, niterations=100, samples=samples)
+    assert og.lloyd(100) == 0
+    assert np.array_equal(g.x, og.get("x"))
+    r0, e0 = og.mesh()
+    assert np.array_equal(g.rowptr, r0) and g.edges.tobytes() == e0.tobytes()
 
 
 @pytest.mark.gpu
