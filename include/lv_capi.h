@@ -214,7 +214,8 @@ int32_t lv_comm_init(LvHandle h, int32_t rank, int32_t nranks, const uint8_t *id
 int32_t lv_remesh_owned_dev(LvHandle h, int64_t n_local, const double *xy_dev, const uint8_t *owned_mask_dev,
                             const int32_t *order_key_dev);
 /* device pointers into the slot-ordered cell list (0 ent_label u32, 1 prim_of_label i32, 2 own u8,
- * 3 ent_xy f64x2, 4 P f64, 5 area f64; strip mode: 6 local positions f64x2, 7 local global labels i32) */
+ * 3 ent_xy f64x2, 4 P f64, 5 area f64; strip mode: 6 local positions f64x2, 7 local global labels i32, 8 the same
+ * array counted to the owned generators only) */
 int32_t lv_device_array(LvHandle h, int32_t which, void **ptr, int64_t *count);
 /* per peer rank: how many values this rank sends / receives and the (device) slot lists, concatenated */
 int32_t lv_halo_plan(LvHandle h, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count,
@@ -237,6 +238,15 @@ int32_t lv_strip_setup(LvHandle h, int32_t npeers, const int32_t *peer_rank, con
 int32_t lv_strip_map(LvHandle h, const uint8_t *handles);
 int32_t lv_strip_set_owned(LvHandle h, int64_t n_own, const double *xy, int32_t xy_on_host, const int32_t *global_label_dev);
 int32_t lv_strip_remesh(LvHandle h, int64_t *counts_out);
+/* bucket-row ownership of all ranks (R[0..world]: rank r owns rows [R[r], R[r+1])): needed by the migration that the
+ * device-resident move! / relaxation_step! run on strips */
+int32_t lv_strip_set_rows(LvHandle h, int32_t world, const int32_t *R);
+/* Device-resident stepping on strips (move.jl:9-33, relaxation.jl:36-73 across GPUs): make this rank's owned generators
+ * the resident state ("x" aliases the strip's position array; other fields via lv_state_set with n_own values).  Every
+ * lv_step_* sweep then refreshes the ghost entries it reads from their owners (NVLink pulls), the moving sweeps hand
+ * generators that left the strip -- with all their fields -- to the new owner before the strip remesh, and the multiphase
+ * projector's MINRES sums its dot products over the ranks. */
+int32_t lv_state_attach_strip(LvHandle h);
 /* Peer-memory allreduce of the two CG scalars: every rank exports a mailbox (CUDA IPC handle, 64 bytes), maps the
  * mailboxes of all ranks and from then on posts / collects partial sums with NVLink stores and flags; sums are
  * taken in rank order, so the result is deterministic and identical on every rank. */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
     "lv_launch_count", "lv_device_bytes", "lv_comm_unique_id", "lv_comm_init", "lv_remesh_owned_dev", "lv_device_array",
-    "lv_halo_plan", "lv_halo_exchange_dev", "lv_strip_setup", "lv_strip_map", "lv_strip_set_owned", "lv_strip_remesh", "lv_mailbox_export", "lv_mailbox_plan", "lv_peer_disable", "lv_peer_close",
+    "lv_halo_plan", "lv_halo_exchange_dev", "lv_strip_setup", "lv_strip_map", "lv_strip_set_owned", "lv_strip_remesh", "lv_strip_set_rows", "lv_state_attach_strip", "lv_mailbox_export", "lv_mailbox_plan", "lv_peer_disable", "lv_peer_close",
     "lv_state_set", "lv_state_get", "lv_state_ptr", "lv_state_remesh", "lv_step_move", "lv_step_eos", "lv_step_find_pressure",
     "lv_step_pressure_step", "lv_step_gravity", "lv_step_find_D", "lv_step_viscous_step", "lv_step_bdary_friction", "lv_step_bdary_friction_ex", "lv_step_find_dv", "lv_step_relaxation_step", "lv_step_lloyd", "lv_step_multiphase_projection", "lv_step_multiphase_apply",
 ]
@@ -118,6 +118,8 @@ def load_library() -> C.CDLL:
     L.lv_strip_map.argtypes = [vp, C.POINTER(C.c_uint8)]
     L.lv_strip_set_owned.argtypes = [vp, C.c_int64, vp, C.c_int32, vp]
     L.lv_strip_remesh.argtypes = [vp, ip]
+    L.lv_strip_set_rows.argtypes = [vp, C.c_int32, i32p]
+    L.lv_state_attach_strip.argtypes = [vp]
     L.lv_peer_close.argtypes = [vp]
     L.lv_mesh_hash.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.lv_step_multiphase_apply.argtypes = [vp, vp, vp, vp]

@@ -220,6 +220,7 @@ int32_t lv_destroy(LvHandle c) {
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1], c->d_io_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);
+    if (c->st_x_alias) c->st_field[0] = nullptr; // owned by the strip state
     for (double *v : c->st_field) if (v) cudaFree(v);
     if (c->st_tmp) cudaFree(c->st_tmp);
     if (c->h_flags) cudaFreeHost(c->h_flags);

@@ -310,6 +310,7 @@ int32_t lv_device_array(LvHandle c, int32_t which, void **ptr, int64_t *count) {
     case 5: *ptr = c->d_area; *count = c->nslot; break;
     case 6: *ptr = c->strip.loc_xy; *count = c->strip.n_loc; break;  // strip mode: local generators (owned first, then ghosts)
     case 7: *ptr = c->strip.loc_key; *count = c->strip.n_loc; break; // ... and their global labels (int32)
+    case 8: *ptr = c->strip.loc_key; *count = c->strip.n_own; break; // the owned generators' global labels
     default: return lv_set_error(c, LV_EINVAL, "unknown device array %d", which);
     }
     return LV_OK;

@@ -16,6 +16,7 @@
 #include "../../include/lv_capi.h"
 
 #define LV_SP_MAXP 4 // strip neighbours per rank (2 in practice)
+#define LV_STATE_MAX 16 // resident state fields (lv_step.cu)
 #define LV_IMAGE_BIT 0x80000000u // set in ent_label[] for periodic-image slots
 
 struct LvPathNode { // neighborlist.jl:6-9, truncated table (see lv_capi.cu:build_magic_path)
@@ -125,6 +126,7 @@ struct LvContext {
     // device-resident polygon fields in label order (lv_step.cu)
     double *st_field[16] = {nullptr};
     double *st_tmp = nullptr;
+    bool st_x_alias = false; // strip mode: st_field[0] (x) is the strip's position array, not an allocation of its own
     int64_t st_n = 0, st_cap = 0;
     // multi-GPU: NCCL communicator + halo plan (lv_dist.cu)
     void *comm = nullptr; // ncclComm_t
@@ -158,7 +160,11 @@ struct LvContext {
         int *h_counts = nullptr;   // mapped pinned [16]
         int *send_pos0 = nullptr, *send_pos1 = nullptr; // [cap_slot] slot -> position in the halo outbox, or -1
         int64_t cap_pos = 0;
-        int gseq = 0, hseq = 0;    // remeshes / halo exchanges issued so far (same on every rank)
+        int gseq = 0, hseq = 0, mseq = 0; // remeshes / halo exchanges / migrations issued so far (same on every rank)
+        int *mig = nullptr, *holes = nullptr; // migration scratch: leavers per peer; holes + tails of the compaction
+        unsigned char *leave = nullptr;       // [cap_loc]
+        std::vector<int> world_rows;          // R[0..world]: bucket rows owned by every rank
+        int last_mig_out = 0, last_mig_in = 0;
         bool mapped = false;
     } strip;
     int64_t owned_count = -1; // >= 0: labels below it are owned (strip mode), instead of owned_mask
@@ -261,6 +267,8 @@ struct LvHaloPack { // what a producer kernel needs to pack its freshly written 
     int seq;                                    // value to publish
 };
 int lv_strip_pack_args(LvContext *c, LvHaloPack *out); // advances the exchange sequence
+int lv_strip_halo_state(LvContext *c, double *field_label_order, int ncomp); // ghosts of a label-ordered field (lv_step.cu state)
+int lv_strip_migrate(LvContext *c, int nf, double *const *fields, const int *ncomp); // after a move: leavers travel with their state
 int lv_remesh_common(LvContext *c, int64_t n);
 int lv_bdry_index(LvContext *c); // numbers the boundary edges of the current mesh (d_bdry_ptr, n_bedge)
 

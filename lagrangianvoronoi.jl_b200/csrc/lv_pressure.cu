@@ -1017,16 +1017,22 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
                     double rtol, double atol, int itmax, int *iters, int *solved) {
     if (iters) *iters = 0;
     if (solved) *solved = 1;
-    if (n == 0) return LV_OK;
+    const bool multi = c->comm != nullptr;
+    if (n == 0 && !multi) return LV_OK;
+    if (multi && !c->mailbox_ready) return lv_set_error(c, LV_EINVAL, "lv_minres_apply on several GPUs needs the peer mailboxes");
     cudaStream_t st = c->stream;
     double *scal = c->d_red, *partial = c->d_red + SC_COUNT;
     const int NBMAX = 4096;
     const int nb = pr_grid(c, n);
-    const MailArgs nomail{nullptr, 1, 0, 0, c->d_tickets + 7};
+    // reductions over the rows of this rank; on several GPUs the two sums of every step are exchanged through the mailboxes
+    auto scalars = [&](int mode) {
+        if (multi) k_cg_scalars<<<1, 256, 0, st>>>(mode, 3, nb, NBMAX, partial, scal, rtol, atol, MailArgs{(LvMailSlot *const *)c->d_mailbox_ptrs, c->nranks, c->rank, ++c->ar_seq, c->d_tickets + 7});
+        else k_cg_scalars<<<1, 256, 0, st>>>(mode, 0, nb, NBMAX, partial, scal, rtol, atol, MailArgs{nullptr, 1, 0, 0, c->d_tickets + 7});
+    };
     double *r1 = c->d_vec[0], *r2 = c->d_vec[1], *y = c->d_vec[2], *w1 = c->d_vec[3], *w2 = c->d_vec[4];
     LV_CUDA(c, cudaMemsetAsync(y, 0, sizeof(double) * (size_t)n, st)); // A*x0 with x0 = 0
     k_mr_init<<<nb, PR_BLOCK, 0, st>>>(n, b, y, r1, r2, w1, w2, x, partial);
-    k_cg_scalars<<<1, 256, 0, st>>>(4, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+    scalars(4);
     c->launches += 2;
     int done = 0;
     bool conv = false;
@@ -1036,11 +1042,11 @@ int lv_minres_apply(LvContext *c, int n, const std::function<int(const double *,
             const int iter = done + it + 1;
             LV_TRY(apply(r2, y));
             k_mr_a<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r2, r1, y, partial);
-            k_cg_scalars<<<1, 256, 0, st>>>(5, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            scalars(5);
             k_mr_b<<<nb, PR_BLOCK, 0, st>>>(n, iter, scal, r1, r2, y, w1, w2, partial, nullptr);
-            k_cg_scalars<<<1, 256, 0, st>>>(6, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            scalars(6);
             k_mr_c<<<nb, PR_BLOCK, 0, st>>>(n, scal, iter == 1 ? w2 : w1, x, partial);
-            k_cg_scalars<<<1, 256, 0, st>>>(7, 0, nb, NBMAX, partial, scal, rtol, atol, nomail);
+            scalars(7);
             c->launches += 6;
             if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
         }

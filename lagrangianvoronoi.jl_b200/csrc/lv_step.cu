@@ -427,7 +427,31 @@ static int field_index(const char *name) {
     return -1;
 }
 
+// Strip mode (lv_strip.cu): the state arrays cover the LOCAL generator list -- owned generators first, at [0, n_own), then the
+// ghosts -- with the fixed capacity of the strip; "x" is the strip's own position array (the ghost exchange of every remesh
+// writes the ghosts' positions there); sweeps run over the owned generators and read ghosts through label-order halos.
+static inline bool st_strip(const LvContext *c) { return c->strip.on; }
 static int state_ensure(LvContext *c, int64_t n) {
+    if (st_strip(c)) {
+        if (n > c->strip.cap_loc) return lv_set_error(c, LV_ECAPACITY, "strip: %lld generators exceed the local capacity", (long long)n);
+        if (!c->st_field[F_V] || c->st_cap < c->strip.cap_loc) {
+            LV_CUDA(c, cudaStreamSynchronize(c->stream));
+            const int64_t cap = c->strip.cap_loc;
+            for (int k = 0; k < F_COUNT; k++) {
+                if (k == F_X) continue;
+                if (c->st_field[k]) lv_free(c, c->st_field[k], sizeof(double) * (size_t)FIELD_NC[k] * (size_t)c->st_cap);
+                LV_TRY(lv_alloc(c, (void **)&c->st_field[k], sizeof(double) * (size_t)FIELD_NC[k] * (size_t)cap));
+                LV_CUDA(c, cudaMemsetAsync(c->st_field[k], 0, sizeof(double) * (size_t)FIELD_NC[k] * (size_t)cap, c->stream));
+            }
+            if (c->st_tmp) lv_free(c, c->st_tmp, sizeof(double) * 2 * (size_t)c->st_cap);
+            LV_TRY(lv_alloc(c, (void **)&c->st_tmp, sizeof(double) * 2 * (size_t)cap));
+            c->st_cap = cap;
+        }
+        c->st_field[F_X] = (double *)c->strip.loc_xy;
+        c->st_x_alias = true;
+        c->st_n = n;
+        return LV_OK;
+    }
     if (c->st_cap >= n && c->st_field[0]) { c->st_n = n; return LV_OK; }
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     const int64_t cap = n + n / 16 + 64;
@@ -459,12 +483,36 @@ static StepView make_view(LvContext *c) {
 
 static int need_mesh(LvContext *c) {
     if (!c->st_field[0]) return lv_set_error(c, LV_EINVAL, "no device state: call lv_state_set(\"x\", ...) first");
-    if (!c->mesh_valid || c->n != c->st_n) return lv_set_error(c, LV_EINVAL, "no mesh for the device state: call lv_state_remesh first");
+    const int64_t n_mesh = st_strip(c) ? c->strip.n_loc : c->st_n;
+    if (!c->mesh_valid || c->n != n_mesh || (st_strip(c) && c->st_n != c->strip.n_own))
+        return lv_set_error(c, LV_EINVAL, "no mesh for the device state: call lv_state_remesh first");
     return LV_OK;
 }
 
+// ghosts of label-ordered fields from their owners (no-op on one GPU)
+static int st_halo(LvContext *c, std::initializer_list<int> fields) {
+    if (!st_strip(c)) return LV_OK;
+    for (int k : fields) {
+        if (FIELD_NC[k] <= 4) LV_TRY(lv_strip_halo_state(c, c->st_field[k], FIELD_NC[k]));
+    }
+    return LV_OK;
+}
+
+extern "C" int32_t lv_strip_remesh(LvHandle c, int64_t *counts_out);
 static int state_remesh(LvContext *c) {
     if (!c->st_field[0]) return lv_set_error(c, LV_EINVAL, "no device state");
+    if (st_strip(c)) {
+        // generators that left the strip take their fields to the new owner, then the strip remesh (ghost exchange + clipping)
+        double *fields[F_COUNT];
+        int nc[F_COUNT], nf = 0;
+        for (int k = 0; k < F_COUNT; k++) {
+            if (k == F_X) continue;
+            fields[nf] = c->st_field[k]; nc[nf] = FIELD_NC[k]; nf++;
+        }
+        LV_TRY(lv_strip_migrate(c, nf, fields, nc));
+        c->st_n = c->strip.n_own;
+        return lv_strip_remesh(c, nullptr);
+    }
     return lv_remesh_dev(c, c->st_n, c->st_field[F_X]);
 }
 
@@ -478,8 +526,10 @@ int32_t lv_state_set(LvHandle c, const char *name, const double *host, int64_t n
     LV_CUDA(c, cudaSetDevice(c->device));
     const int k = field_index(name);
     if (k < 0) return lv_set_error(c, LV_EINVAL, "unknown field '%s'", name);
-    if (k == F_X) LV_TRY(state_ensure(c, n));
-    else if (!c->st_field[0] || n != c->st_n) return lv_set_error(c, LV_EINVAL, "set \"x\" first; field length must equal the number of polygons");
+    if (k == F_X) {
+        LV_TRY(state_ensure(c, n));
+        if (st_strip(c)) c->strip.n_own = n; // the owned generators; their global labels come from lv_strip_set_owned
+    } else if (!c->st_field[0] || n != c->st_n) return lv_set_error(c, LV_EINVAL, "set \"x\" first; field length must equal the number of polygons");
     if (n > 0) LV_CUDA(c, cudaMemcpyAsync(c->st_field[k], host, sizeof(double) * (size_t)FIELD_NC[k] * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     if (k == F_X) c->mesh_valid = false;
@@ -501,6 +551,15 @@ int32_t lv_state_ptr(LvHandle c, const char *name, void **dev_ptr, int64_t *n) {
     *dev_ptr = c->st_field[k];
     if (n) *n = c->st_n;
     return LV_OK;
+}
+
+// Strip mode: make the generators this rank owns (lv_strip_set_owned) the resident state -- "x" is the strip's own position
+// array, every other field is allocated for the local list (owned + ghosts) and zeroed; fill them with lv_state_set (n_own
+// values each).  From then on move! / relaxation_step! migrate generators between ranks together with their fields.
+int32_t lv_state_attach_strip(LvHandle c) {
+    if (!c || !c->strip.on) return lv_set_error(c, LV_EINVAL, "lv_state_attach_strip: not in strip mode");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    return state_ensure(c, c->strip.n_own);
 }
 
 int32_t lv_state_remesh(LvHandle c) { // remesh!(grid) on the resident positions
@@ -536,9 +595,13 @@ int32_t lv_step_pressure_step(LvHandle c, double dt) { // pressure_step!(grid, d
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
+    LV_TRY(st_halo(c, {F_P}));
     if (S.n > 0) {
         k_pressure_step_v<<<GRID(S.n)>>>(S, dt, (double2 *)c->st_tmp);
         LV_CUDA(c, cudaMemcpyAsync(S.v, c->st_tmp, sizeof(double2) * (size_t)S.n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    LV_TRY(st_halo(c, {F_V})); // the energy sweep reads the neighbours' NEW velocities
+    if (S.n > 0) {
         k_pressure_step_e<<<GRID(S.n)>>>(S, dt);
         c->launches += 2;
     }
@@ -561,6 +624,7 @@ int32_t lv_step_find_D(LvHandle c) { // find_D!(grid)  diffusion.jl:8-19
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
+    LV_TRY(st_halo(c, {F_V}));
     if (S.n > 0) { k_find_D<<<GRID(S.n)>>>(S); c->launches++; }
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
@@ -572,9 +636,13 @@ int32_t lv_step_viscous_step(LvHandle c, double dt, int32_t artificial_viscosity
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     const double avdr = artificial_viscosity ? c->dr : 0.0;
+    LV_TRY(st_halo(c, {F_D, F_MU, F_RHO})); // getS of the neighbours  diffusion.jl:22-29
     if (S.n > 0) {
         k_viscous_v<<<GRID(S.n)>>>(S, dt, avdr, (double2 *)c->st_tmp);
         LV_CUDA(c, cudaMemcpyAsync(S.v, c->st_tmp, sizeof(double2) * (size_t)S.n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    LV_TRY(st_halo(c, {F_V}));
+    if (S.n > 0) {
         k_viscous_e<<<GRID(S.n)>>>(S, dt, avdr);
         c->launches += 2;
     }
@@ -636,6 +704,7 @@ int32_t lv_step_relaxation_step(LvHandle c, double dt, int32_t rusanov) { // rel
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
+    LV_TRY(st_halo(c, {F_DV, F_V, F_RHO, F_E, F_PHASE}));
     if (S.n > 0) {
         k_relax_flux<<<GRID(S.n)>>>(S, dt, rusanov, c->st_tmp);
         k_relax_apply<<<GRID(S.n)>>>(S, dt, c->st_tmp);
@@ -665,18 +734,23 @@ int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, doub
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_TRY(need_mesh(c));
-    if (c->comm) return lv_set_error(c, LV_EINVAL, "the multiphase projector is single-GPU in this build");
+    if (c->comm && !lv_strip_peer_mode(c)) return lv_set_error(c, LV_EINVAL, "the multiphase projector on several GPUs needs the peer-memory strip exchange");
     LV_TRY(lv_pr_ensure(c));
     StepView S = make_view(c);
     const int n = (int)S.n;
-    if (n == 0) return LV_OK;
+    if (n == 0 && !c->comm) return LV_OK;
+    // On strips the vectors are label-ordered over the local generator list: rows [0, n_own) are this rank's unknowns, the
+    // ghost entries behind them are refreshed from their owners before every sweep that reads neighbours; dot products
+    // run over the owned rows and are summed over the ranks by lv_minres_apply.
     double *b = c->d_vec[6], *sol = c->d_vec[5];
     double2 *tmp = (double2 *)c->st_tmp;
-    k_mp_apply<<<GRID(S.n)>>>(S, S.dv, b); // refresh!: b_i = -sum lrr (dot(dv_i - dv_j, m-z) - 0.5 dot(dv_i + dv_j, x-y))
-    c->launches++;
+    LV_TRY(st_halo(c, {F_PHASE, F_DV}));
+    if (n > 0) { k_mp_apply<<<GRID(S.n)>>>(S, S.dv, b); c->launches++; } // refresh!: b_i = -sum lrr (dot(dv_i - dv_j, m-z) - 0.5 dot(dv_i + dv_j, x-y))
     auto apply = [&](const double *in, double *out) -> int {
-        k_mp_tmp<<<GRID(S.n)>>>(S, in, tmp);
-        k_mp_apply<<<GRID(S.n)>>>(S, tmp, out);
+        if (st_strip(c)) LV_TRY(lv_strip_halo_state(c, (double *)in, 1));
+        if (n > 0) k_mp_tmp<<<GRID(S.n)>>>(S, in, tmp);
+        if (st_strip(c)) LV_TRY(lv_strip_halo_state(c, (double *)tmp, 2));
+        if (n > 0) k_mp_apply<<<GRID(S.n)>>>(S, tmp, out);
         c->launches += 2;
         return LV_OK;
     };
@@ -684,8 +758,11 @@ int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, doub
     LV_TRY(lv_minres_apply(c, n, apply, b, sol, rtol, atol, itmax, &it, &ok));
     if (iters) *iters = it;
     if (solved) *solved = ok;
-    k_mp_update<<<GRID(S.n)>>>(S, sol, quality_threshold, tmp);
-    LV_CUDA(c, cudaMemcpyAsync(S.dv, tmp, sizeof(double2) * (size_t)S.n, cudaMemcpyDeviceToDevice, c->stream));
+    if (st_strip(c)) LV_TRY(lv_strip_halo_state(c, sol, 1));
+    if (n > 0) {
+        k_mp_update<<<GRID(S.n)>>>(S, sol, quality_threshold, tmp);
+        LV_CUDA(c, cudaMemcpyAsync(S.dv, tmp, sizeof(double2) * (size_t)S.n, cudaMemcpyDeviceToDevice, c->stream));
+    }
     c->launches++;
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
@@ -703,9 +780,12 @@ int32_t lv_step_multiphase_apply(LvHandle c, const double *x, double *y, double 
     const size_t bytes = sizeof(double) * (size_t)S.n;
     double *dx = c->d_vec[5], *dy = c->d_vec[6];
     double2 *tmp = (double2 *)c->st_tmp;
+    LV_TRY(st_halo(c, {F_PHASE, F_DV}));
     if (x && y) {
         LV_CUDA(c, cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (st_strip(c)) LV_TRY(lv_strip_halo_state(c, dx, 1));
         k_mp_tmp<<<GRID(S.n)>>>(S, dx, tmp);
+        if (st_strip(c)) LV_TRY(lv_strip_halo_state(c, (double *)tmp, 2));
         k_mp_apply<<<GRID(S.n)>>>(S, tmp, dy);
         c->launches += 2;
         LV_CUDA(c, cudaMemcpyAsync(y, dy, bytes, cudaMemcpyDeviceToHost, c->stream));

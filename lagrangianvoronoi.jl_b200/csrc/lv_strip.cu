@@ -29,15 +29,22 @@ struct LvGhost { double x, y; long long key; }; // 24 B
 struct LvStripHdr {
     int gseq;               // remeshes whose ghost outbox + counts are published
     int hseq;               // halo exchanges whose outbox is published
-    int pad0[2];
+    int mseq;               // migrations whose outbox + counts are published
+    int pad0;
     int gcount[2][LV_SP_MAXP]; // [parity][peer index]: ghosts I send to that peer
-    int pad1[52];
+    int mcount[2][LV_SP_MAXP]; // [parity][peer index]: generators that migrate to that peer
+    int pad1[44];
 };
 static_assert(sizeof(LvStripHdr) == 256, "header is 256 bytes");
 
 static inline size_t sp_off_hbox(int64_t capg) { return sizeof(LvStripHdr) + (size_t)2 * LV_SP_MAXP * (size_t)capg * sizeof(LvGhost); }
-static inline size_t sp_hbox_half(int64_t capg) { return (size_t)LV_SP_MAXP * (size_t)capg * 2 * sizeof(double); } // ncomp <= 2
-static inline size_t sp_area_bytes(int64_t capg) { return sp_off_hbox(capg) + 2 * sp_hbox_half(capg); }
+#define SP_HB_NC 4   // components per halo value the outbox has room for (D of find_D! has four)
+#define SP_MIG_REC 24 // doubles per migrating generator: x (2), global label (1), every resident field (21)
+static inline size_t sp_hbox_half(int64_t capg) { return (size_t)LV_SP_MAXP * (size_t)capg * SP_HB_NC * sizeof(double); }
+static inline int64_t sp_capm(int64_t capg) { return capg / 8 + 1024; } // migrants per peer and step: a small fraction of the ghost band
+static inline size_t sp_off_mbox(int64_t capg) { return sp_off_hbox(capg) + 2 * sp_hbox_half(capg); }
+static inline size_t sp_mbox_half(int64_t capg) { return (size_t)LV_SP_MAXP * (size_t)sp_capm(capg) * SP_MIG_REC * sizeof(double); }
+static inline size_t sp_area_bytes(int64_t capg) { return sp_off_mbox(capg) + 2 * sp_mbox_half(capg); }
 
 #define sp_ld_acquire lv_ld_acquire_sys
 #define sp_st_release lv_st_release_sys
@@ -47,6 +54,7 @@ struct SpPeers { // by value to kernels
     int idx_there[LV_SP_MAXP];
     int lo[LV_SP_MAXP], hi[LV_SP_MAXP];
     int nsend[LV_SP_MAXP], nrecv[LV_SP_MAXP], soff[LV_SP_MAXP], roff[LV_SP_MAXP];
+    int rank[LV_SP_MAXP];
     int np;
 };
 static SpPeers sp_peers(const LvContext *c) {
@@ -54,7 +62,7 @@ static SpPeers sp_peers(const LvContext *c) {
     P.np = c->strip.npeers;
     for (int p = 0; p < P.np; p++) {
         const auto &q = c->strip.peer[p];
-        P.area[p] = q.area; P.idx_there[p] = q.idx_there; P.lo[p] = q.lo; P.hi[p] = q.hi;
+        P.area[p] = q.area; P.idx_there[p] = q.idx_there; P.lo[p] = q.lo; P.hi[p] = q.hi; P.rank[p] = q.rank;
         P.nsend[p] = (int)q.nsend; P.nrecv[p] = (int)q.nrecv; P.soff[p] = (int)q.soff; P.roff[p] = (int)q.roff;
     }
     return P;
@@ -98,17 +106,18 @@ __global__ void __launch_bounds__(256) k_strip_select(SpPeers P, double oy, doub
 }
 
 // ---- 2. counts: publish mine, read the neighbours' ----------------------------------------------------------------
-__global__ void k_strip_counts(LvStripHdr *me, SpPeers P, int par, int seq, const int *__restrict__ cnt, int *dead, int *host_out) {
+// `mig` selects the migration words (mseq / mcount) instead of the ghost words (gseq / gcount)
+__global__ void k_strip_counts(LvStripHdr *me, SpPeers P, int par, int seq, int mig, const int *__restrict__ cnt, int *dead, int *host_out) {
     const int t = threadIdx.x;
-    if (t < P.np) me->gcount[par][t] = cnt[t];
-    __threadfence_system(); // the outbox written by k_strip_select and the counts, before the sequence word
+    if (t < P.np) (mig ? me->mcount : me->gcount)[par][t] = cnt[t];
+    __threadfence_system(); // the outbox written before and the counts, before the sequence word
     __syncwarp();           // every lane's fence has completed before lane 0 publishes
-    if (t == 0) sp_st_release(&me->gseq, seq);
+    if (t == 0) sp_st_release(mig ? &me->mseq : &me->gseq, seq);
     if (t < P.np) {
         const LvStripHdr *ph = (const LvStripHdr *)P.area[t];
-        const bool ok = lv_wait_ge(&ph->gseq, seq, dead);
+        const bool ok = lv_wait_ge(mig ? &ph->mseq : &ph->gseq, seq, dead);
         host_out[t] = cnt[t];
-        host_out[4 + t] = ok ? __ldcv(&ph->gcount[par][P.idx_there[t]]) : -1;
+        host_out[4 + t] = ok ? __ldcv(&(mig ? ph->mcount : ph->gcount)[par][P.idx_there[t]]) : -1;
     }
     __syncwarp();
     __threadfence_system();
@@ -240,6 +249,183 @@ int lv_strip_pack_args(LvContext *c, LvHaloPack *out) {
     return LV_OK;
 }
 
+// ---- halo of a LABEL-ordered field (device-resident state of lv_step.cu): owned generators sit at [0, n_own), the ghosts
+// received from peer p at n_own + roff[p] + i in the order of that peer's send list -> no slot lists are needed
+__global__ void __launch_bounds__(256) k_hs_pack(SpPeers P, int capg, int nc, const int *__restrict__ sel, const double *__restrict__ field,
+                                                 double *__restrict__ outbox) {
+    const int p = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nsend[p]) return;
+    const int src = sel[(size_t)p * capg + i];
+    for (int k = 0; k < nc; k++) outbox[((size_t)p * capg + i) * nc + k] = field[(size_t)nc * src + k];
+}
+__global__ void __launch_bounds__(256) k_hs_pull(SpPeers P, int capg, int nc, size_t hbox_off, int seq, int n_own, double *__restrict__ field, int *dead) {
+    const int p = blockIdx.y;
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = lv_wait_ge(&((const LvStripHdr *)P.area[p])->hseq, seq, dead) ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nrecv[p]) return;
+    const double *src = (const double *)(P.area[p] + hbox_off) + ((size_t)P.idx_there[p] * capg + i) * nc;
+    double *dst = field + ((size_t)n_own + P.roff[p] + i) * nc;
+    for (int k = 0; k < nc; k++) dst[k] = __ldcv(src + k);
+}
+int lv_strip_halo_state(LvContext *c, double *field, int nc) {
+    auto &S = c->strip;
+    if (!lv_strip_peer_mode(c) || S.npeers == 0) return LV_OK;
+    if (nc < 1 || nc > SP_HB_NC) return lv_set_error(c, LV_EINVAL, "halo of %d components", nc);
+    const int seq = ++S.hseq;
+    const size_t off = sp_off_hbox(S.capg) + (size_t)(seq & 1) * sp_hbox_half(S.capg);
+    const SpPeers P = sp_peers(c);
+    dim3 gs(sp_grid(sp_max_send(c)), S.npeers), gr(sp_grid(sp_max_recv(c)), S.npeers);
+    k_hs_pack<<<gs, 256, 0, c->stream>>>(P, (int)S.capg, nc, S.sel, field, (double *)(S.area + off));
+    k_hb_signal<<<1, 1, 0, c->stream>>>((LvStripHdr *)S.area, seq);
+    k_hs_pull<<<gr, 256, 0, c->stream>>>(P, (int)S.capg, nc, off, seq, (int)S.n_own, field, c->d_tickets + 7);
+    c->launches += 3;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// ---- migration: generators that left the strip take their state to the new owner ---------------------------------------
+struct SpRows { int R[LV_MB_MAX_RANKS + 1]; int world, rank; double oy, h; }; // bucket rows [R[r], R[r+1]) belong to rank r
+struct SpFields { double *ptr[LV_STATE_MAX]; int nc[LV_STATE_MAX]; int nf; };
+
+__global__ void __launch_bounds__(256) k_mig_select(SpPeers P, SpRows W, int n_own, const double2 *__restrict__ xy, int capm,
+                                                    int *__restrict__ cnt, int *__restrict__ mig, unsigned char *__restrict__ leave, int *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const double q = floor((xy[i].y - W.oy) / W.h); // findkey  neighborlist.jl:47-52
+    int owner = 0;
+    while (owner + 1 < W.world && q >= (double)W.R[owner + 1]) owner++;
+    if (owner == W.rank || !(q == q)) { leave[i] = 0; return; }
+    int p = -1;
+    for (int k = 0; k < P.np; k++)
+        if (P.rank[k] == owner) p = k;
+    if (p < 0) { atomicOr(&flags[LVF_OVERFLOW], 32); leave[i] = 0; return; } // jumped over a whole strip in one step
+    leave[i] = 1;
+    const int pos = atomicAdd(&cnt[p], 1);
+    if (pos < capm) mig[(size_t)p * capm + pos] = i;
+}
+__global__ void __launch_bounds__(128) k_mig_pack(SpPeers P, int capm, SpFields F, const double2 *__restrict__ xy, const int *__restrict__ key,
+                                                  const int *__restrict__ mig, const int *__restrict__ cnt, double *__restrict__ outbox) {
+    const int p = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = cnt[p] < capm ? cnt[p] : capm;
+    if (k >= m) return;
+    const int i = mig[(size_t)p * capm + k];
+    double *rec = outbox + ((size_t)p * capm + k) * SP_MIG_REC;
+    rec[0] = xy[i].x; rec[1] = xy[i].y; rec[2] = (double)key[i];
+    int o = 3;
+    for (int f = 0; f < F.nf; f++)
+        for (int cpt = 0; cpt < F.nc[f]; cpt++) rec[o++] = F.ptr[f][(size_t)F.nc[f] * i + cpt];
+}
+// holes = leavers below n_stay, tails = stayers at or above n_stay; there are equally many of both
+__global__ void __launch_bounds__(256) k_mig_lists(int n_stay, int n_own, const unsigned char *__restrict__ leave, int *__restrict__ holes,
+                                                   int *__restrict__ tails, int *__restrict__ cnt2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    if (i < n_stay && leave[i]) holes[atomicAdd(&cnt2[0], 1)] = i;
+    if (i >= n_stay && !leave[i]) tails[atomicAdd(&cnt2[1], 1)] = i;
+}
+__global__ void __launch_bounds__(128) k_mig_fill_bounded(int nmax, const int *__restrict__ cnt2, const int *__restrict__ holes, const int *__restrict__ tails,
+                                                          SpFields F, double2 *__restrict__ xy, int *__restrict__ key) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nmax || j >= cnt2[0]) return; // cnt2[0] = number of holes (= cnt2[1], the number of tails)
+    const int dst = holes[j], src = tails[j];
+    xy[dst] = xy[src];
+    key[dst] = key[src];
+    for (int f = 0; f < F.nf; f++)
+        for (int cpt = 0; cpt < F.nc[f]; cpt++) F.ptr[f][(size_t)F.nc[f] * dst + cpt] = F.ptr[f][(size_t)F.nc[f] * src + cpt];
+}
+struct SpMigIn { int n[LV_SP_MAXP], off[LV_SP_MAXP]; };
+__global__ void __launch_bounds__(128) k_mig_pull(SpPeers P, SpMigIn in, int par, int capm, size_t mbox_off, size_t mbox_half, int n_stay, SpFields F,
+                                                  double2 *__restrict__ xy, int *__restrict__ key) {
+    const int p = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= in.n[p]) return;
+    const double *rec = (const double *)(P.area[p] + mbox_off + (size_t)par * mbox_half) + ((size_t)P.idx_there[p] * capm + k) * SP_MIG_REC;
+    const int dst = n_stay + in.off[p] + k;
+    xy[dst] = make_double2(__ldcv(rec), __ldcv(rec + 1));
+    key[dst] = (int)__ldcv(rec + 2);
+    int o = 3;
+    for (int f = 0; f < F.nf; f++)
+        for (int cpt = 0; cpt < F.nc[f]; cpt++) F.ptr[f][(size_t)F.nc[f] * dst + cpt] = __ldcv(rec + o++);
+}
+
+// After positions moved: every owned generator whose bucket row now belongs to another rank travels there with all its
+// resident fields (fields: label-ordered device arrays with `nc` components each); the owned set stays contiguous at the
+// front of the local arrays (order is irrelevant: buckets are ordered by global label).  Collective over the strip
+// neighbours; one host synchronisation.  The mesh is invalid afterwards (lv_strip_remesh follows).
+int lv_strip_migrate(LvContext *c, int nf, double *const *fields, const int *ncomp) {
+    auto &S = c->strip;
+    if (!S.on) return lv_set_error(c, LV_EINVAL, "lv_strip_migrate: not in strip mode");
+    if (S.npeers == 0) return LV_OK;
+    if (!S.mapped) return lv_set_error(c, LV_EINVAL, "lv_strip_migrate: peers not mapped");
+    if (S.world_rows.empty()) return lv_set_error(c, LV_EINVAL, "lv_strip_migrate: strip rows unknown (lv_strip_set_rows)");
+    SpFields F{};
+    int rec = 3;
+    if (nf > LV_STATE_MAX) return lv_set_error(c, LV_EINVAL, "too many fields");
+    F.nf = nf;
+    for (int f = 0; f < nf; f++) { F.ptr[f] = fields[f]; F.nc[f] = ncomp[f]; rec += ncomp[f]; }
+    if (rec > SP_MIG_REC) return lv_set_error(c, LV_EINVAL, "migration record of %d doubles exceeds %d", rec, SP_MIG_REC);
+    cudaStream_t st = c->stream;
+    const int capm = (int)sp_capm(S.capg);
+    if (!S.mig) {
+        LV_CUDA(c, cudaMalloc((void **)&S.mig, sizeof(int) * (size_t)LV_SP_MAXP * capm));
+        LV_CUDA(c, cudaMalloc((void **)&S.holes, sizeof(int) * (size_t)LV_SP_MAXP * capm * 2));
+        LV_CUDA(c, cudaMalloc((void **)&S.leave, (size_t)S.cap_loc));
+    }
+    SpRows W{};
+    W.world = (int)S.world_rows.size() - 1; W.rank = c->rank; W.oy = c->gp.oy; W.h = c->gp.h;
+    for (size_t k = 0; k < S.world_rows.size(); k++) W.R[k] = S.world_rows[k];
+    const int seq = ++S.mseq, par = seq & 1;
+    SpPeers P = sp_peers(c);
+    double *outbox = (double *)(S.area + sp_off_mbox(S.capg) + (size_t)par * sp_mbox_half(S.capg));
+    LV_CUDA(c, cudaMemsetAsync(S.cnt, 0, sizeof(int) * 8, st));
+    LV_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, st));
+    const int n_own = (int)S.n_own;
+    if (n_own > 0) k_mig_select<<<sp_grid(n_own), 256, 0, st>>>(P, W, n_own, S.loc_xy, capm, S.cnt, S.mig, S.leave, c->d_flags);
+    {
+        dim3 g((capm + 127) / 128, S.npeers);
+        k_mig_pack<<<g, 128, 0, st>>>(P, capm, F, S.loc_xy, S.loc_key, S.mig, S.cnt, outbox);
+    }
+    k_strip_counts<<<1, 32, 0, st>>>((LvStripHdr *)S.area, P, par, seq, 1, S.cnt, c->d_tickets + 7, S.h_counts);
+    c->launches += 3;
+    LV_TRY(lv_publish_flags(c, nullptr)); // synchronises
+    if (c->h_flags[LVF_OVERFLOW] & 32) return lv_set_error(c, LV_EINVAL, "strip: a generator moved past a neighbouring strip in one step");
+    SpMigIn in{};
+    int out_total = 0, in_total = 0;
+    for (int p = 0; p < S.npeers; p++) {
+        const int ns = S.h_counts[p], nr = S.h_counts[4 + p];
+        if (nr < 0) return lv_set_error(c, LV_ECUDA, "strip: rank %d did not publish its migrants (peer timeout)", S.peer[p].rank);
+        if (ns > capm || nr > capm) return lv_set_error(c, LV_ECAPACITY, "strip: %d / %d migrants exceed the capacity %d", ns, nr, capm);
+        in.n[p] = nr; in.off[p] = in_total;
+        out_total += ns; in_total += nr;
+    }
+    const int n_stay = n_own - out_total;
+    if ((int64_t)n_stay + in_total > S.cap_loc) return lv_set_error(c, LV_ECAPACITY, "strip: owned generators exceed the local capacity after migration");
+    if (out_total > 0) {
+        LV_CUDA(c, cudaMemsetAsync(S.cnt, 0, sizeof(int) * 8, st));
+        k_mig_lists<<<sp_grid(n_own), 256, 0, st>>>(n_stay, n_own, S.leave, S.holes, S.holes + (size_t)LV_SP_MAXP * capm, S.cnt);
+        // #holes = #leavers below n_stay <= out_total; the lists are complete when the kernel is: launch with the upper bound
+        k_mig_fill_bounded<<<(out_total + 127) / 128, 128, 0, st>>>(out_total, S.cnt, S.holes, S.holes + (size_t)LV_SP_MAXP * capm, F, S.loc_xy, S.loc_key);
+        c->launches += 2;
+    }
+    if (in_total > 0) {
+        int mx = 0;
+        for (int p = 0; p < S.npeers; p++) mx = in.n[p] > mx ? in.n[p] : mx;
+        dim3 g((mx + 127) / 128, S.npeers);
+        k_mig_pull<<<g, 128, 0, st>>>(P, in, par, capm, sp_off_mbox(S.capg), sp_mbox_half(S.capg), n_stay, F, S.loc_xy, S.loc_key);
+        c->launches++;
+    }
+    LV_CUDA(c, cudaGetLastError());
+    S.n_own = n_stay + in_total;
+    S.last_mig_out = out_total; S.last_mig_in = in_total;
+    c->mesh_valid = false;
+    return LV_OK;
+}
+
 void lv_strip_unmap(LvContext *c) {
     auto &S = c->strip;
     for (int p = 0; p < S.npeers; p++)
@@ -250,7 +436,7 @@ void lv_strip_destroy(LvContext *c) {
     auto &S = c->strip;
     lv_strip_unmap(c);
     cudaFree(S.area); cudaFree(S.loc_xy); cudaFree(S.loc_key); cudaFree(S.sel); cudaFree(S.cnt);
-    cudaFree(S.send_pos0); cudaFree(S.send_pos1);
+    cudaFree(S.send_pos0); cudaFree(S.send_pos1); cudaFree(S.mig); cudaFree(S.holes); cudaFree(S.leave);
     if (S.h_counts) cudaFreeHost(S.h_counts);
     S = LvContext::Strip();
 }
@@ -316,6 +502,13 @@ int32_t lv_strip_map(LvHandle c, const uint8_t *handles /* npeers x 64 */) {
     return LV_OK;
 }
 
+// bucket-row ownership of all ranks, R[0..world]: rank r owns rows [R[r], R[r+1]) -- what migration needs to find new owners
+int32_t lv_strip_set_rows(LvHandle c, int32_t world, const int32_t *R) {
+    if (!c || !c->strip.on || world < 1 || world > LV_MB_MAX_RANKS || !R) return lv_set_error(c, LV_EINVAL, "lv_strip_set_rows: bad arguments");
+    c->strip.world_rows.assign(R, R + world + 1);
+    return LV_OK;
+}
+
 // Owned generators of this rank: positions (host or device memory) and their global labels (device int32, may be NULL
 // to keep the previous ones), copied to the front of the library's local arrays.
 int32_t lv_strip_set_owned(LvHandle c, int64_t n_own, const double *xy, int32_t xy_on_host, const int32_t *key_dev) {
@@ -349,7 +542,7 @@ int32_t lv_strip_remesh(LvHandle c, int64_t *counts_out) {
         LvGhost *outbox = (LvGhost *)(S.area + sizeof(LvStripHdr)) + (size_t)par * LV_SP_MAXP * (size_t)S.capg;
         k_strip_select<<<sp_grid(S.n_own), 256, 0, st>>>(P, c->gp.oy, c->gp.h, c->gp.yperiod, c->gp.yper, (int)S.n_own, S.loc_xy, S.loc_key,
                                                         (int)S.capg, S.cnt, S.sel, outbox);
-        k_strip_counts<<<1, 32, 0, st>>>(me, P, par, seq, S.cnt, c->d_tickets + 7, S.h_counts);
+        k_strip_counts<<<1, 32, 0, st>>>(me, P, par, seq, 0, S.cnt, c->d_tickets + 7, S.h_counts);
         c->launches += 2;
         LV_CUDA(c, cudaGetLastError());
         LV_CUDA(c, cudaStreamSynchronize(st));

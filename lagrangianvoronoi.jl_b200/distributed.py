@@ -390,6 +390,7 @@ class StripGrid:
             self._agree_on_peer_memory(ok)
         self._strip_ready = bool(self.use_peer_memory or self.world == 1)
         self._capg, self._cap_loc = capg, cap_loc
+        check(L.lv_strip_set_rows(g._h, self.world, (C.c_int32 * (self.world + 1))(*[int(v) for v in plan.R])), g._h)
 
     def _agree_on_peer_memory(self, ok: bool) -> None:
         """CUDA IPC mapping can be refused (container policy).  All ranks switch to the NCCL path together."""
@@ -531,6 +532,55 @@ class StripGrid:
         check(L.lv_halo_plan(g._h, npeer, pr, sc, ptr(s_all) if s_all.numel() else None, rc,
                              ptr(r_all) if r_all.numel() else None), g._h)
         self.halo_counts = {q: (int(send_slots[q].numel()), int(recv_slots[q].numel())) for q in peers}
+
+    # -- device-resident stepping on strips (stepping.py functions take ``self.grid``) ---------------------------------
+    def state_attach(self) -> None:
+        """Make the owned generators the resident state of the lv_step_* sweeps (after ``remesh()``).  Fields are zero until
+        ``state_set``.  Needs the library strip path (peer memory, or one rank)."""
+        if not self._strip_ready:
+            raise RuntimeError("device-resident stepping on strips needs the peer-memory strip exchange")
+        check(self._L.lv_state_attach_strip(self.grid._h), self.grid._h)
+        self.grid._resident = True
+
+    def n_owned(self) -> int:
+        p, n = C.c_void_p(), C.c_int64()
+        check(self._L.lv_device_array(self.grid._h, 8, C.byref(p), C.byref(n)), self.grid._h)
+        return int(n.value)
+
+    def owned_labels(self) -> torch.Tensor:
+        """Global labels of the owned generators in their current local order (it changes when generators migrate)."""
+        return self._dev_tensor(8, "<i4", torch.int32).to(torch.int64)
+
+    def state_set(self, name: str, arr) -> None:
+        """One field for the owned generators, in the order of ``owned_labels()``."""
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        check(self._L.lv_state_set(self.grid._h, name.encode(), ptr(a), self.n_owned()), self.grid._h)
+
+    def state_get(self, name: str) -> np.ndarray:
+        nc = {"x": 2, "v": 2, "dv": 2, "momentum": 2, "D": 4}.get(name, 1)
+        n = self.n_owned()
+        pp, cnt = C.c_void_p(), C.c_int64()
+        check(self._L.lv_state_ptr(self.grid._h, name.encode(), C.byref(pp), C.byref(cnt)), self.grid._h)
+        if n == 0:
+            return np.zeros((0, nc) if nc > 1 else 0)
+        t = torch.as_tensor(_DevArray(pp.value, n * nc, "<f8"), device=self.dev)
+        torch.cuda.current_stream(self.dev).synchronize()
+        a = t.cpu().numpy()
+        return a.reshape(n, nc) if nc > 1 else a
+
+    def refresh(self) -> None:
+        """After a sweep that moved generators (move / relaxation_step / lloyd): re-read the counts and the views."""
+        self._n_own = self.n_owned()
+        p, n = C.c_void_p(), C.c_int64()
+        check(self._L.lv_device_array(self.grid._h, 7, C.byref(p), C.byref(n)), self.grid._h)
+        self.n_loc = int(n.value)
+        self.grid._dev_n = self.n_loc
+        self.xy_loc = self._dev_tensor(6, "<f8", torch.float64, ncomp=2)
+        self.key_loc = self._dev_tensor(7, "<i4", torch.int32)
+        self.lab_loc = self.key_loc.to(torch.int64)
+        self.mask_loc = (torch.arange(self.n_loc, device=self.dev) < self._n_own).to(torch.uint8)
+        self.xy_own, self.lab_own = self.xy_loc[: self._n_own], self.lab_loc[: self._n_own]
+        self._owned_dirty = False
 
     # -- results --------------------------------------------------------------------------------------
     def owned_index(self) -> torch.Tensor:

@@ -114,6 +114,96 @@ def check_case(kind, n_side, xper, yper, rank, world, dev, peer=True, krylov="cg
     return used_peer
 
 
+def check_stepping(kind, n_side, xper, yper, rank, world, dev, two_phase=False, nsteps=4):
+    """Device-resident stepping on strips vs one GPU: the canonical step! (examples/gresho.jl:100-114; with gravity and the
+    multiphase projector of examples/rayleightaylor.jl:90-102 when two_phase) for a few steps.  Generators cross the strip
+    boundaries and migrate with their fields; per-generator results are compared through the global labels."""
+    S = lv.stepping
+    xy, dr, bmin, bmax = make_points(kind, n_side, 5)
+    n = len(xy)
+    dt = 0.2 * dr
+    rng = np.random.default_rng(2)
+    v = 0.6 * lv.synthetic.taylor_green_fields(xy)[0] + 0.05 * rng.standard_normal((n, 2))
+    if two_phase:
+        up = xy[:, 1] > 0.5 * (bmin[1] + bmax[1]) + 0.05 * np.cos(2 * np.pi * xy[:, 0])
+    else:
+        up = np.zeros(n, dtype=bool)
+    rho = np.where(up, 1.8, 1.0)
+    fields = {"v": v, "rho": rho, "P": 10.0 - 0.3 * rho * xy[:, 1], "mu": np.full(n, 2e-3), "phase": np.where(up, 0.0, 1.0),
+              "quality": np.ones(n), "dv": np.zeros((n, 2)), "c2": np.full(n, 14.0)}
+
+    def init_fields(area, sel):
+        f = {k: a[sel].copy() for k, a in fields.items()}
+        f["mass"] = f["rho"] * area
+        f["e"] = 0.5 * (f["v"] ** 2).sum(1) + f["P"] / (f["rho"] * 0.4)
+        return f
+
+    def step(grid, solver):
+        S.move(grid, dt)
+        if two_phase:
+            S.gravity_step(grid, (0.0, -1.0), dt)
+        S.ideal_eos(grid, 1.4, 0.0)
+        S.find_pressure_resident(solver, dt)
+        S.pressure_step(grid, dt); S.find_D(grid); S.viscous_step(grid, dt, True); S.find_dv(grid, dt)
+        if two_phase:
+            S.multiphase_projection(grid, rtol=1e-11, atol=1e-11, itmax=3000)
+        S.relaxation_step(grid, dt)
+
+    # ---- one GPU
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper, device=dev.index)
+    g.set_points(xy)
+    lv.remesh(g, edges=False)
+    for k, a in init_fields(lv.area(g), slice(None)).items():
+        getattr(g, k)[...] = a
+    S.to_device(g)
+    sol = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=50000)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(nsteps):
+            step(g, sol)
+    S.from_device(g)
+    # ---- strips
+    sg = StripGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper, device=dev.index)
+    X = torch.from_numpy(xy).to(dev)
+    lab = torch.arange(1, n + 1, dtype=torch.int64, device=dev)
+    mine = sg.plan.owner(X[:, 1]) == rank
+    sg.set_owned(X[mine], lab[mine])
+    sg.remesh()
+    sg.state_attach()
+    own0 = sg.owned_labels().cpu().numpy() - 1
+    _, _, area_loc, _ = sg.mesh_download(edges=False)
+    for k, a in init_fields(area_loc[: len(own0)], own0).items():
+        sg.state_set(k, a)
+    lv._capi.check(sg._L.lv_state_remesh(sg.grid._h), sg.grid._h)     # migrate (nobody moves yet) + strip remesh on the resident state
+    sg.refresh()
+    ssol = StripSolver(sg, rtol=1e-12, atol=0.0, itmax=50000)
+    moved = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(nsteps):
+            before = set(sg.owned_labels().cpu().numpy().tolist())
+            step(sg.grid, ssol)
+            sg.refresh()
+            moved += len(set(sg.owned_labels().cpu().numpy().tolist()) - before)
+    own = sg.owned_labels().cpu().numpy() - 1
+    cnt = torch.tensor([len(own), moved], device=dev)
+    dist.all_reduce(cnt)
+    assert int(cnt[0]) == n, (int(cnt[0]), n)                          # every generator still has exactly one owner
+    worst = 0.0
+    for nm in ("x", "v", "e", "rho", "P", "mass"):
+        a, b = sg.state_get(nm), getattr(g, nm)[own]
+        err = np.abs(a - b).max() / np.abs(getattr(g, nm)).max()
+        worst = max(worst, err)
+        assert err <= (1e-5 if two_phase else 1e-8), (nm, err)   # the projector is singular: its MINRES stops a few digits short
+    assert mesh_witness(sg.grid, sg.key_loc, dev, world) is not None
+    if rank == 0:
+        print(f"stepping {kind} n={n} per=({xper},{yper}) world={world} two_phase={two_phase}: {nsteps} steps, "
+              f"{int(cnt[1])} generators changed strips, worst field error {worst:.2e}", flush=True)
+    del ssol
+    sg.close()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -124,6 +214,9 @@ def main():
     check_case("rect2x1", 128, True, False, rank, world, dev)
     check_case("jitter", 128, True, True, rank, world, dev, krylov="minres")
     check_case("jitter", 128, True, True, rank, world, dev, peer=False)       # NCCL fallback path
+    if peer_ok:
+        check_stepping("jitter", 96, True, True, rank, world, dev)
+        check_stepping("poisson", 80, True, False, rank, world, dev, two_phase=True)
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU OK (peer memory {'used' if peer_ok else 'UNAVAILABLE: NCCL fallback everywhere'})", flush=True)
