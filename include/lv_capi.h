@@ -49,7 +49,7 @@ enum {
     LV_ECAPACITY = 5   /* caller buffer too small (nnz > cap) or polygon exceeded the internal limit */
 };
 
-enum { LV_SOLVER_CG = 0, LV_SOLVER_MINRES = 1 };
+enum { LV_SOLVER_CG = 0, LV_SOLVER_MINRES = 1, LV_SOLVER_PCG = 2 /* CG with the Jacobi preconditioner 1/A_ii; same stopping rule on ||r||_2 */ };
 
 /* profiling slots for lv_prof_get */
 enum {

@@ -33,7 +33,7 @@ struct LvGridDesc            # typedef struct LvGridDesc
     bmin::NTuple{2,Cdouble}; bmax::NTuple{2,Cdouble}
 end
 const LV_OK, LV_EINVAL, LV_EDESTROYED, LV_ENAN, LV_ECUDA, LV_ECAPACITY = Int32.(0:5)
-const LV_SOLVER_CG, LV_SOLVER_MINRES = Int32(0), Int32(1)
+const LV_SOLVER_CG, LV_SOLVER_MINRES, LV_SOLVER_PCG = Int32(0), Int32(1), Int32(2)
 
 # `Edge` (src/geometry.jl:82-87) is isbits {SVector{2,Float64}, SVector{2,Float64}, Int64} = 40 bytes,
 # exactly `LvEdge`; a Vector{Edge} can be handed to the library as LvEdge*.

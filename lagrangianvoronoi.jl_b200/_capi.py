@@ -14,7 +14,15 @@ EDGE_DTYPE = np.dtype([("v1", "<f8", (2,)), ("v2", "<f8", (2,)), ("label", "<i8"
 assert EDGE_DTYPE.itemsize == 40
 
 LV_OK, LV_EINVAL, LV_EDESTROYED, LV_ENAN, LV_ECUDA, LV_ECAPACITY = range(6)
-LV_SOLVER_CG, LV_SOLVER_MINRES = 0, 1
+LV_SOLVER_CG, LV_SOLVER_MINRES, LV_SOLVER_PCG = 0, 1, 2
+
+
+def solver_kind(name: str) -> int:
+    """"cg" (north star), "minres" (the reference's Krylov method) or "pcg" (CG with the Jacobi preconditioner 1/A_ii)."""
+    try:
+        return {"cg": LV_SOLVER_CG, "minres": LV_SOLVER_MINRES, "pcg": LV_SOLVER_PCG}[name]
+    except KeyError:
+        raise ValueError(f"unknown Krylov method {name!r}") from None
 PROF_SLOTS = {"cells": 0, "clip": 1, "assemble": 2, "matvec": 3, "vecops": 4}
 
 # every symbol include/lv_capi.h declares; tests check the library exports all of them

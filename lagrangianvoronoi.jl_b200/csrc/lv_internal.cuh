@@ -101,6 +101,7 @@ struct LvContext {
     double *d_mass = nullptr, *d_rho = nullptr, *d_c2 = nullptr, *d_P = nullptr;
     double2 *d_v = nullptr, *d_GP = nullptr;
     double *d_diag = nullptr, *d_w = nullptr; // operator: diagonal [nslot], weights [nnz]
+    double *d_dinv = nullptr;                 // [nslot] 1/A_ii: Jacobi preconditioner of LV_SOLVER_PCG
     double *d_lrr = nullptr;                  // [nnz] lr_ratio of the edge (polygon.jl:228)
     double2 *d_mx = nullptr, *d_mz = nullptr; // [nnz] m - p.x and m - z (pressure.jl:178,198)
     double *d_bvel = nullptr;                 // [nslot] P-independent part of the right-hand side
@@ -235,7 +236,7 @@ int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap,
 int lv_pr_ensure(LvContext *c);
 int lv_pr_assemble(LvContext *c, double dt);
 int lv_pr_matvec(LvContext *c, const double *x, double *y); // slot-order device vectors
-int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done);
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done, bool pcg);
 int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres, bool pre_init);
 int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double atol, int itmax, int solver,
                         const double *vbc_wall, int32_t *iters_out, double *relres_out);

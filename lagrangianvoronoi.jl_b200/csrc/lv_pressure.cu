@@ -11,7 +11,7 @@
 #define PR_BLOCK 256
 
 // scalars kept on the device between kernels (doubles in c->d_red[0..15])
-enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_DEAD = 13 /* a peer wait timed out */, SC_SOLVED = 12 /* MINRES: stats.solved (tolerance met; not the ill-conditioned / NaN exits) */,
+enum { SC_RR = 0, SC_ALPHA = 1, SC_BETA = 2, SC_TOL = 3, SC_PAP = 4, SC_RR0 = 5, SC_BNORM2 = 6, SC_RES2 = 7, SC_ITER = 8, SC_CONV = 9, SC_TMP0 = 10, SC_TMP1 = 11, SC_DEAD = 13 /* a peer wait timed out */, SC_RZ = 14 /* r.z of the preconditioned iteration (= r.r without preconditioner) */, SC_SOLVED = 12 /* MINRES: stats.solved (tolerance met; not the ill-conditioned / NaN exits) */,
        // MINRES (Paige-Saunders, in the formulation of Krylov.jl 0.9.8 minres!) scalar state
        MR_BETA = 16, MR_OLDB = 17, MR_DBAR = 18, MR_EPS = 19, MR_CS = 20, MR_SN = 21, MR_PHIBAR = 22, MR_GAMMA = 23, MR_PHI = 24,
        MR_DELTA = 25, MR_ANORM2 = 26, MR_GMAX = 27, MR_GMIN = 28, MR_XENORM2 = 29, MR_ROOT = 30, MR_BETA1 = 31, MR_ERRV = 32 /* ..36 */,
@@ -67,7 +67,7 @@ int lv_pr_ensure(LvContext *c) {
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     const int64_t need = c->cap_slot;
     if (c->pr_cap < need || !c->d_mass) {
-        double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
+        double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_dinv, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
                           &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
         for (double **p : one) {
             int64_t cap = *p ? c->pr_cap : 0;
@@ -108,12 +108,14 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
                                                        const double2 *__restrict__ v2, const double *__restrict__ mass,
                                                        const double *__restrict__ rho, const double *__restrict__ c2,
                                                        double *__restrict__ diag, double *__restrict__ w, double *__restrict__ lrr_out,
-                                                       double2 *__restrict__ mx_out, double2 *__restrict__ mz_out) {
+                                                       double2 *__restrict__ mx_out, double2 *__restrict__ mz_out, double *__restrict__ dinv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslot) return;
-    if (!own[i]) { diag[i] = 0.0; return; }
+    if (!own[i]) { diag[i] = 0.0; dinv[i] = 0.0; return; }
     const double ri = rho[i];
-    diag[i] = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
+    const double dg = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
+    diag[i] = dg;
+    double aii = dg; // A_ii = diagonal + sum of the row's weights: the Jacobi preconditioner of LV_SOLVER_PCG
     const double2 x = ent_xy[i];
     const int r0 = rowptr[i], r1 = r0 + rdeg[i];
     for (int k = r0; k < r1; k++) {
@@ -126,10 +128,13 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
         const double ex = a.x - b.x, ey = a.y - b.y, dx = x.x - y.x, dy = x.y - y.y;
         const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy)); // lr_ratio  polygon.jl:228-232
         lrr_out[k] = lrr;
-        w[k] = lrr * (0.5 / ri + 0.5 / rho[j]);                             // pressure.jl:113
+        const double wk = lrr * (0.5 / ri + 0.5 / rho[j]);                  // pressure.jl:113
+        w[k] = wk;
+        aii += wk;
         const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);        // midpoint(p.x, y)  pressure.jl:196
         mz_out[k] = make_double2(mx - zx, my - zy);
     }
+    dinv[i] = aii > 0.0 ? 1.0 / aii : 0.0;
 }
 
 int lv_pr_assemble(LvContext *c, double dt) {
@@ -140,7 +145,7 @@ int lv_pr_assemble(LvContext *c, double dt) {
     if (ns > 0) {
         k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                              c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
-                                                                             c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz);
+                                                                             c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, c->d_dinv);
         c->launches++;
         LV_CUDA(c, cudaGetLastError());
     }
@@ -182,7 +187,7 @@ __device__ __noinline__ void cg_finish(int mode, int stage, int nblk, int nblk_m
     __shared__ double sh[2], m0[LV_MB_MAX_RANKS], m1[LV_MB_MAX_RANKS];
     if (stage == 3) {
         double a = 0.0, b2 = 0.0;
-        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3) b2 += __ldcg(&partial[nblk_max + k]); }
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3 || mode >= 8) b2 += __ldcg(&partial[nblk_max + k]); }
         const double t1 = block_sum(a, sm);
         const double t2 = block_sum(b2, sm);
         if (threadIdx.x == 0) { sh[0] = t1; sh[1] = t2; }
@@ -209,11 +214,11 @@ __device__ __noinline__ void cg_finish(int mode, int stage, int nblk, int nblk_m
         __syncthreads();
         stage = 2; // fall through to the update from scal[SC_TMP0..1]
     }
-    if (stage != 1 && mode != 0 && mode != 3 && mode != 4 && scal[SC_CONV] != 0.0) return;
+    if (stage != 1 && mode != 0 && mode != 3 && mode != 4 && mode != 8 && scal[SC_CONV] != 0.0) return;
     double s1, s2;
     if (stage != 2) {
         double a = 0.0, b2 = 0.0;
-        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3) b2 += __ldcg(&partial[nblk_max + k]); }
+        for (int k = threadIdx.x; k < nblk; k += blockDim.x) { a += __ldcg(&partial[k]); if (mode == 0 || mode == 3 || mode >= 8) b2 += __ldcg(&partial[nblk_max + k]); }
         s1 = block_sum(a, sm);
         s2 = block_sum(b2, sm);
         if (stage == 1) {
@@ -222,7 +227,22 @@ __device__ __noinline__ void cg_finish(int mode, int stage, int nblk, int nblk_m
         }
     } else { s1 = scal[SC_TMP0]; s2 = scal[SC_TMP1]; }
     if (threadIdx.x != 0) return;
-    if (mode == 0) {
+    if (mode == 8 || mode == 9) { // Jacobi-preconditioned CG: s1 = r.r (stopping test, unpreconditioned), s2 = r.z with z = D^-1 r
+        if (mode == 8) {
+            scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_RZ] = s2;
+            const double tol = atol + rtol * sqrt(s1);
+            scal[SC_TOL] = tol;
+            scal[SC_ITER] = 0.0;
+            scal[SC_CONV] = (sqrt(s1) <= tol) ? 1.0 : 0.0;
+        } else {
+            scal[SC_BETA] = s2 / scal[SC_RZ];
+            scal[SC_RZ] = s2;
+            scal[SC_RR] = s1;
+            scal[SC_ITER] += 1.0;
+            if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
+        }
+    } else if (mode == 0) {
+        scal[SC_RZ] = s1;
         scal[SC_RR] = s1; scal[SC_RR0] = s1; scal[SC_BNORM2] = s2;
         const double tol = atol + rtol * sqrt(s1); // Krylov: eps = atol + rtol*||r0||
         scal[SC_TOL] = tol;
@@ -230,11 +250,12 @@ __device__ __noinline__ void cg_finish(int mode, int stage, int nblk, int nblk_m
         scal[SC_CONV] = (sqrt(s1) <= tol) ? 1.0 : 0.0;
     } else if (mode == 1) {
         scal[SC_PAP] = s1;
-        scal[SC_ALPHA] = scal[SC_RR] / s1;
+        scal[SC_ALPHA] = scal[SC_RZ] / s1;
     } else if (mode == 2) {
         const double rr_old = scal[SC_RR];
         scal[SC_BETA] = s1 / rr_old;
         scal[SC_RR] = s1;
+        scal[SC_RZ] = s1;
         scal[SC_ITER] += 1.0;
         if (sqrt(s1) <= scal[SC_TOL] || !(s1 == s1)) scal[SC_CONV] = 1.0;
     } else if (mode == 3) {
@@ -566,7 +587,8 @@ __global__ void __launch_bounds__(PR_BLOCK, INIT ? 4 : 8) k_rhs_corr(int nslot, 
                                                        const double *__restrict__ c2, const double *__restrict__ P,
                                                        const double *__restrict__ bvel, const double2 *__restrict__ GP,
                                                        double *__restrict__ b, const double *__restrict__ AP, double *__restrict__ r,
-                                                       double *__restrict__ p, double *__restrict__ partial, int nblk_max) {
+                                                       double *__restrict__ p, double *__restrict__ partial, int nblk_max,
+                                                       const double *__restrict__ dinv) {
     __shared__ double sm[32];
     double rr = 0.0, bb = 0.0;
     const int stride = INIT ? gridDim.x * blockDim.x : nslot;
@@ -601,9 +623,9 @@ __global__ void __launch_bounds__(PR_BLOCK, INIT ? 4 : 8) k_rhs_corr(int nslot, 
         if (INIT) {
             const double ri = bi - AP[i];
             r[i] = ri;
-            p[i] = ri;
             rr += ri * ri;
-            bb += bi * bi;
+            if (dinv) { const double zi = dinv[i] * ri; p[i] = zi; bb += ri * zi; } // Jacobi: p = z, second sum = r.z
+            else { p[i] = ri; bb += bi * bi; }
         }
     }
     if (INIT) {
@@ -614,7 +636,7 @@ __global__ void __launch_bounds__(PR_BLOCK, INIT ? 4 : 8) k_rhs_corr(int nslot, 
 }
 
 static inline int pr_grid(const LvContext *c, int64_t n);
-int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done) {
+int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool fuse_init, bool *init_done, bool pcg) {
     if (init_done) *init_done = false;
     LV_TRY(lv_pr_ensure(c));
     if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
@@ -650,11 +672,11 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool
         if (fused) {
             k_rhs_corr<true><<<pr_grid(c, ns), PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area,
                                                                          c->d_rho, c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, c->d_vec[2],
-                                                                         c->d_vec[0], c->d_vec[1], c->d_red + SC_COUNT, 4096);
+                                                                         c->d_vec[0], c->d_vec[1], c->d_red + SC_COUNT, 4096, pcg ? c->d_dinv : nullptr);
             if (init_done) *init_done = true;
         } else
             k_rhs_corr<false><<<nb, PR_BLOCK, 0, c->stream>>>(ns, dt, c->d_own, c->d_rowptr, c->d_deg, c->d_col, c->d_lrr, c->d_mz, c->d_area, c->d_rho,
-                                                              c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, nullptr, nullptr, nullptr, nullptr, 4096);
+                                                              c->d_c2, c->d_P, c->d_bvel, c->d_GP, c->d_b, nullptr, nullptr, nullptr, nullptr, 4096, nullptr);
         c->launches++;
     }
     LV_CUDA(c, cudaGetLastError());
@@ -663,18 +685,19 @@ int lv_pr_rhs(LvContext *c, double dt, int gp_step, const double *vbc_wall, bool
 
 // ---- K5: conjugate gradients, scalars resident on the device ------------------------------------------
 // r = b - A x ; p = r ; partial(r.r), partial(b.b)
+// dinv (nullable): Jacobi preconditioner 1/A_ii -- then p = z = dinv r and the second partial is r.z instead of b.b
 __global__ void __launch_bounds__(PR_BLOCK) k_cg_init(int nslot, const double *__restrict__ b, const double *__restrict__ Ax,
                                                       double *__restrict__ r, double *__restrict__ p, double *__restrict__ partial,
-                                                      int nblk_max) {
+                                                      int nblk_max, const double *__restrict__ dinv) {
     __shared__ double sm[32];
     double rr = 0.0, bb = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
         const double bi = b[i];
         const double ri = bi - Ax[i];
         r[i] = ri;
-        p[i] = ri;
         rr += ri * ri;
-        bb += bi * bi;
+        if (dinv) { const double zi = dinv[i] * ri; p[i] = zi; bb += ri * zi; }
+        else { p[i] = ri; bb += bi * bi; }
     }
     const double s1 = block_sum(rr, sm);
     const double s2 = block_sum(bb, sm);
@@ -776,23 +799,30 @@ __global__ void __launch_bounds__(PR_BLOCK) k_axpy1(int nslot, const double *__r
 
 // r -= alpha Ap ; partial(r.r).  The x update rides along with the p update below, which reads p anyway:
 // 8 instead of 9 vector streams per iteration, same arithmetic per element.
-template <bool FUSE>
+// PC: Jacobi-preconditioned CG -- the kernel also accumulates r.z = sum dinv_i r_i^2 (second partial) and finishes with mode 9
+template <bool FUSE, bool PC>
 __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_r(int nslot, double *scal, const double *__restrict__ Ap,
-                                                          double *__restrict__ r, double *__restrict__ partial, FuseArgs fz) {
+                                                          double *__restrict__ r, double *__restrict__ partial, FuseArgs fz,
+                                                          const double *__restrict__ dinv, int nblk_max) {
     __shared__ double sm[32];
     const bool idle = scal[SC_CONV] != 0.0;
     if (idle && !FUSE) return;
     const double alpha = scal[SC_ALPHA];
-    double rr = 0.0;
+    double rr = 0.0, rz = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (idle ? 0 : nslot); i += gridDim.x * blockDim.x) {
         const double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
         rr += ri * ri;
+        if (PC) rz += ri * (dinv[i] * ri);
     }
     const double s = block_sum(rr, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
-    if (FUSE && lv_last_block(fz.ticket)) { // mode 2: beta, iteration count, convergence test
-        cg_finish(2, fz.stage, gridDim.x, fz.nblk_max, partial, scal, fz.rtol, fz.atol, fz.mail);
+    if (PC) {
+        const double s2 = block_sum(rz, sm);
+        if (threadIdx.x == 0) partial[nblk_max + blockIdx.x] = s2;
+    }
+    if (FUSE && lv_last_block(fz.ticket)) { // mode 2 (9 with the preconditioner): beta, iteration count, convergence test
+        cg_finish(PC ? 9 : 2, fz.stage, gridDim.x, fz.nblk_max, partial, scal, fz.rtol, fz.atol, fz.mail);
         if (threadIdx.x == 0) *fz.ticket = 0;
     }
 }
@@ -804,7 +834,8 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_r(int nslot, double *sca
 // the interior) and its last block publishes the exchange's sequence word -- no pack / signal launches.
 template <bool PACK>
 __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xp(int nslot, int iter, const double *__restrict__ scal, const double *__restrict__ r,
-                                                           double *__restrict__ x, double *__restrict__ p, LvHaloPack hp) {
+                                                           double *__restrict__ x, double *__restrict__ p, LvHaloPack hp,
+                                                           const double *__restrict__ dinv) {
     const bool conv = scal[SC_CONV] != 0.0;
     const bool idle = conv && scal[SC_ITER] != (double)iter;
     if (idle && !PACK) return;
@@ -818,7 +849,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_cg_update_xp(int nslot, int iter, 
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += gridDim.x * blockDim.x) {
             const double pi = p[i];
             x[i] += alpha * pi;
-            const double pn = r[i] + beta * pi;
+            const double pn = (dinv ? dinv[i] * r[i] : r[i]) + beta * pi; // p = z + beta p, z = D^-1 r with the Jacobi preconditioner
             p[i] = pn;
             if (PACK && (i < b0 || i >= b1)) {
                 const int s0 = hp.send_pos0[i];
@@ -859,8 +890,9 @@ __global__ void __launch_bounds__(PR_BLOCK) k_resid(int nslot, const double *__r
 // A x = b with x = c->d_P (initial guess in, solution out), b = c->d_b
 int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, int *iters, double *relres, bool pre_init) {
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
-    if (solver != LV_SOLVER_CG && solver != LV_SOLVER_MINRES) return lv_set_error(c, LV_EINVAL, "unknown solver %d", solver);
-    const bool minres = solver == LV_SOLVER_MINRES;
+    if (solver != LV_SOLVER_CG && solver != LV_SOLVER_MINRES && solver != LV_SOLVER_PCG) return lv_set_error(c, LV_EINVAL, "unknown solver %d", solver);
+    const bool minres = solver == LV_SOLVER_MINRES, pcg = solver == LV_SOLVER_PCG;
+    const double *dinv = pcg ? c->d_dinv : nullptr; // Jacobi preconditioner 1/A_ii (k_assemble)
     const int ns = (int)c->nslot;
     if (iters) *iters = 0;
     if (relres) *relres = 0.0;
@@ -907,6 +939,7 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         return LV_OK;
     };
     if (pre_init && minres) return lv_set_error(c, LV_EINVAL, "pre-initialised solves are CG only");
+    if (pcg && !c->d_dinv) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     if (!pre_init) {
         LV_TRY(lv_halo_exchange(c, x, 1)); // ghost columns of the initial guess
         matvec_plain(x, Ap);
@@ -915,10 +948,10 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
         {
             LvProfScope prof(c, LV_PROF_VECOPS);
             if (!pre_init) { // otherwise the right-hand-side kernels left r, p and the partial sums behind (lv_pr_rhs)
-                k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX);
+                k_cg_init<<<nb, PR_BLOCK, 0, st>>>(ns, b, Ap, r, p, partial, NBMAX, dinv);
                 c->launches++;
             }
-            LV_TRY(finish(0));
+            LV_TRY(finish(pcg ? 8 : 0));
             if (peer) LV_TRY(lv_strip_halo_post(c, p, 1)); // p = r is ready for the neighbours
         }
         // Iterations are queued in batches; kernels turn into no-ops once the device-side convergence
@@ -939,17 +972,20 @@ int lv_pr_solve(LvContext *c, int solver, double rtol, double atol, int itmax, i
                     else mv_launch<true, false>(c, nb_mv, st, ns, p, Ap, partial, scal);
                 }
                 LvProfScope prof(c, LV_PROF_VECOPS);
-                if (fuse) k_cg_update_r<true><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, fuse_args(1));
-                else {
+                if (fuse) {
+                    if (pcg) k_cg_update_r<true, true><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, fuse_args(1), dinv, NBMAX);
+                    else k_cg_update_r<true, false><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, fuse_args(1), nullptr, NBMAX);
+                } else {
                     LV_TRY(finish(1));
-                    k_cg_update_r<false><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, FuseArgs());
-                    LV_TRY(finish(2));
+                    if (pcg) k_cg_update_r<false, true><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, FuseArgs(), dinv, NBMAX);
+                    else k_cg_update_r<false, false><<<nb, PR_BLOCK, 0, st>>>(ns, scal, Ap, r, partial, FuseArgs(), nullptr, NBMAX);
+                    LV_TRY(finish(pcg ? 9 : 2));
                 }
                 if (peer) {
                     LvHaloPack hp;
                     LV_TRY(lv_strip_pack_args(c, &hp));
-                    k_cg_update_xp<true><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, hp);
-                } else k_cg_update_xp<false><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, LvHaloPack());
+                    k_cg_update_xp<true><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, hp, dinv);
+                } else k_cg_update_xp<false><<<nb, PR_BLOCK, 0, st>>>(ns, done + it + 1, scal, r, x, p, LvHaloPack(), dinv);
                 c->launches += 2;
             }
             done += todo;
@@ -1068,7 +1104,7 @@ int lv_pr_find_pressure(LvContext *c, double dt, int niter, double rtol, double 
     LV_TRY(lv_pr_assemble(c, dt));
     for (int it = 1; it <= niter; it++) {
         bool init_done = false;
-        LV_TRY(lv_pr_rhs(c, dt, it > 1, vbc_wall, solver == LV_SOLVER_CG, &init_done));
+        LV_TRY(lv_pr_rhs(c, dt, it > 1, vbc_wall, solver == LV_SOLVER_CG || solver == LV_SOLVER_PCG, &init_done, solver == LV_SOLVER_PCG));
         int iters = 0;
         double relres = 0.0;
         LV_TRY(lv_pr_solve(c, solver, rtol, atol, itmax, &iters, relres_out ? &relres : nullptr, init_done));
@@ -1090,7 +1126,7 @@ int32_t lv_pressure_destroy(LvHandle c) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
-    double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
+    double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_dinv, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
                       &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
     for (double **p : one) { lv_free(c, *p, sizeof(double) * (size_t)c->pr_cap); *p = nullptr; }
     lv_free(c, c->d_lrr, sizeof(double) * (size_t)c->cap_w); c->d_lrr = nullptr;
@@ -1282,7 +1318,7 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
 int32_t lv_pressure_rhs(LvHandle c, double dt, int32_t gp_step, const double *vbc_wall, double *b, double *GP) {
     if (!c) return LV_EINVAL;
     LV_CUDA(c, cudaSetDevice(c->device));
-    LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall, false, nullptr));
+    LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall, false, nullptr, false));
     if (b) LV_TRY(download_slots(c, c->d_b, b, 1));
     if (GP) LV_TRY(download_slots(c, (const double *)c->d_GP, GP, 2));
     return LV_OK;

@@ -325,7 +325,7 @@ class PressureSolver:
         b = np.ascontiguousarray(b, np.float64)
         x = np.array(x0, np.float64, copy=True)
         it, rr = C.c_int32(), C.c_double()
-        kind = LV_SOLVER_MINRES if (solver or self.solver) == "minres" else LV_SOLVER_CG
+        kind = _capi.solver_kind(solver or self.solver)
         check(g._L.lv_pressure_solve(g._h, kind, ptr(b), ptr(x), rtol, atol, int(itmax), C.byref(it), C.byref(rr)), g._h)
         return x, it.value, rr.value
 
@@ -334,7 +334,7 @@ class PressureSolver:
         iters = np.zeros(niter, np.int32)
         relres = np.zeros(niter) if want_relres else None
         vw = None if vbc_wall is None else np.ascontiguousarray(vbc_wall, np.float64).reshape(4, 2)
-        kind = LV_SOLVER_MINRES if self.solver == "minres" else LV_SOLVER_CG
+        kind = _capi.solver_kind(self.solver)
         check(g._L.lv_find_pressure_dev(g._h, float(dt), int(niter), self.rtol, self.atol, int(self.itmax), kind, ptr(vw),
                                         iters.ctypes.data_as(C.POINTER(C.c_int32)),
                                         None if relres is None else relres.ctypes.data_as(C.POINTER(C.c_double))), g._h)
@@ -401,7 +401,7 @@ def find_pressure(solver: PressureSolver, dt: float, niter: int = 10, boundary_v
     iters = np.zeros(niter, np.int32)
     relres = np.zeros(niter) if solver.verbose else None
     vw, ve = _wall_velocities(g, boundary_velocity)
-    kind = LV_SOLVER_MINRES if solver.solver == "minres" else LV_SOLVER_CG
+    kind = _capi.solver_kind(solver.solver)
     P_out = g.P
     check(g._L.lv_find_pressure(g._h, float(dt), int(niter), solver.rtol, solver.atol, int(solver.itmax), kind,
                                 ptr(g.mass), ptr(g.rho), ptr(g.c2), ptr(g.P), ptr(g.v), ptr(vw), ptr(ve),

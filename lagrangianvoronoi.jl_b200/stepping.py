@@ -23,7 +23,8 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import LV_SOLVER_CG, LV_SOLVER_MINRES, check, ptr
+from . import _capi
+from ._capi import check, ptr
 from .host import PressureSolver, VoronoiGrid, _FIELDS, _host_empty, _wall_velocities
 
 _STATE_FIELDS = ["v", "dv", "momentum", "rho", "e", "P", "c2", "mass", "energy", "quality", "mu", "phase"]
@@ -86,7 +87,7 @@ def find_pressure_resident(solver: PressureSolver, dt: float, niter: int = 10, b
     relres = np.zeros(niter) if solver.verbose else None
     vw, ve = _wall_velocities(g, boundary_velocity)
     check(g._L.lv_set_boundary_velocity(g._h, ptr(ve), 0 if ve is None else int(ve.shape[0])), g._h)
-    kind = LV_SOLVER_MINRES if solver.solver == "minres" else LV_SOLVER_CG
+    kind = _capi.solver_kind(solver.solver)
     check(g._L.lv_step_find_pressure(g._h, float(dt), int(niter), solver.rtol, solver.atol, int(solver.itmax), kind, ptr(vw),
                                      iters.ctypes.data_as(C.POINTER(C.c_int32)),
                                      None if relres is None else relres.ctypes.data_as(C.POINTER(C.c_double))), g._h)

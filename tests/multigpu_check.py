@@ -138,16 +138,21 @@ def check_stepping(kind, n_side, xper, yper, rank, world, dev, two_phase=False, 
         f["e"] = 0.5 * (f["v"] ** 2).sum(1) + f["P"] / (f["rho"] * 0.4)
         return f
 
-    def step(grid, solver):
-        S.move(grid, dt)
+    def step(grid, solver, probe=None):
+        ops = [("move", lambda: S.move(grid, dt))]
         if two_phase:
-            S.gravity_step(grid, (0.0, -1.0), dt)
-        S.ideal_eos(grid, 1.4, 0.0)
-        S.find_pressure_resident(solver, dt)
-        S.pressure_step(grid, dt); S.find_D(grid); S.viscous_step(grid, dt, True); S.find_dv(grid, dt)
+            ops.append(("gravity", lambda: S.gravity_step(grid, (0.0, -1.0), dt)))
+        ops += [("eos", lambda: S.ideal_eos(grid, 1.4, 0.0)), ("find_pressure", lambda: S.find_pressure_resident(solver, dt)),
+                ("pressure_step", lambda: S.pressure_step(grid, dt)), ("find_D", lambda: S.find_D(grid)),
+                ("viscous", lambda: S.viscous_step(grid, dt, True)), ("find_dv", lambda: S.find_dv(grid, dt))]
         if two_phase:
-            S.multiphase_projection(grid, rtol=1e-11, atol=1e-11, itmax=3000)
-        S.relaxation_step(grid, dt)
+            ops.append(("projection", lambda: S.multiphase_projection(grid, rtol=1e-11, atol=1e-11, itmax=3000)))
+        ops.append(("relaxation", lambda: S.relaxation_step(grid, dt)))
+        for name, op in ops:
+            op()
+            if probe is not None and name not in ("move", "relaxation"):
+                bad = [nm for nm in ("v", "e", "P", "rho", "dv", "mass") if not np.isfinite(probe(nm)).all()]
+                assert not bad, f"rank {rank}: non-finite {bad} after {name}"
 
     # ---- one GPU
     g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=xper, yperiodic=yper, device=dev.index)
@@ -183,7 +188,7 @@ def check_stepping(kind, n_side, xper, yper, rank, world, dev, two_phase=False, 
         warnings.simplefilter("ignore")
         for _ in range(nsteps):
             before = set(sg.owned_labels().cpu().numpy().tolist())
-            step(sg.grid, ssol)
+            step(sg.grid, ssol, probe=sg.state_get if os.environ.get("LV_DEBUG_STEP") else None)
             sg.refresh()
             moved += len(set(sg.owned_labels().cpu().numpy().tolist()) - before)
     own = sg.owned_labels().cpu().numpy() - 1
