@@ -10,6 +10,7 @@
 // the period is in general not a multiple of h, so image buckets are NOT translated copies
 // of the primary buckets and must be keyed individually to reproduce the candidate order.
 #include "lv_internal.cuh"
+#include <cmath>
 
 // position of periodic image k of x, k in the reference's insertion order
 // 0: x, 1: +X, 2: -X, 3: +Y, 4: -Y, 5: +X+Y, 6: +X-Y, 7: -X+Y, 8: -X-Y   (voronoigrid.jl:130-147)
@@ -254,7 +255,19 @@ int lv_cells_build(LvContext *c) {
     int nslot = 0;
     LV_TRY(lv_publish_flags(c, c->d_cell_start + ncell_ext));
     nslot = c->h_flags[8];
-    if (c->h_flags[LVF_NAN]) return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf");
+    if (c->h_flags[LVF_NAN]) {
+        // error path only: name the first offending generator (in strip mode: owned or ghost) -- positions come to the host
+        std::vector<double2> h((size_t)n);
+        long long bad = -1;
+        if (cudaMemcpy(h.data(), c->xy, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int64_t i = 0; i < n && bad < 0; i++)
+                if (!std::isfinite(h[(size_t)i].x) || !std::isfinite(h[(size_t)i].y)) bad = i;
+        if (c->strip.on)
+            return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf (local generator %lld of %lld; %lld owned -> %s; last migration out %d in %d)",
+                                bad, (long long)n, (long long)c->strip.n_own, bad >= 0 && bad < c->strip.n_own ? "owned" : "ghost",
+                                c->strip.last_mig_out, c->strip.last_mig_in);
+        return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf (generator %lld of %lld)", bad + 1, (long long)n);
+    }
     c->nslot = nslot;
     {
         int64_t cap = c->cap_slot;
