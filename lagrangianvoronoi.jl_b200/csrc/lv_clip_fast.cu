@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         int t_scan = -1, s = 0, s_end = 0, t_end = g.npath, t_chk = -1; // scan cursor / last node whose entry test ran
         bool scan_done = !active;
         int qh = 0, qn = 0; // queue = positions [qh, qn) modulo QCAP
+        const double hpx = 0.5 * g.xperiod, hpy = 0.5 * g.yperiod;
+        const double slack = 2e-15 * (fabs(x.x) + fabs(x.y)); // 2 * rounding bound of x - (x + v), see phase A
         if (active) {
             // reset!  polygon.jl:37-47: B->A DOWN, A->D LEFT, D->C UP, C->B RIGHT (storage order 0..3)
             p.V(0) = make_double2(g.cmaxx, g.cminy); p.L(0) = BD_DOWN;
@@ -122,36 +124,47 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
 
         // ---- voronoicut!(grid, poly)  voronoigrid.jl:53-81
         while (__any_sync(FULL, alive)) {
-            // phase A: scan ahead, queue candidates that pass the distance filter with the current radius
+            // phase A: scan ahead, queue candidates that pass the distance filter with the current radius.  One event = (advance to
+            // the next path node if the current bucket is exhausted) + (test one candidate): lanes that just entered a bucket test
+            // its first entry in the same event, so the candidate part runs with more lanes and a cell needs fewer events.
+            // The filter here is CONSERVATIVE (phase B re-applies the reference's exact test before anything is decided): the
+            // candidate is dropped only if it is outside the influence radius by more than the rounding error that separates
+            // |q - x|^2 from the reference's |x - (x + arrow)|^2 -- at most ulp(x + v) per component, bounded by
+            // 1e-15 (|x.x| + |x.y|) + 1e-15 |v| (see lv_neighbor_pos: the periodic shift itself is the same operation).
 #pragma unroll 1
             for (int ev = 0; ev < EV; ev++) {
                 const bool scanning = alive && !scan_done && (qn - qh) < QCAP;
                 if (!__any_sync(FULL, scanning)) break;
                 if (scanning) {
-                    if (s < s_end) {
+                    if (s >= s_end) {
+                        if (++t_scan >= g.npath) {
+                            scan_done = true; t_end = g.npath;
+                        } else {
+                            const LvPathNode nd = spath[t_scan];
+                            if (nd.rr > prr || nd.rr > g.rr_max) { scan_done = true; t_end = t_scan; } // the walk ends here at the latest
+                            else {
+                                const int c1 = k1 + nd.i1, c2 = k2 + nd.i2;
+                                s = s_end = 0;
+                                if (c1 >= 1 && c1 <= g.n1 && c2 >= 1 && c2 <= g.n2) {
+                                    const int lin = (c1 - 1) + g.n1 * (c2 - 1);
+                                    s = a.cell_start[lin];
+                                    s_end = a.cell_start[lin + 1];
+                                }
+                            }
+                        }
+                    }
+                    if (!scan_done && s < s_end) {
                         const double2 q = a.ent_xy[s];
-                        const double2 y = lv_neighbor_pos(g, x, q);
-                        const double ex = x.x - y.x, ey = x.y - y.y;
-                        if (!((x.x == y.x && x.y == y.y) || (ex * ex + ey * ey > prr))) {
+                        double vx = q.x - x.x, vy = q.y - x.y;
+                        if (g.xper) { if (vx > hpx) vx -= g.xperiod; else if (vx < -hpx) vx += g.xperiod; }
+                        if (g.yper) { if (vy > hpy) vy -= g.yperiod; else if (vy < -hpy) vy += g.yperiod; }
+                        const double d2 = vx * vx + vy * vy;
+                        if (!(d2 * (1.0 - 2e-15) - (fabs(vx) + fabs(vy)) * slack > prr)) { // NaN ends up queued: phase B decides
                             sq[(qn & (QCAP - 1)) * BLOCK + threadIdx.x] = s;
                             sqt[(qn & (QCAP - 1)) * BLOCK + threadIdx.x] = t_scan;
                             qn++;
                         }
                         s++;
-                    } else if (++t_scan >= g.npath) {
-                        scan_done = true; t_end = g.npath;
-                    } else {
-                        const LvPathNode nd = spath[t_scan];
-                        if (nd.rr > prr || nd.rr > g.rr_max) { scan_done = true; t_end = t_scan; } // the walk ends here at the latest
-                        else {
-                            const int c1 = k1 + nd.i1, c2 = k2 + nd.i2;
-                            s = s_end = 0;
-                            if (c1 >= 1 && c1 <= g.n1 && c2 >= 1 && c2 <= g.n2) {
-                                const int lin = (c1 - 1) + g.n1 * (c2 - 1);
-                                s = a.cell_start[lin];
-                                s_end = a.cell_start[lin + 1];
-                            }
-                        }
                     }
                 }
             }
