@@ -216,7 +216,7 @@ int32_t lv_destroy(LvHandle c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
-                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_flags, c->d_tickets, c->d_bdry_ptr, c->d_vbc_edge, c->d_bf_on, c->d_scratch,
+                    c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_park_v, c->d_park_l, c->d_park_nxt, c->d_park_hdr, c->d_flags, c->d_tickets, c->d_bdry_ptr, c->d_vbc_edge, c->d_bf_on, c->d_scratch,
                     c->d_mass, c->d_rho, c->d_c2, c->d_P, c->d_v, c->d_GP, c->d_diag, c->d_dinv, c->d_w, c->d_b, c->d_red, c->d_lrr, c->d_mx, c->d_mz, c->d_bvel, c->d_deg, c->d_own, c->d_stage_buf[0], c->d_stage_buf[1], c->d_io_stage};
     for (void *b : bufs) if (b) cudaFree(b);
     for (double *v : c->d_vec) if (v) cudaFree(v);

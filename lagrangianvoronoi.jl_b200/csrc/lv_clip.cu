@@ -307,6 +307,7 @@ int lv_clip_run(LvContext *c) {
         a.tile_state = c->d_tile_state;
         a.flags = c->d_flags;
         a.cap_nnz = c->cap_nnz;
+        a.park_v = nullptr; a.park_l = nullptr; a.park_nxt = nullptr; a.park_hdr = nullptr;
         { const char *fa = getenv("LV_CLIP_FORCE_ANOMALY"); a.force_anomaly = fa && fa[0] == '1'; }
         {
             LvProfScope prof(c, LV_PROF_CLIP);

@@ -27,6 +27,11 @@ struct ClipArgs {
     unsigned long long *tile_state;
     int *flags;
     long long cap_nnz;
+    // lane-refill kernel (lv_clip_fast.cu): parked rings, [ring slot][mesh slot]
+    double2 *park_v;
+    int *park_l;
+    unsigned long long *park_nxt;
+    int *park_hdr;
     int force_anomaly; // test hook (LV_CLIP_FORCE_ANOMALY=1): pretend some polygons are not generic
 };
 

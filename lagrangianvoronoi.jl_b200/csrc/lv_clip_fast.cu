@@ -107,188 +107,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         int qh = 0, qn = 0; // queue = positions [qh, qn) modulo QCAP
         const double hpx = 0.5 * g.xperiod, hpy = 0.5 * g.yperiod;
         const double slack = 2e-15 * (fabs(x.x) + fabs(x.y)); // 2 * rounding bound of x - (x + v), see phase A
-        if (active) {
-            // reset!  polygon.jl:37-47: B->A DOWN, A->D LEFT, D->C UP, C->B RIGHT (storage order 0..3)
-            p.V(0) = make_double2(g.cmaxx, g.cminy); p.L(0) = BD_DOWN;
-            p.V(1) = make_double2(g.cminx, g.cminy); p.L(1) = BD_LEFT;
-            p.V(2) = make_double2(g.cminx, g.cmaxy); p.L(2) = BD_UP;
-            p.V(3) = make_double2(g.cmaxx, g.cmaxy); p.L(3) = BD_RIGHT;
-            p.ord = 0x3210ull; p.pos = 0x3210ull;
-            p.nxt = 0x0321ull; // 0->1->2->3->0
-            p.prv = 0x2103ull;
-            p.used = 0xfu;
-            p.m = 4;
-            prr = ring_influence_rr(p, x);
-            if (!lv_findkey(g, x, k1, k2)) { atomicOr(&a.flags[LVF_NAN], 1); k1 = k2 = -(1 << 30); }
-        }
-
+#include "lv_clip_init.inc"
         // ---- voronoicut!(grid, poly)  voronoigrid.jl:53-81
         while (__any_sync(FULL, alive)) {
-            // phase A: scan ahead, queue candidates that pass the distance filter with the current radius.  One event = (advance to
-            // the next path node if the current bucket is exhausted) + (test one candidate): lanes that just entered a bucket test
-            // its first entry in the same event, so the candidate part runs with more lanes and a cell needs fewer events.
-            // The filter here is CONSERVATIVE (phase B re-applies the reference's exact test before anything is decided): the
-            // candidate is dropped only if it is outside the influence radius by more than the rounding error that separates
-            // |q - x|^2 from the reference's |x - (x + arrow)|^2 -- at most ulp(x + v) per component, bounded by
-            // 1e-15 (|x.x| + |x.y|) + 1e-15 |v| (see lv_neighbor_pos: the periodic shift itself is the same operation).
-#pragma unroll 1
-            for (int ev = 0; ev < EV; ev++) {
-                const bool scanning = alive && !scan_done && (qn - qh) < QCAP;
-                if (!__any_sync(FULL, scanning)) break;
-                if (scanning) {
-                    if (s >= s_end) {
-                        if (++t_scan >= g.npath) {
-                            scan_done = true; t_end = g.npath;
-                        } else {
-                            const LvPathNode nd = spath[t_scan];
-                            if (nd.rr > prr || nd.rr > g.rr_max) { scan_done = true; t_end = t_scan; } // the walk ends here at the latest
-                            else {
-                                const int c1 = k1 + nd.i1, c2 = k2 + nd.i2;
-                                s = s_end = 0;
-                                if (c1 >= 1 && c1 <= g.n1 && c2 >= 1 && c2 <= g.n2) {
-                                    const int lin = (c1 - 1) + g.n1 * (c2 - 1);
-                                    s = a.cell_start[lin];
-                                    s_end = a.cell_start[lin + 1];
-                                }
-                            }
-                        }
-                    }
-                    if (!scan_done && s < s_end) {
-                        const double2 q = a.ent_xy[s];
-                        double vx = q.x - x.x, vy = q.y - x.y;
-                        if (g.xper) { if (vx > hpx) vx -= g.xperiod; else if (vx < -hpx) vx += g.xperiod; }
-                        if (g.yper) { if (vy > hpy) vy -= g.yperiod; else if (vy < -hpy) vy += g.yperiod; }
-                        const double d2 = vx * vx + vy * vy;
-                        if (!(d2 * (1.0 - 2e-15) - (fabs(vx) + fabs(vy)) * slack > prr)) { // NaN ends up queued: phase B decides
-                            sq[(qn & (QCAP - 1)) * BLOCK + threadIdx.x] = s;
-                            sqt[(qn & (QCAP - 1)) * BLOCK + threadIdx.x] = t_scan;
-                            qn++;
-                        }
-                        s++;
-                    }
-                }
-            }
-            __syncwarp();
-            // phase B: pop candidates in order until one has a vertex outside its half plane
-            unsigned plus = 0, zero = 0;
-            double dx = 0, dy = 0, c = 0;
-            int cand = 0;
-            while (alive && qh < qn && !plus) {
-                cand = sq[(qh & (QCAP - 1)) * BLOCK + threadIdx.x];
-                const int tq = sqt[(qh & (QCAP - 1)) * BLOCK + threadIdx.x];
-                qh++;
-                if (tq > t_chk) { // node entry test of the reference, with the radius of this moment (voronoigrid.jl:60-62)
-                    t_chk = tq;
-                    if (spath[tq].rr > prr) { alive = false; break; }
-                }
-                const double2 q = a.ent_xy[cand];
-                const double2 y = lv_neighbor_pos(g, x, q);
-                const double ex = x.x - y.x, ey = x.y - y.y;
-                if ((x.x == y.x && x.y == y.y) || (ex * ex + ey * ey > prr)) continue; // voronoigrid.jl:73-75
-                dx = y.x - x.x; dy = y.y - x.y;                                        // polygon.jl:52-54
-                const double mx = 0.5 * (y.x + x.x), my = 0.5 * (y.y + x.y);
-                c = dx * mx + dy * my;
-                zero = 0;
-                for (unsigned u = p.used; u; u &= u - 1) {
-                    const int sk = __ffs(u) - 1;
-                    const double2 v = p.V(sk);
-                    const double f = (dx * v.x + dy * v.y) - c;
-                    if (f > SIGNUM_EPS) plus |= 1u << sk;
-                    else if (!(f < -SIGNUM_EPS)) zero |= 1u << sk;
-                }
-            }
-            if (alive && !plus && scan_done && qh >= qn) {
-                // the scan stopped at node t_end; replay that node's entry test with the final radius
-                if (t_end < g.npath) {
-                    const LvPathNode nd = spath[t_end];
-                    if (!(nd.rr > prr) && nd.rr > g.rr_max) atomicOr(&a.flags[LVF_DESTROYED], 1); // voronoigrid.jl:63-65
-                }
-                alive = false;
-            }
-            __syncwarp();
-            // phase C: cut (polygon.jl:59-96)
-            if (plus) {
-                const int np = __popc(plus);
-                unsigned starts = 0; // outside vertices whose predecessor is not outside
-                for (unsigned u = plus; u; u &= u - 1) {
-                    const int sk = __ffs(u) - 1;
-                    if (!((plus >> nib(p.prv, sk)) & 1)) starts |= 1u << sk;
-                }
-                if (__popc(starts) != 1) bad = true;
-                else {
-                    const int pfirst = __ffs(starts) - 1;
-                    const int a_slot = nib(p.prv, pfirst); // edge (-|0, +): the polygon is left here
-                    int b_slot = pfirst, cnt = 1;          // edge (+, -|0): the polygon is re-entered here
-                    unsigned del = 0;                      // edges with s1 + s2 >= 1 (polygon.jl:81-85)
-                    while (cnt < np && ((plus >> nib(p.nxt, b_slot)) & 1)) { del |= 1u << b_slot; b_slot = nib(p.nxt, b_slot); cnt++; }
-                    const int nb = nib(p.nxt, b_slot);
-                    if (cnt != np || ((plus >> nb) & 1)) bad = true; // outside vertices not contiguous
-                    else {
-                        const bool za = (zero >> a_slot) & 1, zb = (zero >> nb) & 1;
-                        if (za) del |= 1u << a_slot;
-                        if (zb) del |= 1u << b_slot;
-                        const double2 va1 = p.V(a_slot), va2 = p.V(pfirst), vb1 = p.V(b_slot), vb2 = p.V(nb);
-                        double2 XA, XB;
-                        {
-                            const double f1 = (dx * va1.x + dy * va1.y) - c, f2 = (dx * va2.x + dy * va2.y) - c;
-                            const double r = 1.0 / (f1 - f2);
-                            XA = make_double2(r * (f1 * va2.x - f2 * va1.x), r * (f1 * va2.y - f2 * va1.y));
-                            if (za) XA = va1;
-                        }
-                        {
-                            const double f1 = (dx * vb1.x + dy * vb1.y) - c, f2 = (dx * vb2.x + dy * vb2.y) - c;
-                            const double r = 1.0 / (f1 - f2);
-                            XB = make_double2(r * (f1 * vb2.x - f2 * vb1.x), r * (f1 * vb2.y - f2 * vb1.y));
-                            if (zb) XB = vb2;
-                        }
-                        // which of the two edges the reference's scan over the storage order meets last
-                        int last_kind, mm = p.m;
-                        u64 o = p.ord;
-                        if (del == 0) last_kind = nib(p.pos, b_slot) > nib(p.pos, a_slot) ? 2 : 1;
-                        else { // replay deleteat! (swap-remove) on the storage order
-                            int i = 0;
-                            last_kind = 0;
-                            while (i < mm) {
-                                const int sk = nib(o, i);
-                                if (sk == a_slot) last_kind = 1;
-                                else if (sk == b_slot) last_kind = 2;
-                                if ((del >> sk) & 1) { o = setnib(o, i, nib(o, mm - 1)); mm--; }
-                                else { p.pos = setnib(p.pos, sk, i); i++; }
-                            }
-                        }
-                        // the reference's X is the point met last, Y the one before (polygon.jl:67-69, 87-95)
-                        const double2 X = last_kind == 2 ? XB : XA, Y = last_kind == 2 ? XA : XB;
-                        const double cr = (Y.x - X.x) * (x.y - X.y) - (Y.y - X.y) * (x.x - X.x);
-                        const bool invert = cr > 0.0;
-                        const bool nanx = (isnan(XA.x) && isnan(XA.y)) || (isnan(XB.x) && isnan(XB.y)) || isnan(cr);
-                        const bool same = (XA.x == XB.x && XA.y == XB.y);
-                        const unsigned freemask = ~(p.used & ~del) & ((1u << MAXE) - 1u);
-                        if (nanx || same || (invert != (last_kind == 2))) bad = true; // not the generic case
-                        else if (!freemask) { bad = true; atomicOr(&a.flags[LVF_OVERFLOW], OVF_POLY); }
-                        else {
-                            p.used &= ~del;
-                            const int ns = __ffs(freemask) - 1;
-                            p.used |= 1u << ns;
-                            p.V(ns) = XA; // new edge XA -> XB keeps the generator on its right
-                            p.L(ns) = cand;
-                            const int pa = za ? nib(p.prv, a_slot) : a_slot; // last surviving edge before the new one
-                            p.nxt = setnib(p.nxt, pa, ns);
-                            p.prv = setnib(p.prv, ns, pa);
-                            const int sb = zb ? nb : b_slot;                 // first surviving edge after the new one
-                            if (!zb) p.V(b_slot) = XB;                       // edge b keeps its end, starts at XB
-                            p.nxt = setnib(p.nxt, ns, sb);
-                            p.prv = setnib(p.prv, sb, ns);
-                            p.ord = setnib(o, mm, ns); // push!
-                            p.pos = setnib(p.pos, ns, mm);
-                            p.m = mm + 1;
-                            const double prr_new = ring_influence_rr(p, x); // voronoigrid.jl:76-78
-                            if (!(prr_new <= prr)) bad = true;              // scanning ahead relied on a non-increasing radius
-                            prr = prr_new;
-                        }
-                    }
-                }
-                if (bad) alive = false;
-            }
+#include "lv_clip_round.inc"
         }
         __syncwarp();
         if (a.force_anomaly && active && (slot % 1009) == 7) bad = true;
@@ -370,7 +192,196 @@ static int launch_fast(LvContext *c, const ClipArgs &a) {
     return LV_OK;
 }
 
+
+// ---- lane-refill variant ------------------------------------------------------------------------------------------------
+// The tile kernel above keeps a warp on its 32 polygons until the slowest one is done: with 8-14 cuts per polygon about a
+// third of the lanes idle in every round.  Here a lane whose polygon is finished PARKS it -- the raw ring: start vertices,
+// labels, links -- in global memory and takes the next unassigned slot of the warp's chunk, so the rounds run with nearly
+// all lanes busy.  The CSR rows, areas and centroids are produced afterwards by k_clip_emit, one thread per slot: a fully
+// convergent walk of the parked rings with the same warp-contiguous row placement (and the same checks) as the tile kernel.
+// Rounds, cuts and emission arithmetic are the same code (lv_clip_round.inc), hence the same bytes.
+#define RF_CHUNK 256 // slots per ticket
+#define RF_THR 6     // lanes without a live polygon that trigger a park + refill pass
+
+template <int MAXE, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_clip_refill(ClipArgs a, int nchunks) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2 *sv = (double2 *)smem;
+    int *sl = (int *)(sv + MAXE * BLOCK);
+    int *sq = sl + MAXE * BLOCK;
+    int *sqt = sq + QCAP * BLOCK;
+    LvPathNode *spath = (LvPathNode *)(sqt + QCAP * BLOCK);
+    const LvGridParams g = a.g;
+    for (int k = threadIdx.x; k < g.npath; k += BLOCK) spath[k] = a.path[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const double hpx = 0.5 * g.xperiod, hpy = 0.5 * g.yperiod;
+    const size_t nsl = (size_t)a.nslot;
+
+    Ring<MAXE, BLOCK> p;
+    p.sv = sv; p.sl = sl; p.m = 0; p.used = 0; p.ord = p.pos = p.nxt = p.prv = 0;
+    bool running = false, alive = false, active = false, bad = false, scan_done = true, nowork = false;
+    double2 x = make_double2(0.0, 0.0);
+    double prr = 0.0, slack = 0.0;
+    int slot = -1, k1 = 0, k2 = 0, t_scan = -1, s = 0, s_end = 0, t_end = g.npath, t_chk = -1, qh = 0, qn = 0;
+    int chunk_next = 0, chunk_end = 0; // the warp's current chunk (same values in every lane)
+
+    for (;;) {
+        // ---- park finished polygons
+        if (running && !alive) {
+            if (a.force_anomaly && (slot % 1009) == 7) bad = true;
+            if (bad) atomicOr(&a.flags[LVF_OVERFLOW], OVF_ANOMALY);
+            for (unsigned u = p.used; u; u &= u - 1) {
+                const int sk = __ffs(u) - 1;
+                a.park_v[(size_t)sk * nsl + slot] = p.V(sk);
+                a.park_l[(size_t)sk * nsl + slot] = p.L(sk);
+            }
+            a.park_nxt[slot] = p.nxt;
+            a.park_hdr[slot] = (bad ? 0 : p.m) | (nib(p.ord, 0) << 8); // degree, first edge of the sorted chain (IO.jl:35-48)
+            running = false;
+        }
+        __syncwarp();
+        // ---- hand idle lanes the next slots of the chunk
+        unsigned need = __ballot_sync(FULL, !running);
+        while (need && !nowork) {
+            const int avail = chunk_end - chunk_next;
+            if (avail <= 0) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&a.flags[LVF_TICKET], 1);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= nchunks) { nowork = true; break; }
+                chunk_next = t * RF_CHUNK;
+                chunk_end = chunk_next + RF_CHUNK < a.nslot ? chunk_next + RF_CHUNK : a.nslot;
+                continue;
+            }
+            const int rank = __popc(need & lt);
+            if (!running && rank < avail) {
+                slot = chunk_next + rank;
+                active = a.own[slot] != 0; // image / ghost slots have no polygon: their header stays 0 (memset)
+                if (active) {
+                    x = a.ent_xy[slot];
+                    alive = true; running = true; bad = false;
+                    prr = 0.0; k1 = k2 = 0;
+                    t_scan = -1; s = 0; s_end = 0; t_end = g.npath; t_chk = -1;
+                    scan_done = false; qh = 0; qn = 0;
+                    slack = 2e-15 * (fabs(x.x) + fabs(x.y));
+                    p.m = 0; p.used = 0; p.ord = p.pos = p.nxt = p.prv = 0;
+#include "lv_clip_init.inc"
+                }
+            }
+            const int asked = __popc(need);
+            chunk_next += asked < avail ? asked : avail;
+            need = __ballot_sync(FULL, !running);
+        }
+        if (!__any_sync(FULL, running)) break;
+        // ---- rounds (voronoicut!(grid, poly)  voronoigrid.jl:53-81) until enough lanes are free again
+        for (;;) {
+#include "lv_clip_round.inc"
+            const unsigned al = __ballot_sync(FULL, alive);
+            if (!al) break;
+            if (!nowork && __popc(~al) >= RF_THR) break;
+        }
+    }
+}
+
+// One thread per slot: CSR row + area + centroid from the parked ring.  Same walk, arithmetic and checks as the emission
+// part of k_clip_fast; rows of 32 consecutive slots are contiguous (one atomicAdd per warp).
+template <int MAXE>
+__global__ void __launch_bounds__(256) k_clip_emit(ClipArgs a) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const bool valid = slot < a.nslot;
+    const size_t nsl = (size_t)a.nslot;
+    const int hdr = valid ? a.park_hdr[slot] : 0;
+    const int deg = hdr & 0xff;
+    int inc = deg;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc, o2);
+        if (lane >= o2) inc += v;
+    }
+    const int tile_total = __shfl_sync(FULL, inc, 31);
+    int base = 0;
+    if (lane == 0 && tile_total > 0) base = atomicAdd(&a.flags[LVF_NNZ], tile_total);
+    base = __shfl_sync(FULL, base, 0);
+    const long long off = (long long)base + inc - deg;
+    if (!valid) return;
+    double area = 0.0, cx = 0.0, cy = 0.0;
+    const bool fits = (long long)base + tile_total <= a.cap_nnz;
+    if (!fits && deg > 0) atomicOr(&a.flags[LVF_OVERFLOW], OVF_NNZ);
+    if (deg > 0) {
+        const double2 x = a.ent_xy[slot];
+        const u64 nxt = a.park_nxt[slot];
+        int cur = (hdr >> 8) & 15;
+        const int start = cur;
+        double2 u = a.park_v[(size_t)cur * nsl + slot];
+        bool zero_len = false;
+        for (int k = 0; k < deg; k++) {
+            const int nx = nib(nxt, cur);
+            const double2 w = a.park_v[(size_t)nx * nsl + slot];
+            zero_len |= (u.x == w.x && u.y == w.y);
+            const double ax = u.x - x.x, ay = u.y - x.y, bx = w.x - x.x, by = w.y - x.y;
+            const double dA = 0.5 * fabs(ax * by - ay * bx); // polygon.jl:114-122, 201-203
+            area += dA;
+            cx += (dA * ((x.x + u.x) + w.x)) / 3.0;        // polygon.jl:210-219
+            cy += (dA * ((x.y + u.y) + w.y)) / 3.0;
+            if (fits) {
+                const int l = a.park_l[(size_t)cur * nsl + slot];
+                int cc = l;
+                if (l >= 0) cc = lv_col_of(a, l);
+                a.col[off + k] = cc;
+                a.v1[off + k] = u;
+                a.v2[off + k] = w;
+            }
+            cur = nx;
+            u = w;
+        }
+        if (cur != start || zero_len) atomicOr(&a.flags[LVF_OVERFLOW], OVF_ANOMALY);
+    }
+    a.rowptr[slot] = (int)off;
+    a.rdeg[slot] = (unsigned char)deg;
+    a.area[slot] = area;
+    a.cen[slot] = deg > 0 ? make_double2(cx / area, cy / area) : make_double2(0.0, 0.0);
+}
+
+template <int MAXE, int BLOCK, int MINB>
+static int launch_refill(LvContext *c, ClipArgs a) {
+    const int64_t nslot = c->nslot;
+    if (nslot == 0) return LV_OK;
+    // parking space: MAXE start vertices + labels per slot, links, header
+    LV_TRY(lv_ensure(c, (void **)&c->d_park_v, &c->cap_park_v, (int64_t)MAXE * nslot, sizeof(double2)));
+    LV_TRY(lv_ensure(c, (void **)&c->d_park_l, &c->cap_park_l, (int64_t)MAXE * nslot, sizeof(int)));
+    LV_TRY(lv_ensure(c, (void **)&c->d_park_nxt, &c->cap_park_n, nslot, sizeof(unsigned long long)));
+    LV_TRY(lv_ensure(c, (void **)&c->d_park_hdr, &c->cap_park_h, nslot, sizeof(int)));
+    a.park_v = (double2 *)c->d_park_v; a.park_l = (int *)c->d_park_l; a.park_nxt = (unsigned long long *)c->d_park_nxt; a.park_hdr = (int *)c->d_park_hdr;
+    LV_CUDA(c, cudaMemsetAsync(c->d_park_hdr, 0, sizeof(int) * (size_t)nslot, c->stream));
+    const size_t smem = (size_t)MAXE * BLOCK * (sizeof(double2) + sizeof(int)) + (size_t)2 * QCAP * BLOCK * sizeof(int) +
+                        sizeof(LvPathNode) * (size_t)c->gp.npath;
+    LV_CUDA(c, cudaFuncSetAttribute(k_clip_refill<MAXE, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nchunks = (int)((nslot + RF_CHUNK - 1) / RF_CHUNK);
+    int per_sm = 1;
+    LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_clip_refill<MAXE, BLOCK, MINB>, BLOCK, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)c->num_sms * per_sm;
+    const long long need = ((long long)nchunks * (RF_CHUNK / 32) + (BLOCK / 32) - 1) / (BLOCK / 32);
+    if (grid > need) grid = need;
+    k_clip_refill<MAXE, BLOCK, MINB><<<(int)grid, BLOCK, smem, c->stream>>>(a, nchunks);
+    k_clip_emit<MAXE><<<(int)((nslot + 255) / 256), 256, 0, c->stream>>>(a);
+    c->launches += 2;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// LV_CLIP_MODE=tile selects the tile kernel (one warp stays on 32 polygons), the default is the lane-refill kernel
 int lv_clip_launch_fast(LvContext *c, const ClipArgs &a, int level) {
-    if (level == 0) return launch_fast<12, 128, 6>(c, a);
-    return launch_fast<16, 128, 4>(c, a);
+    static const bool tile = [] { const char *m = getenv("LV_CLIP_MODE"); return m && !strcmp(m, "tile"); }();
+    if (tile) {
+        if (level == 0) return launch_fast<12, 128, 6>(c, a);
+        return launch_fast<16, 128, 4>(c, a);
+    }
+    if (level == 0) return launch_refill<12, 128, 6>(c, a);
+    return launch_refill<16, 128, 4>(c, a);
 }

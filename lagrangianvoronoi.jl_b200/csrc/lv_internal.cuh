@@ -75,6 +75,8 @@ struct LvContext {
     double *d_area = nullptr;                 // [nslot]
     double2 *d_cen = nullptr;                 // [nslot]
     unsigned long long *d_tile_state = nullptr; // look-back scan state of the clip kernel
+    void *d_park_v = nullptr, *d_park_l = nullptr, *d_park_nxt = nullptr, *d_park_hdr = nullptr; // parked rings of the lane-refill clip kernel
+    int64_t cap_park_v = 0, cap_park_l = 0, cap_park_n = 0, cap_park_h = 0;
     int64_t cap_tiles = 0;
     int *d_flags = nullptr; // [8] device status words, see LvFlag
     int *d_tickets = nullptr; // [8] last-block tickets of fused kernels (0 matvec, 1 update_r, 2 update_xp); [7] = a peer wait timed out
