@@ -375,9 +375,12 @@ static int launch_refill(LvContext *c, ClipArgs a) {
     return LV_OK;
 }
 
-// LV_CLIP_MODE=tile selects the tile kernel (one warp stays on 32 polygons), the default is the lane-refill kernel
+// The tile kernel (one warp stays on its 32 polygons) is the production kernel.  LV_CLIP_MODE=refill selects the lane-refill
+// variant: measured SLOWER on B200 (16.8M cells: 25.8 + 2.8 ms against 21.7 ms; 11.7 instead of 13.3 active lanes per
+// instruction, profiles/r2_clip_refill_16M_full.txt) -- refilled lanes are at different "ages" (young polygons scan, old ones
+// cut), so every round runs all three phases at partial occupancy, whereas a tile's 32 polygons age in lockstep.
 int lv_clip_launch_fast(LvContext *c, const ClipArgs &a, int level) {
-    static const bool tile = [] { const char *m = getenv("LV_CLIP_MODE"); return m && !strcmp(m, "tile"); }();
+    static const bool tile = [] { const char *m = getenv("LV_CLIP_MODE"); return !(m && !strcmp(m, "refill")); }();
     if (tile) {
         if (level == 0) return launch_fast<12, 128, 6>(c, a);
         return launch_fast<16, 128, 4>(c, a);
