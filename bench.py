@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "mesh+pressure step throughput (2 x Voronoi remesh + find_pressure, 10 x Krylov solve)"
 UNIT = "Mcell-steps/s"
+E2E_MODE = "pipeline"  # --e2e-mode
 MATVEC_BYTES_PER_CELL = 100.0   # rowptr 4 + 6*(col 4 + w 8) + diag 8 + x 8 + y 8
 CG_BYTES_PER_CELL_ITER = 172.0  # matvec 100 + 3 vector updates x 24
 REMESH_BYTES_PER_CELL = 250.0
@@ -56,6 +57,8 @@ def parse():
     ap.add_argument("--ref-budget", type=float, default=300.0, help="--impl reference: wall-clock budget of the timed steps, s")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "all"],
+                    help="host-buffer leg: pipeline = lv_set_async_edges(h, 3) (deferred remesh, 20 B/edge wire format), all = mode 2")
     ap.add_argument("--no-strong", action="store_true", help="skip the 64M strong-scaling leg")
     ap.add_argument("--strong-side", type=int, default=STRONG_SIDE)
     ap.add_argument("--strong-steps", type=int, default=5, help="timed steps of the strong leg (min with --steps)")
@@ -274,8 +277,8 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
             # Every mesh output (rowptr, areas, centroids, edge records) is downloaded lazily on a second stream so that
             # it overlaps the next remesh and the pressure solve; the step ends only when every byte is in host memory.
             g.P = p_in.pop() if p_in else g.P
-            lv.remesh(g, lazy="all")
-            lv.remesh(g, lazy="all")
+            lv.remesh(g, lazy=E2E_MODE)
+            lv.remesh(g, lazy=E2E_MODE)
             lv.find_pressure(solver, dt, args.niter)
             lv.wait_edges(g)
             return int(solver.iters.sum())
@@ -292,9 +295,15 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
         ms_e = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
         nnz = int(g.rowptr[-1])
         h2d = 2 * n * 16 + n * 8 * 6                     # 2 x positions + mass, rho, c2, P, v(2)
-        d2h = 2 * ((n + 1) * 8 + nnz * 40 + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
+        # bytes that cross PCIe: the pipelined mode ships 20 B per edge (start vertex + label word, + 16 B per 2^20-edge
+        # chunk) and host threads of the library expand them into the 40-byte records the caller reads
+        per_edge = 20 if E2E_MODE == "pipeline" else 40
+        d2h = 2 * ((n + 1) * 8 + nnz * per_edge + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
         e2e = {"value": n * steps / (ms_e / 1e3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / steps, "contract": "positions + fields up; rowptr, 40-B edge records, areas, centroids (x2) and P down"}
+               "ms_per_step": ms_e / steps, "mode": E2E_MODE,
+               "contract": "positions + fields up; rowptr, 40-B edge records, areas, centroids (x2) and P delivered into the caller's "
+                           "host buffers" + ("; pipelined: uploads overlap the queued clip kernel, edges cross PCIe as 20 B and are "
+                                             "expanded by host threads of the library" if E2E_MODE == "pipeline" else "")}
         # size-independent properties of the result at the full bench size, checked on the host copies after the timed
         # region: Euler count of a periodic triangulation (sum of degrees = 6n), the cells tile the unit box, every
         # pass converged, pressures are finite
@@ -672,11 +681,12 @@ lvcheck = None
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, E2E_MODE
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)  # native libraries (NCCL prints its version banner on stdout) must not pollute the JSON channel
     a = parse()
+    E2E_MODE = a.e2e_mode
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -99,10 +99,24 @@ int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap
  * on = 2 ("everything lazy"): rowptr, areas and centroids travel in the background too, ahead of the edge records on the
  * same copy stream; lv_remesh returns as soon as the device-side conversion is queued and NO output buffer may be read
  * before lv_mesh_wait.  For callers that launch the next device call (a second remesh, find_pressure!) straight away.
+ * on = 3 ("pipelined", lv_pipeline.cu): lv_remesh additionally returns while its clipping kernel is still QUEUED (*nnz = -1;
+ * lv_mesh_nnz after lv_mesh_wait).  The next lv_remesh / lv_find_pressure issues its uploads on a separate stream first and
+ * only then completes the pending remesh, so host->device copies overlap the kernel; errors of a deferred remesh
+ * ("The Voronoi Mesh has been destroyed.", capacity) are reported by that next call or by lv_mesh_wait.  The mesh crosses
+ * PCIe as 20 B per edge (start vertex + 32-bit label word; the end vertex of an edge is the start vertex of its successor
+ * in the chain sort_edges! leaves, checked bit for bit on the device) and host threads of the library (LV_HOST_THREADS,
+ * default min(16, cores - 2)) expand it into the caller's 40-byte records; a mesh with an open chain is delivered as full
+ * records instead.  NO output buffer may be read before lv_mesh_wait.
  * Environment switches (diagnostics): LV_DIRECT_STORE=0 disables the direct stores, LV_FLAG_MODE=memcpy reads status
  * words with cudaMemcpy instead of mapped memory. */
 int32_t lv_set_async_edges(LvHandle h, int32_t on);
 int32_t lv_mesh_wait(LvHandle h);
+/* Decoder of the 20 B/edge wire format of the pipelined mode (host-only, no device needed): `len` consecutive edges of
+ * the label-order edge list; v1[2*(len + has_next)] = their start vertices (+ the next edge's when has_next), word[len]:
+ * bits 0-29 = 1-based label or wall number 1..4, bit 30 = wall, bit 31 = last edge of its row; row_start = start vertex
+ * of the row the first edge belongs to.  Writes the 40-byte records (v2 = successor's v1, or the row's first v1). */
+int32_t lv_wire_expand(const double *v1, const uint32_t *word, int64_t len, int32_t has_next, const double row_start[2],
+                       LvEdge *out);
 /* which kernel produced the current mesh: level 0/1 = linked-slot kernel (12/16 slots), 2/3/4 =
  * edge-list kernel (16/32/128 edges); anomalies = remeshes replayed by the edge-list kernel because
  * the linked-slot kernel met a degenerate configuration (results are identical either way) */

@@ -28,7 +28,7 @@ PROF_SLOTS = {"cells": 0, "clip": 1, "assemble": 2, "matvec": 3, "vecops": 4}
 # every symbol include/lv_capi.h declares; tests check the library exports all of them
 SYMBOLS = [
     "lv_create", "lv_destroy", "lv_last_error", "lv_set_rects", "lv_grid_info", "lv_magic_path", "lv_set_stream",
-    "lv_sync", "lv_remesh", "lv_remesh_dev", "lv_mesh_nnz", "lv_mesh_download", "lv_mesh_faces", "lv_mesh_hash", "lv_boundary_edges", "lv_set_boundary_velocity", "lv_clip_info", "lv_set_async_edges", "lv_mesh_wait",
+    "lv_sync", "lv_remesh", "lv_remesh_dev", "lv_mesh_nnz", "lv_mesh_download", "lv_mesh_faces", "lv_mesh_hash", "lv_boundary_edges", "lv_set_boundary_velocity", "lv_clip_info", "lv_set_async_edges", "lv_mesh_wait", "lv_wire_expand",
     "lv_pressure_create", "lv_pressure_destroy", "lv_fields_upload", "lv_fields_upload_dev", "lv_pressure_download",
     "lv_pressure_assemble", "lv_pressure_operator", "lv_pressure_matvec", "lv_pressure_rhs", "lv_find_pressure",
     "lv_find_pressure_dev", "lv_pressure_solve", "lv_prof_enable", "lv_prof_reset", "lv_prof_get",
@@ -99,6 +99,7 @@ def load_library() -> C.CDLL:
     L.lv_clip_info.argtypes = [vp, i32p, ip]
     L.lv_set_async_edges.argtypes = [vp, C.c_int32]
     L.lv_mesh_wait.argtypes = [vp]
+    L.lv_wire_expand.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
     L.lv_pressure_create.argtypes = [vp]
     L.lv_pressure_destroy.argtypes = [vp]
     L.lv_fields_upload.argtypes = [vp, vp, vp, vp, vp, vp]

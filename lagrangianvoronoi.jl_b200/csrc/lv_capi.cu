@@ -214,6 +214,7 @@ int32_t lv_create(const LvGridDesc *d, int32_t device, LvHandle *out) {
 int32_t lv_destroy(LvHandle c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
+    lv_pipe_destroy(c); // joins the download threads before anything they read is freed
     cudaDeviceSynchronize();
     void *bufs[] = {c->d_path, c->d_xy, c->d_cell_cnt, c->d_cell_start, c->d_ent_label, c->d_ent_xy, c->d_prim_of_label,
                     c->d_rowptr, c->d_col, c->d_v1, c->d_v2, c->d_area, c->d_cen, c->d_tile_state, c->d_park_v, c->d_park_l, c->d_park_nxt, c->d_park_hdr, c->d_flags, c->d_tickets, c->d_bdry_ptr, c->d_vbc_edge, c->d_bf_on, c->d_scratch,
@@ -273,7 +274,7 @@ int32_t lv_magic_path(LvHandle c, int64_t cap, int64_t *i1, int64_t *i2, double 
 
 int32_t lv_set_stream(LvHandle c, void *stream, int32_t own) {
     if (!c) return LV_EINVAL;
-    cudaSetDevice(c->device);
+    LV_ENTER(c);
     cudaStreamSynchronize(c->stream);
     // a NULL stream is a real stream (the legacy default stream torch uses): it must not fall back to the
     // handle's non-blocking stream, which does not order against it
@@ -283,7 +284,7 @@ int32_t lv_set_stream(LvHandle c, void *stream, int32_t own) {
 
 int32_t lv_sync(LvHandle c) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     return LV_OK;
 }
@@ -325,7 +326,7 @@ extern "C" {
 
 int32_t lv_remesh_dev(LvHandle c, int64_t n, const double *xy_dev) {
     if (!c || (n > 0 && !xy_dev)) return lv_set_error(c, LV_EINVAL, "null argument");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(ensure_generators(c, n, false));
     c->xy = (const double2 *)xy_dev; // used in place: positions are only read
     int st = lv_remesh_common(c, n);
@@ -343,6 +344,7 @@ int32_t lv_clip_info(LvHandle c, int32_t *level, int64_t *anomalies) {
 
 int32_t lv_mesh_nnz(LvHandle c, int64_t *nnz) {
     if (!c || !nnz) return LV_EINVAL;
+    LV_ENTER(c);
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     *nnz = c->nnz;
     return LV_OK;
@@ -402,6 +404,7 @@ void *lv_mapped_alias(const void *host) {
 
 int lv_mesh_to_labels(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
+    if (c->pipe) LV_TRY(lv_pipe_drain(c)); // the download threads of the pipelined mode read the same staging buffers
     const int64_t n = c->n, nnz = c->nnz;
     if (edges && cap < nnz) return lv_set_error(c, LV_ECAPACITY, "edge buffer too small: nnz = %lld, cap = %lld", (long long)nnz, (long long)cap);
     if (n == 0) { if (rowptr) rowptr[0] = 0; return LV_OK; }
@@ -487,23 +490,26 @@ extern "C" int32_t lv_mesh_wait(LvHandle c);
 // host and stream the edge records in the background; lv_mesh_wait blocks until they have landed
 int32_t lv_set_async_edges(LvHandle c, int32_t on) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (on && !c->copy_stream) {
         LV_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_conv_done, cudaEventDisableTiming));
         LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_done[0], cudaEventDisableTiming));
         LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_done[1], cudaEventDisableTiming));
     }
-    if (!on) LV_TRY(lv_mesh_wait(c));
-    c->async_edges = on != 0;
+    if (!on || on == 3 || c->pipe_mode) LV_TRY(lv_mesh_wait(c));
+    if (on == 3) LV_TRY(lv_pipe_enable(c));
+    c->pipe_mode = on == 3;
+    c->async_edges = on == 1 || on == 2;
     c->async_all = on == 2;
     return LV_OK;
 }
 int32_t lv_mesh_wait(LvHandle c) {
     if (!c) return LV_EINVAL;
+    if (c->pipe) { LV_CUDA(c, cudaSetDevice(c->device)); LV_TRY(lv_pipe_wait(c)); }
     for (int k = 0; k < 2; k++)
         if (c->stage_pending[k]) {
-            LV_CUDA(c, cudaSetDevice(c->device));
+            LV_ENTER(c);
             LV_CUDA(c, cudaEventSynchronize(c->ev_stage_done[k]));
             c->stage_pending[k] = false;
         }
@@ -512,14 +518,22 @@ int32_t lv_mesh_wait(LvHandle c) {
 
 int32_t lv_mesh_download(LvHandle c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return lv_mesh_to_labels(c, rowptr, edges, cap, area, centroid);
 }
 
 int32_t lv_remesh(LvHandle c, int64_t n, const double *xy, int64_t *rowptr, LvEdge *edges, int64_t cap, int64_t *nnz,
                   double *area, double *centroid) {
     if (!c || (n > 0 && !xy)) return lv_set_error(c, LV_EINVAL, "null argument");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    if (c->pipe_mode && n > 0 && (rowptr || edges || area || centroid)) {
+        // pipelined mode: the upload is issued BEFORE the previous remesh is completed (lv_pipe_remesh), the call returns
+        // with the clip kernel queued, and *nnz is not known yet (-1; lv_mesh_nnz after lv_mesh_wait)
+        LV_CUDA(c, cudaSetDevice(c->device));
+        LV_TRY(ensure_generators(c, n, false));
+        if (nnz) *nnz = -1;
+        return lv_pipe_remesh(c, n, xy, rowptr, edges, cap, area, centroid);
+    }
+    LV_ENTER(c);
     LV_TRY(ensure_generators(c, n, true));
     if (n > 0) LV_CUDA(c, cudaMemcpyAsync(c->d_xy, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     c->xy = c->d_xy;
@@ -543,7 +557,7 @@ __global__ void __launch_bounds__(256) k_faces(int64_t nnz, const double2 *__res
 
 int32_t lv_mesh_faces(LvHandle c, double *length, double *midpoint, int64_t cap) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     const int64_t n = c->n, nnz = c->nnz;
     if (cap < nnz) return lv_set_error(c, LV_ECAPACITY, "face buffer too small");
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(256) k_mesh_hash(int nslot, const unsigned cha
 
 extern "C" int32_t lv_mesh_hash(LvHandle c, const int32_t *global_label_dev, uint64_t out[6]) {
     if (!c || !out) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->mesh_valid) return lv_set_error(c, LV_EINVAL, "no valid mesh: call lv_remesh first");
     for (int k = 0; k < 6; k++) out[k] = 0;
     if (c->nslot == 0) return LV_OK;
@@ -665,7 +679,7 @@ int lv_bdry_index(LvContext *c) {
 
 extern "C" int32_t lv_boundary_edges(LvHandle c, int64_t *count, double *midpoint, int64_t *label, int64_t *polygon, int64_t cap) {
     if (!c || !count) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(lv_bdry_index(c));
     *count = c->n_bedge;
     if (!midpoint && !label && !polygon) return LV_OK;
@@ -694,7 +708,7 @@ extern "C" int32_t lv_boundary_edges(LvHandle c, int64_t *count, double *midpoin
 // NULL returns to the four per-wall constants
 extern "C" int32_t lv_set_boundary_velocity(LvHandle c, const double *vbc_edge, int64_t n_edge) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     c->bvel_valid = false;
     if (!vbc_edge) { c->vbc_edge_on = false; return LV_OK; }
     LV_TRY(lv_bdry_index(c));

@@ -267,71 +267,110 @@ static int launch_clip(LvContext *c, const ClipArgs &a) {
 // (sticky) capacity level up; an anomaly reported by the linked-slot kernel reruns this remesh
 // with the edge-list kernel, which replays the reference literally.
 // LV_CLIP_MODE=plain forces the edge-list kernel (used by the tests to cross-check both).
-int lv_clip_run(LvContext *c) {
+// One attempt: buffers for need_nnz edges, flag reset, launch at `level` (nothing is synchronised).
+static int clip_attempt(LvContext *c, int level, int64_t need_nnz) {
     const int64_t nslot = c->nslot;
-    // edge buffers: 6n on a torus (Euler), fewer with walls plus the wall edges; grow on demand
-    int64_t need_nnz = 7 * nslot + 1024;
+    if (need_nnz > c->cap_nnz) {
+        int64_t c1 = c->cap_nnz, c2 = c->cap_nnz, c3 = c->cap_nnz;
+        LV_TRY(lv_ensure(c, (void **)&c->d_col, &c1, need_nnz, sizeof(int)));
+        LV_TRY(lv_ensure(c, (void **)&c->d_v1, &c2, need_nnz, sizeof(double2)));
+        LV_TRY(lv_ensure(c, (void **)&c->d_v2, &c3, need_nnz, sizeof(double2)));
+        c->cap_nnz = need_nnz;
+    }
+    const int block = level <= 1 ? 32 : (level == 2 ? 128 : (level == 3 ? 64 : 32)); // tile size
+    const int64_t ntiles = (nslot + block - 1) / block;
+    LV_TRY(lv_ensure(c, (void **)&c->d_tile_state, &c->cap_tiles, ntiles + 1, sizeof(unsigned long long)));
+    LV_CUDA(c, cudaMemsetAsync(c->d_tile_state, 0, sizeof(unsigned long long) * (size_t)(ntiles + 1), c->stream));
+    LV_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream));
+    ClipArgs a;
+    a.g = c->gp;
+    a.path = c->d_path;
+    a.cell_start = c->d_cell_start;
+    a.ent_label = c->d_ent_label;
+    a.ent_xy = c->d_ent_xy;
+    a.prim_of_label = c->d_prim_of_label;
+    a.own = c->d_own;
+    a.nslot = (int)nslot;
+    a.rowptr = c->d_rowptr;
+    a.rdeg = c->d_deg;
+    a.col = c->d_col;
+    a.v1 = c->d_v1;
+    a.v2 = c->d_v2;
+    a.area = c->d_area;
+    a.cen = c->d_cen;
+    a.tile_state = c->d_tile_state;
+    a.flags = c->d_flags;
+    a.cap_nnz = c->cap_nnz;
+    a.park_v = nullptr; a.park_l = nullptr; a.park_nxt = nullptr; a.park_hdr = nullptr;
+    { const char *fa = getenv("LV_CLIP_FORCE_ANOMALY"); a.force_anomaly = fa && fa[0] == '1'; }
+    {
+        LvProfScope prof(c, LV_PROF_CLIP);
+        if (level <= 1) LV_TRY(lv_clip_launch_fast(c, a, level));
+        else if (level == 2) LV_TRY((launch_clip<16, 128>(c, a)));
+        else if (level == 3) LV_TRY((launch_clip<32, 64>(c, a)));
+        else LV_TRY((launch_clip<128, 32>(c, a)));
+    }
+    c->clip_last_level = level;
+    return LV_OK;
+}
+
+// Reads the status words of an attempt (hf: host copy).  done: the mesh stands (c->nnz set); otherwise level / need_nnz
+// say how to try again.
+static int clip_decide(LvContext *c, const int *hf, int &level, int64_t &need_nnz, bool &done) {
+    done = false;
+    if (c->nslot == 0) { c->nnz = 0; done = true; return LV_OK; }
+    if (hf[LVF_NAN]) return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf");
+    if (hf[LVF_DESTROYED]) return lv_set_error(c, LV_EDESTROYED, "The Voronoi Mesh has been destroyed.");
+    const int ov = hf[LVF_OVERFLOW];
+    if (ov == 0) { c->nnz = hf[LVF_NNZ]; done = true; return LV_OK; }
+    if (ov & OVF_NNZ) need_nnz = (int64_t)hf[LVF_NNZ] + 1024;
+    if (ov & OVF_POLY) { // capacity: sticky
+        if (level >= 4) return lv_set_error(c, LV_ECAPACITY, "polygon with more than 128 edges during clipping");
+        level = level == 0 ? 1 : (level < 3 ? 3 : 4);
+        c->clip_level = level;
+    } else if (ov & OVF_ANOMALY) { // exactness: this remesh only
+        c->clip_anomalies++;
+        level = level == 0 ? 2 : 3;
+    }
+    return LV_OK;
+}
+
+static int clip_first_level(const LvContext *c) {
     const char *mode = getenv("LV_CLIP_MODE");
     const bool force_plain = mode && !strcmp(mode, "plain");
     int level = c->clip_level;
     if (force_plain && level < 2) level = 2;
-    for (int attempt = 0; attempt < 8; attempt++) {
-        if (need_nnz > c->cap_nnz) {
-            int64_t c1 = c->cap_nnz, c2 = c->cap_nnz, c3 = c->cap_nnz;
-            LV_TRY(lv_ensure(c, (void **)&c->d_col, &c1, need_nnz, sizeof(int)));
-            LV_TRY(lv_ensure(c, (void **)&c->d_v1, &c2, need_nnz, sizeof(double2)));
-            LV_TRY(lv_ensure(c, (void **)&c->d_v2, &c3, need_nnz, sizeof(double2)));
-            c->cap_nnz = need_nnz;
-        }
-        const int block = level <= 1 ? 32 : (level == 2 ? 128 : (level == 3 ? 64 : 32)); // tile size
-        const int64_t ntiles = (nslot + block - 1) / block;
-        LV_TRY(lv_ensure(c, (void **)&c->d_tile_state, &c->cap_tiles, ntiles + 1, sizeof(unsigned long long)));
-        LV_CUDA(c, cudaMemsetAsync(c->d_tile_state, 0, sizeof(unsigned long long) * (size_t)(ntiles + 1), c->stream));
-        LV_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream));
-        ClipArgs a;
-        a.g = c->gp;
-        a.path = c->d_path;
-        a.cell_start = c->d_cell_start;
-        a.ent_label = c->d_ent_label;
-        a.ent_xy = c->d_ent_xy;
-        a.prim_of_label = c->d_prim_of_label;
-        a.own = c->d_own;
-        a.nslot = (int)nslot;
-        a.rowptr = c->d_rowptr;
-        a.rdeg = c->d_deg;
-        a.col = c->d_col;
-        a.v1 = c->d_v1;
-        a.v2 = c->d_v2;
-        a.area = c->d_area;
-        a.cen = c->d_cen;
-        a.tile_state = c->d_tile_state;
-        a.flags = c->d_flags;
-        a.cap_nnz = c->cap_nnz;
-        a.park_v = nullptr; a.park_l = nullptr; a.park_nxt = nullptr; a.park_hdr = nullptr;
-        { const char *fa = getenv("LV_CLIP_FORCE_ANOMALY"); a.force_anomaly = fa && fa[0] == '1'; }
-        {
-            LvProfScope prof(c, LV_PROF_CLIP);
-            if (level <= 1) LV_TRY(lv_clip_launch_fast(c, a, level));
-            else if (level == 2) LV_TRY((launch_clip<16, 128>(c, a)));
-            else if (level == 3) LV_TRY((launch_clip<32, 64>(c, a)));
-            else LV_TRY((launch_clip<128, 32>(c, a)));
-        }
-        c->clip_last_level = level;
+    return level;
+}
+
+static int clip_loop(LvContext *c, int level, int64_t need_nnz, int attempts) {
+    for (int attempt = 0; attempt < attempts; attempt++) {
+        LV_TRY(clip_attempt(c, level, need_nnz));
         LV_TRY(lv_publish_flags(c, nullptr));
-        if (nslot == 0) { c->nnz = 0; return LV_OK; }
-        if (c->h_flags[LVF_NAN]) return lv_set_error(c, LV_ENAN, "generator position is NaN or Inf");
-        if (c->h_flags[LVF_DESTROYED]) return lv_set_error(c, LV_EDESTROYED, "The Voronoi Mesh has been destroyed.");
-        const int ov = c->h_flags[LVF_OVERFLOW];
-        if (ov == 0) { c->nnz = c->h_flags[LVF_NNZ]; return LV_OK; }
-        if (ov & OVF_NNZ) need_nnz = (int64_t)c->h_flags[LVF_NNZ] + 1024;
-        if (ov & OVF_POLY) { // capacity: sticky
-            if (level >= 4) return lv_set_error(c, LV_ECAPACITY, "polygon with more than 128 edges during clipping");
-            level = level == 0 ? 1 : (level < 3 ? 3 : 4);
-            c->clip_level = level;
-        } else if (ov & OVF_ANOMALY) { // exactness: this remesh only
-            c->clip_anomalies++;
-            level = level == 0 ? 2 : 3;
-        }
+        bool done = false;
+        LV_TRY(clip_decide(c, c->h_flags, level, need_nnz, done));
+        if (done) return LV_OK;
     }
     return lv_set_error(c, LV_ECAPACITY, "clip kernel did not fit after retries");
+}
+
+int lv_clip_run(LvContext *c) {
+    // edge buffers: 6n on a torus (Euler), fewer with walls plus the wall edges; grow on demand
+    return clip_loop(c, clip_first_level(c), 7 * c->nslot + 1024, 8);
+}
+
+// Pipelined host-buffer mode (lv_pipeline.cu): the first attempt is only queued -- its status words are stored into a
+// snapshot in mapped pinned memory by a kernel behind it -- and lv_clip_resume looks at them once the host gets there.
+int lv_clip_attempt_first(LvContext *c) {
+    return clip_attempt(c, clip_first_level(c), 7 * c->nslot + 1024);
+}
+int lv_clip_resume(LvContext *c, const int *snap, bool *replayed) {
+    int level = c->clip_last_level;
+    int64_t need_nnz = c->cap_nnz;
+    bool done = false;
+    *replayed = false;
+    LV_TRY(clip_decide(c, snap, level, need_nnz, done));
+    if (done) return LV_OK;
+    *replayed = true;
+    return clip_loop(c, level, need_nnz, 7);
 }

@@ -181,7 +181,7 @@ int32_t lv_comm_unique_id(uint8_t *out128) {
 
 int32_t lv_comm_init(LvHandle c, int32_t rank, int32_t nranks, const uint8_t *id128) {
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return lv_set_error(c, LV_EINVAL, "bad communicator arguments");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     std::string err;
     if (!load_nccl(err)) return lv_set_error(c, LV_ECUDA, "%s", err.c_str());
     ncclUniqueId id;
@@ -200,7 +200,7 @@ int32_t lv_comm_init(LvHandle c, int32_t rank, int32_t nranks, const uint8_t *id
 int32_t lv_halo_plan(LvHandle c, int32_t npeers, const int32_t *peer_rank, const int64_t *send_count, const int32_t *send_slots_dev,
                      const int64_t *recv_count, const int32_t *recv_slots_dev) {
     if (!c || npeers < 0) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     c->peers.clear();
     int64_t so = 0, ro = 0;
     for (int k = 0; k < npeers; k++) {
@@ -233,7 +233,7 @@ int32_t lv_halo_plan(LvHandle c, int32_t npeers, const int32_t *peer_rank, const
 // CUDA IPC handle (64 B) of this rank's allreduce mailbox; lv_mailbox_plan maps the mailboxes of all ranks
 int32_t lv_mailbox_export(LvHandle c, uint8_t *out64) {
     if (!c || !out64) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->d_mailbox) {
         LV_CUDA(c, cudaMalloc(&c->d_mailbox, sizeof(MailSlot) * 2 * MB_MAX_RANKS));
         LV_CUDA(c, cudaMemset(c->d_mailbox, 0, sizeof(MailSlot) * 2 * MB_MAX_RANKS));
@@ -246,7 +246,7 @@ int32_t lv_mailbox_export(LvHandle c, uint8_t *out64) {
 
 int32_t lv_mailbox_plan(LvHandle c, int32_t nranks, const uint8_t *handles /* nranks x 64 */) {
     if (!c || !c->comm || nranks != c->nranks || nranks > MB_MAX_RANKS) return lv_set_error(c, LV_EINVAL, "lv_mailbox_plan: bad arguments");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (c->mailbox_ready && !memcmp(c->mailbox_handles, handles, 64 * (size_t)nranks)) return LV_OK;
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     close_mailboxes(c);
@@ -282,7 +282,7 @@ int32_t lv_peer_disable(LvHandle c) {
 // then lv_destroy: memory exported over CUDA IPC must not be freed while an importer still has it mapped.
 int32_t lv_peer_close(LvHandle c) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     lv_strip_unmap(c);
     close_mailboxes(c);
@@ -292,7 +292,7 @@ int32_t lv_peer_close(LvHandle c) {
 // exchange a caller's slot-ordered device vector (tests; the solver calls lv_halo_exchange directly)
 int32_t lv_halo_exchange_dev(LvHandle c, double *vec_dev, int32_t ncomp) {
     if (!c || !vec_dev || (ncomp != 1 && ncomp != 2)) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return lv_halo_exchange(c, vec_dev, ncomp);
 }
 

@@ -40,8 +40,14 @@ struct LvProfSlot {
     int64_t launches = 0;
 };
 
+struct LvPipe; // lv_pipeline.cu
+
 struct LvContext {
     int device = 0;
+    // pipelined host-buffer mode (lv_set_async_edges(h, 3), lv_pipeline.cu): pipe_pending = the last remesh is only
+    // queued; lv_pipe_finish completes it (every entry point does that first, see LV_ENTER)
+    LvPipe *pipe = nullptr;
+    bool pipe_mode = false, pipe_pending = false;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     std::string err;
     // grid (voronoigrid.jl:14-25)
@@ -212,6 +218,22 @@ int lv_set_error(LvContext *c, int code, const char *fmt, ...);
         int _s = (expr);                   \
         if (_s != LV_OK) return _s;        \
     } while (0)
+
+// entry-point prologue: select the device and complete a deferred remesh of the pipelined mode
+int lv_pipe_finish(LvContext *c);
+#define LV_ENTER(c)                                             \
+    do {                                                        \
+        LV_CUDA((c), cudaSetDevice((c)->device));               \
+        if ((c)->pipe_pending) LV_TRY(lv_pipe_finish(c));       \
+    } while (0)
+int lv_pipe_enable(LvContext *c);
+int lv_pipe_remesh(LvContext *c, int64_t n, const double *xy, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid);
+int lv_pipe_wait(LvContext *c);  // deferred remesh completed and every queued download delivered
+int lv_pipe_drain(LvContext *c); // every queued download delivered
+bool lv_pipe_busy(const LvContext *c);
+void lv_pipe_destroy(LvContext *c);
+int lv_pipe_upload_begin(LvContext *c, const double *const src[5], const int nc[5], const double *dev[5]);
+int lv_pipe_upload_join(LvContext *c);
 
 int lv_ensure(LvContext *c, void **ptr, int64_t *cap, int64_t need, size_t elt); // grow-only device buffer
 int lv_alloc(LvContext *c, void **ptr, size_t bytes);

@@ -1119,12 +1119,12 @@ extern "C" {
 
 int32_t lv_pressure_create(LvHandle c) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return lv_pr_ensure(c);
 }
 int32_t lv_pressure_destroy(LvHandle c) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     double **one[] = {&c->d_mass, &c->d_rho, &c->d_c2, &c->d_P, &c->d_diag, &c->d_dinv, &c->d_b, &c->d_bvel, &c->d_vec[0], &c->d_vec[1],
                       &c->d_vec[2], &c->d_vec[3], &c->d_vec[4], &c->d_vec[5], &c->d_vec[6], &c->d_vec[7]};
@@ -1139,7 +1139,10 @@ int32_t lv_pressure_destroy(LvHandle c) {
     return LV_OK;
 }
 
-static int upload_fields(LvContext *c, const double *mass, const double *rho, const double *c2, const double *P, const double *v, bool dev) {
+// staged != NULL: the five label-order arrays are already on their way into the device staging buffer on the upload stream
+// of the pipelined mode (lv_pipe_upload_begin); the gathers wait for that stream
+static int upload_fields(LvContext *c, const double *mass, const double *rho, const double *c2, const double *P, const double *v, bool dev,
+                         const double *const *staged = nullptr) {
     LV_TRY(lv_pr_ensure(c));
     const int64_t n = c->n;
     struct Item { const double *src; double *dst; int nc; double fill; };
@@ -1148,13 +1151,14 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
     // run back to back on the copy engine and no cudaMalloc / cudaFree (device-wide sync) sits on the path
     char *stage = nullptr;
     const size_t nn = (size_t)(n > 0 ? n : 1);
+    if (staged) { dev = true; LV_TRY(lv_pipe_upload_join(c)); }
     if (!dev) LV_TRY(lv_io_stage(c, (void **)&stage, sizeof(double) * 6 * nn));
     int st = LV_OK;
     size_t off = 0;
     const double *src_dev[5];
     int k = 0;
     for (const Item &it : items) {
-        src_dev[k] = it.src;
+        src_dev[k] = staged ? staged[k] : it.src;
         if (it.src && !dev) {
             cudaError_t e = cudaMemcpyAsync(stage + off, it.src, sizeof(double) * (size_t)it.nc * (size_t)n, cudaMemcpyHostToDevice, c->stream);
             if (e != cudaSuccess) { st = lv_set_error(c, LV_ECUDA, "field upload failed: %s", cudaGetErrorString(e)); break; }
@@ -1169,7 +1173,7 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
         if (it.src) st = lv_gather_to_slots(c, src_dev[k], it.dst, it.nc, it.fill);
         k++;
     }
-    if (!dev) cudaStreamSynchronize(c->stream); // the host buffers may be reused as soon as we return
+    if (!dev || staged) cudaStreamSynchronize(c->stream); // the host buffers may be reused as soon as we return
     // neighbours' density, pressure and velocity across the strip edges
     if (st == LV_OK && rho) st = lv_halo_exchange(c, c->d_rho, 1);
     if (st == LV_OK && P) st = lv_halo_exchange(c, c->d_P, 1);
@@ -1182,12 +1186,12 @@ static int upload_fields(LvContext *c, const double *mass, const double *rho, co
 
 int32_t lv_fields_upload(LvHandle c, const double *mass, const double *rho, const double *c2, const double *P, const double *v) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return upload_fields(c, mass, rho, c2, P, v, false);
 }
 int32_t lv_fields_upload_dev(LvHandle c, const double *mass, const double *rho, const double *c2, const double *P, const double *v) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return upload_fields(c, mass, rho, c2, P, v, true);
 }
 
@@ -1196,7 +1200,7 @@ static int download_slots(LvContext *c, const double *src_slot, double *dst_host
     if (n == 0) return LV_OK;
     // while an edge view is still streaming to the host the copy engine is taken: scatter straight into the caller's
     // buffer when it is pinned (mapped), otherwise through the staging buffer + cudaMemcpy
-    double *direct = (c->stage_pending[0] || c->stage_pending[1]) ? (double *)lv_mapped_alias(dst_host) : nullptr;
+    double *direct = (c->stage_pending[0] || c->stage_pending[1] || lv_pipe_busy(c)) ? (double *)lv_mapped_alias(dst_host) : nullptr;
     void *stage = direct;
     if (!direct) LV_TRY(lv_io_stage(c, &stage, sizeof(double) * (size_t)nc * (size_t)n));
     int st = lv_scatter_to_labels(c, src_slot, (double *)stage, nc);
@@ -1212,14 +1216,14 @@ static int download_slots(LvContext *c, const double *src_slot, double *dst_host
 
 int32_t lv_pressure_download(LvHandle c, double *P_out) {
     if (!c || !P_out) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->d_P) return lv_set_error(c, LV_EINVAL, "no pressure workspace");
     return download_slots(c, c->d_P, P_out, 1);
 }
 
 int32_t lv_pressure_assemble(LvHandle c, double dt) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return lv_pr_assemble(c, dt);
 }
 
@@ -1254,7 +1258,7 @@ __global__ void __launch_bounds__(256) k_op_deg(int64_t n, const int *__restrict
 
 int32_t lv_pressure_operator(LvHandle c, int64_t *rowptr, int64_t *col, double *w, int64_t cap, double *diag) {
     if (!c || !rowptr) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     const int64_t n = c->n, nnz = c->nnz;
     if (n == 0) { rowptr[0] = 0; return LV_OK; }
@@ -1298,7 +1302,7 @@ int32_t lv_pressure_operator(LvHandle c, int64_t *rowptr, int64_t *col, double *
 
 int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
     if (!c || !x || !y) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     const int64_t n = c->n;
     if (n == 0) return LV_OK;
@@ -1317,7 +1321,7 @@ int32_t lv_pressure_matvec(LvHandle c, const double *x, double *y) {
 
 int32_t lv_pressure_rhs(LvHandle c, double dt, int32_t gp_step, const double *vbc_wall, double *b, double *GP) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(lv_pr_rhs(c, dt, gp_step, vbc_wall, false, nullptr, false));
     if (b) LV_TRY(download_slots(c, c->d_b, b, 1));
     if (GP) LV_TRY(download_slots(c, (const double *)c->d_GP, GP, 2));
@@ -1327,7 +1331,7 @@ int32_t lv_pressure_rhs(LvHandle c, double dt, int32_t gp_step, const double *vb
 int32_t lv_find_pressure_dev(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
                              const double *vbc_wall, int32_t *iters_out, double *relres_out) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out);
 }
 
@@ -1336,7 +1340,21 @@ int32_t lv_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, doub
                          const double *vbc_wall, const double *vbc_edge, int64_t n_vbc_edge, double *P_out, int32_t *iters_out,
                          double *relres_out) {
     if (!c || !mass || !rho || !c2 || !P_in || !v || !P_out) return lv_set_error(c, LV_EINVAL, "null argument");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    if (c->pipe_mode && c->n > 0) {
+        // pipelined mode: the five fields go up on the upload stream while the clip kernel of the remesh just queued is
+        // still running; only then does the host wait for that remesh
+        LV_CUDA(c, cudaSetDevice(c->device));
+        const double *src[5] = {mass, rho, c2, P_in, v};
+        const int nc[5] = {1, 1, 1, 1, 2};
+        const double *staged[5];
+        LV_TRY(lv_pipe_upload_begin(c, src, nc, staged));
+        LV_TRY(lv_pipe_finish(c));
+        LV_TRY(lv_set_boundary_velocity(c, vbc_edge, n_vbc_edge));
+        LV_TRY(upload_fields(c, mass, rho, c2, P_in, v, false, staged));
+        LV_TRY(lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out));
+        return download_slots(c, c->d_P, P_out, 1);
+    }
+    LV_ENTER(c);
     LV_TRY(lv_set_boundary_velocity(c, vbc_edge, n_vbc_edge)); // NULL: the four per-wall constants
     LV_TRY(upload_fields(c, mass, rho, c2, P_in, v, false));
     LV_TRY(lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out));
@@ -1346,7 +1364,7 @@ int32_t lv_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, doub
 int32_t lv_pressure_solve(LvHandle c, int32_t solver, const double *b, double *x, double rtol, double atol, int32_t itmax,
                           int32_t *iters, double *relres) {
     if (!c || !b || !x) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->assembled) return lv_set_error(c, LV_EINVAL, "operator not assembled");
     const int64_t n = c->n;
     if (n == 0) return LV_OK;

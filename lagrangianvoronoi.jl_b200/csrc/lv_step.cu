@@ -523,7 +523,7 @@ extern "C" {
 // polygon fields in label order: x v dv momentum (2 each), rho e P c2 mass energy quality mu phase, D (4)
 int32_t lv_state_set(LvHandle c, const char *name, const double *host, int64_t n) {
     if (!c || !name || (!host && n > 0)) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     const int k = field_index(name);
     if (k < 0) return lv_set_error(c, LV_EINVAL, "unknown field '%s'", name);
     if (k == F_X) {
@@ -537,7 +537,7 @@ int32_t lv_state_set(LvHandle c, const char *name, const double *host, int64_t n
 }
 int32_t lv_state_get(LvHandle c, const char *name, double *host) {
     if (!c || !name || !host) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     const int k = field_index(name);
     if (k < 0 || !c->st_field[0]) return lv_set_error(c, LV_EINVAL, "unknown field or no device state");
     if (c->st_n > 0) LV_CUDA(c, cudaMemcpyAsync(host, c->st_field[k], sizeof(double) * (size_t)FIELD_NC[k] * (size_t)c->st_n, cudaMemcpyDeviceToHost, c->stream));
@@ -558,19 +558,19 @@ int32_t lv_state_ptr(LvHandle c, const char *name, void **dev_ptr, int64_t *n) {
 // values each).  From then on move! / relaxation_step! migrate generators between ranks together with their fields.
 int32_t lv_state_attach_strip(LvHandle c) {
     if (!c || !c->strip.on) return lv_set_error(c, LV_EINVAL, "lv_state_attach_strip: not in strip mode");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return state_ensure(c, c->strip.n_own);
 }
 
 int32_t lv_state_remesh(LvHandle c) { // remesh!(grid) on the resident positions
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     return state_remesh(c);
 }
 
 int32_t lv_step_move(LvHandle c, double dt) { // move!(grid, dt)  move.jl:9-21
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     LV_CUDA(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream));
@@ -582,7 +582,7 @@ int32_t lv_step_move(LvHandle c, double dt) { // move!(grid, dt)  move.jl:9-21
 
 int32_t lv_step_eos(LvHandle c, double gamma, double p0, int32_t stiffened) { // stiffened_eos!(grid, gamma, P0) / ideal_eos!(grid, gamma; Pmin)
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     if (S.n > 0) { k_eos<<<GRID(S.n)>>>(S, gamma, p0, stiffened); c->launches++; }
@@ -592,7 +592,7 @@ int32_t lv_step_eos(LvHandle c, double gamma, double p0, int32_t stiffened) { //
 
 int32_t lv_step_pressure_step(LvHandle c, double dt) { // pressure_step!(grid, dt)  pressure.jl:10-25
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     LV_TRY(st_halo(c, {F_P}));
@@ -611,7 +611,7 @@ int32_t lv_step_pressure_step(LvHandle c, double dt) { // pressure_step!(grid, d
 
 int32_t lv_step_gravity(LvHandle c, double gx, double gy, double dt) { // gravity_step!(grid, g, dt)  pressure.jl:77-82
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->st_field[0]) return lv_set_error(c, LV_EINVAL, "no device state");
     StepView S = make_view(c);
     if (S.n > 0) { k_gravity<<<GRID(S.n)>>>(S, gx, gy, dt); c->launches++; }
@@ -621,7 +621,7 @@ int32_t lv_step_gravity(LvHandle c, double gx, double gy, double dt) { // gravit
 
 int32_t lv_step_find_D(LvHandle c) { // find_D!(grid)  diffusion.jl:8-19
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     LV_TRY(st_halo(c, {F_V}));
@@ -632,7 +632,7 @@ int32_t lv_step_find_D(LvHandle c) { // find_D!(grid)  diffusion.jl:8-19
 
 int32_t lv_step_viscous_step(LvHandle c, double dt, int32_t artificial_viscosity) { // viscous_step!  diffusion.jl:39-53
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     const double avdr = artificial_viscosity ? c->dr : 0.0;
@@ -653,7 +653,7 @@ int32_t lv_step_viscous_step(LvHandle c, double dt, int32_t artificial_viscosity
 int32_t lv_step_bdary_friction_ex(LvHandle c, double dt, const double *vwall, const uint8_t *wall_on, const double *v_edge,
                                   const uint8_t *on_edge, int64_t n_edge) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     WallVel w;
@@ -691,7 +691,7 @@ int32_t lv_step_bdary_friction(LvHandle c, double dt, const double *vwall) { // 
 
 int32_t lv_step_find_dv(LvHandle c, double dt, double alpha) { // find_dv!(grid, dt, alpha)  relaxation.jl:10-25
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     if (S.n > 0) { k_find_dv<<<GRID(S.n)>>>(S, dt, alpha); c->launches++; }
@@ -701,7 +701,7 @@ int32_t lv_step_find_dv(LvHandle c, double dt, double alpha) { // find_dv!(grid,
 
 int32_t lv_step_relaxation_step(LvHandle c, double dt, int32_t rusanov) { // relaxation_step!  relaxation.jl:36-73
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     StepView S = make_view(c);
     LV_TRY(st_halo(c, {F_DV, F_V, F_RHO, F_E, F_PHASE}));
@@ -717,7 +717,7 @@ int32_t lv_step_relaxation_step(LvHandle c, double dt, int32_t rusanov) { // rel
 // populate_lloyd!'s relaxation loop (populate.jl:132-145): niter x (remesh!; p.x = centroid(p)), then a final remesh!
 int32_t lv_step_lloyd(LvHandle c, int32_t niter) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (!c->st_field[0]) return lv_set_error(c, LV_EINVAL, "no device state");
     for (int it = 0; it < niter; it++) {
         LV_TRY(state_remesh(c));
@@ -732,7 +732,7 @@ int32_t lv_step_lloyd(LvHandle c, int32_t niter) {
 int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, double rtol, double atol, int32_t itmax, int32_t *iters,
                                       int32_t *solved) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     if (c->comm && !lv_strip_peer_mode(c)) return lv_set_error(c, LV_EINVAL, "the multiphase projector on several GPUs needs the peer-memory strip exchange");
     LV_TRY(lv_pr_ensure(c));
@@ -772,7 +772,7 @@ int32_t lv_step_multiphase_projection(LvHandle c, double quality_threshold, doub
 // vectors in label order: the operator the projection solves with, exposed for direct parity checks.  NULL skips.
 int32_t lv_step_multiphase_apply(LvHandle c, const double *x, double *y, double *b) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     LV_TRY(lv_pr_ensure(c));
     StepView S = make_view(c);
@@ -804,7 +804,7 @@ int32_t lv_step_multiphase_apply(LvHandle c, const double *x, double *y, double 
 int32_t lv_step_find_pressure(LvHandle c, double dt, int32_t niter, double rtol, double atol, int32_t itmax, int32_t solver,
                               const double *vbc_wall, int32_t *iters_out, double *relres_out) {
     if (!c) return LV_EINVAL;
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_TRY(need_mesh(c));
     LV_TRY(lv_fields_upload_dev(c, c->st_field[F_MASS], c->st_field[F_RHO], c->st_field[F_C2], c->st_field[F_P], c->st_field[F_V]));
     LV_TRY(lv_pr_find_pressure(c, dt, niter, rtol, atol, itmax, solver, vbc_wall, iters_out, relres_out));

@@ -450,7 +450,7 @@ int32_t lv_strip_setup(LvHandle c, int32_t npeers, const int32_t *peer_rank, con
                        const int32_t *hi, int64_t capg, int64_t cap_loc, uint8_t *out64) {
     if (!c || npeers < 0 || npeers > LV_SP_MAXP || capg < 1 || cap_loc < 1 || !out64) return lv_set_error(c, LV_EINVAL, "lv_strip_setup: bad arguments");
     if (capg * LV_SP_MAXP >= ((int64_t)1 << 30)) return lv_set_error(c, LV_EINVAL, "lv_strip_setup: ghost capacity too large");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     lv_strip_destroy(c);
     auto &S = c->strip;
@@ -482,7 +482,7 @@ int32_t lv_strip_setup(LvHandle c, int32_t npeers, const int32_t *peer_rank, con
 // Map the exchange areas of the peers (handles in the order of lv_strip_setup's peer list).
 int32_t lv_strip_map(LvHandle c, const uint8_t *handles /* npeers x 64 */) {
     if (!c || !c->strip.on || (c->strip.npeers > 0 && !handles)) return lv_set_error(c, LV_EINVAL, "lv_strip_map: call lv_strip_setup first");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     auto &S = c->strip;
     lv_strip_unmap(c);
     for (int p = 0; p < S.npeers; p++) {
@@ -515,7 +515,7 @@ int32_t lv_strip_set_owned(LvHandle c, int64_t n_own, const double *xy, int32_t 
     if (!c || !c->strip.on || n_own < 0 || (n_own > 0 && !xy)) return lv_set_error(c, LV_EINVAL, "lv_strip_set_owned: bad arguments");
     auto &S = c->strip;
     if (n_own + (int64_t)S.npeers * 0 > S.cap_loc) return lv_set_error(c, LV_ECAPACITY, "strip: %lld owned generators exceed the capacity %lld", (long long)n_own, (long long)S.cap_loc);
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     if (n_own > 0) {
         LV_CUDA(c, cudaMemcpyAsync(S.loc_xy, xy, sizeof(double2) * (size_t)n_own, xy_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
         if (key_dev) LV_CUDA(c, cudaMemcpyAsync(S.loc_key, key_dev, sizeof(int) * (size_t)n_own, cudaMemcpyDeviceToDevice, c->stream));
@@ -530,7 +530,7 @@ int32_t lv_strip_remesh(LvHandle c, int64_t *counts_out) {
     if (!c || !c->strip.on) return lv_set_error(c, LV_EINVAL, "lv_strip_remesh: call lv_strip_setup first");
     auto &S = c->strip;
     if (S.npeers > 0 && !S.mapped) return lv_set_error(c, LV_EINVAL, "lv_strip_remesh: peers not mapped");
-    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_ENTER(c);
     cudaStream_t st = c->stream;
     LvStripHdr *me = (LvStripHdr *)S.area;
     int64_t nrecv_total = 0;

@@ -199,8 +199,11 @@ class VoronoiGrid:
 
 
 def wait_edges(grid: VoronoiGrid) -> None:
-    """Block until the edge view of the last lazy remesh has landed in ``grid.edges``."""
+    """Block until the edge view of the last lazy remesh has landed in ``grid.edges``.  In the pipelined mode
+    (``lazy="pipeline"``) this is also where a deferred remesh reports its errors and where ``grid.edges`` gets its length."""
     check(grid._L.lv_mesh_wait(grid._h), grid._h)
+    if getattr(grid, "_lazy_edges", 0) == 3 and getattr(grid, "_edge_buf", None) is not None and grid.n:
+        grid.edges = grid._edge_buf[: grid.mesh_nnz()]
 
 
 def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
@@ -209,6 +212,9 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
     ``lazy=True`` returns once ``rowptr``, areas and centroids are back and lets the edge records (40 B each, the bulk
     of the traffic) arrive in the background; call ``wait_edges(grid)`` before reading ``grid.edges``.  ``lazy="all"``
     sends rowptr, areas and centroids in the background as well: nothing may be read before ``wait_edges(grid)``.
+    ``lazy="pipeline"`` additionally returns while the clipping kernel is still queued (the next call's uploads overlap
+    it; errors of this remesh surface at the next call or at ``wait_edges``) and moves the mesh over PCIe in a 20 B/edge
+    wire format that host threads of the library expand into the 40-byte records (lv_pipeline.cu).
 
     Gathers ``grid.x``, runs the cell-list build and the clipping kernel on the GPU and leaves
     ``grid.rowptr`` / ``grid.edges`` (the flat ``p.edges`` view), areas and centroids on the host.
@@ -222,11 +228,14 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
         grid._centroid = _host_empty((n, 2), np.float64)
     nnz = C.c_int64()
     if not edges:
+        if getattr(grid, "_lazy_edges", 0) == 3:  # rowptr / areas / centroids are wanted on return: leave the pipelined mode
+            check(L.lv_set_async_edges(grid._h, 0), grid._h)
+            grid._lazy_edges = 0
         check(L.lv_remesh(grid._h, n, ptr(grid.x), ptr(grid.rowptr), None, 0, C.byref(nnz), ptr(grid._area),
                           ptr(grid._centroid)), grid._h)
         grid.edges = None
         return
-    mode = 2 if lazy == "all" else int(bool(lazy))
+    mode = 3 if lazy == "pipeline" else (2 if lazy == "all" else int(bool(lazy)))
     if mode != getattr(grid, "_lazy_edges", 0):
         check(L.lv_set_async_edges(grid._h, mode), grid._h)
         grid._lazy_edges = mode
@@ -242,7 +251,7 @@ def remesh(grid: VoronoiGrid, edges: bool = True, lazy: bool = False) -> None:
         st = L.lv_mesh_download(grid._h, ptr(grid.rowptr), ptr(grid._edge_buf), nnz.value, ptr(grid._area),
                                 ptr(grid._centroid))
     check(st, grid._h)
-    grid.edges = grid._edge_buf[: nnz.value]
+    grid.edges = grid._edge_buf[: nnz.value] if nnz.value >= 0 else None  # pipelined: known after wait_edges
 
 
 def area(grid: VoronoiGrid) -> np.ndarray:

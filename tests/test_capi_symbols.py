@@ -75,3 +75,38 @@ def test_synthetic_generator_is_deterministic(lv):
     s = lv.synthetic.jittered_lattice(16, 0, rows=(4, 8))
     full = a.reshape(16, 16, 2)[:, 4:8].reshape(-1, 2)
     assert np.array_equal(s, full)
+
+
+def test_wire_format_decoder_rebuilds_the_oracles_edge_records(lv, oracle):
+    """lv_wire_expand (host-only part of the pipelined download): the 20 B/edge wire format -- start vertex + label word
+    with wall / end-of-row bits -- decodes to exactly the 40-byte Edge records, for any split of the edge list into chunks."""
+    import numpy as np
+    from lvb200._capi import EDGE_DTYPE, load_library, ptr
+    from .conftest import make_points
+    L = load_library()
+    for kind, n_side, per in (("jitter", 40, True), ("poisson", 24, False)):
+        xy, dr, bmin, bmax = make_points(kind, n_side, 1)
+        og = oracle.OracleGrid(bmin, bmax, dr, xperiodic=per, yperiodic=per)
+        og.set_points(xy)
+        assert og.remesh() == 0
+        rowptr, edges = og.mesh()
+        nnz = int(rowptr[-1])
+        v1 = np.ascontiguousarray(edges["v1"])
+        lab = edges["label"]
+        word = np.where(lab > 0, lab, (1 << 30) | (-lab)).astype(np.uint32)
+        word[rowptr[1:][np.diff(rowptr) > 0] - 1] |= np.uint32(1 << 31)
+        row_of = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+        for chunk in (nnz, 1000, 7):
+            out = np.zeros(nnz, EDGE_DTYPE)
+            for k0 in range(0, nnz, chunk):
+                ln = min(chunk, nnz - k0)
+                has_next = k0 + ln < nnz
+                vv = np.ascontiguousarray(v1[k0:k0 + ln + has_next])
+                ww = np.ascontiguousarray(word[k0:k0 + ln])
+                rs = np.ascontiguousarray(v1[rowptr[row_of[k0]]])
+                seg = out[k0:k0 + ln]
+                assert L.lv_wire_expand(ptr(vv), ptr(ww), ln, int(has_next), ptr(rs), ptr(seg)) == 0
+            assert out.tobytes() == edges.tobytes(), (kind, chunk)
+    # a list that stops inside a row is refused
+    bad = np.zeros(1, np.uint32)
+    assert L.lv_wire_expand(ptr(np.zeros(2)), ptr(bad), 1, 0, ptr(np.zeros(2)), ptr(np.zeros(1, EDGE_DTYPE))) != 0

@@ -195,6 +195,73 @@ def test_lazy_edge_download_is_identical(lv):
     assert g.edges.tobytes() == ref[1].tobytes()
 
 
+def test_pipelined_mode_delivers_the_same_bytes(lv, monkeypatch):
+    """lv_set_async_edges(h, 3): remesh returns with the clip kernel queued, the mesh crosses PCIe as 20 B/edge and host
+    threads of the library expand it.  After wait_edges every output is the synchronous path's, byte for byte -- on a mesh
+    of several wire chunks (> 2^20 edges), with walls, and through find_pressure (fields uploaded before the pending
+    remesh is completed)."""
+    for kind, n_side, per in (("jitter", 480, True), ("poisson", 64, False), ("rect2x1", 40, False)):
+        xy, dr, bmin, bmax = make_points(kind, n_side, 4)
+        g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=per, yperiodic=per)
+        g.set_points(xy)
+        lv.remesh(g)
+        ref = (g.rowptr.copy(), g.edges.copy(), lv.area(g).copy(), lv.centroid(g).copy())
+        v, P = lv.synthetic.taylor_green_fields(xy)
+        for name, val in (("rho", 1.0), ("mass", ref[2]), ("c2", 100.0), ("v", v), ("P", P)):
+            getattr(g, name)[...] = val
+        s = lv.PressureSolver(g, rtol=1e-10, atol=0.0, itmax=5000)
+        lv.find_pressure(s, 0.1 * dr, 2)
+        P_ref, it_ref = g.P.copy(), s.iters.copy()
+        for rep in range(3):
+            g.edges[...] = 0; g.rowptr[...] = 0; g._area[...] = 0; g._centroid[...] = 0
+            g.P[...] = P
+            lv.remesh(g, lazy="pipeline")
+            assert g.edges is None                                # length unknown until the remesh is completed
+            lv.remesh(g, lazy="pipeline")                         # completes the first, queues the second
+            lv.find_pressure(s, 0.1 * dr, 2)                      # uploads first, then completes the second remesh
+            lv.wait_edges(g)
+            assert np.array_equal(g.rowptr, ref[0]) and g.edges.tobytes() == ref[1].tobytes()
+            assert np.array_equal(lv.area(g), ref[2]) and np.array_equal(lv.centroid(g), ref[3])
+            assert np.array_equal(s.iters, it_ref) and np.array_equal(g.P, P_ref)
+        lv.remesh(g)                                              # back to the synchronous mode
+        assert g.edges.tobytes() == ref[1].tobytes()
+
+
+def test_pipelined_mode_on_degenerate_and_replayed_meshes(lv, monkeypatch):
+    """The deferred remesh climbs the same ladder: anomalies replay with the edge-list kernel when the remesh is completed,
+    meshes whose chains are not closed bit for bit come back as full records, and a destroyed mesh raises at the wait."""
+    for name, xy in _degenerate_sets(3).items():
+        g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1 / 24)
+        g.set_points(xy)
+        lv.remesh(g)
+        ref = (g.rowptr.copy(), g.edges.copy(), lv.area(g).copy())
+        g.edges[...] = 0; g.rowptr[...] = 0
+        lv.remesh(g, lazy="pipeline")
+        lv.wait_edges(g)
+        assert np.array_equal(g.rowptr, ref[0]) and g.edges.tobytes() == ref[1].tobytes(), name
+        assert np.array_equal(lv.area(g), ref[2]), name
+    monkeypatch.setenv("LV_CLIP_FORCE_ANOMALY", "1")
+    xy, dr, bmin, bmax = make_points("jitter", 64, 5)
+    g = lv.VoronoiGrid(lv.Rectangle(bmin, bmax), dr, xperiodic=True, yperiodic=True)
+    g.set_points(xy)
+    lv.remesh(g)
+    ref = (g.rowptr.copy(), g.edges.copy())
+    n_an = g.clip_info()[1]
+    g.edges[...] = 0
+    lv.remesh(g, lazy="pipeline")
+    lv.wait_edges(g)
+    assert g.clip_info()[1] == n_an + 1 and g.edges.tobytes() == ref[1].tobytes()
+    monkeypatch.delenv("LV_CLIP_FORCE_ANOMALY")
+    # voronoigrid.jl:63-65: an isolated generator cannot be closed within r_max
+    g2 = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1 / 50)
+    g2.set_points(np.array([[0.5, 0.5], [0.52, 0.5]]))
+    with pytest.raises(lv.LvError, match="destroyed"):
+        lv.remesh(g2)
+    lv.remesh(g2, lazy="pipeline")                              # queued: the error belongs to the completion
+    with pytest.raises(lv.LvError, match="The Voronoi Mesh has been destroyed."):
+        lv.wait_edges(g2)
+
+
 def _degenerate_sets(seed):
     """Inputs on which the clipping decisions hinge on SIGNUM_EPS and the cut order (excluded from the north star's
     bit-exact claim, yet the GPU path must still reproduce the reference because its fast kernel detects what it cannot
