@@ -277,14 +277,19 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
             # Every mesh output (rowptr, areas, centroids, edge records) is downloaded lazily on a second stream so that
             # it overlaps the next remesh and the pressure solve; the step ends only when every byte is in host memory.
             g.P = p_in.pop() if p_in else g.P
-            lv.remesh(g, lazy=E2E_MODE)
-            lv.remesh(g, lazy=E2E_MODE)
-            lv.find_pressure(solver, dt, args.niter)
-            lv.wait_edges(g)
+            t = [time.perf_counter()]
+            lv.remesh(g, lazy=E2E_MODE); t.append(time.perf_counter())
+            lv.remesh(g, lazy=E2E_MODE); t.append(time.perf_counter())
+            lv.find_pressure(solver, dt, args.niter); t.append(time.perf_counter())
+            lv.wait_edges(g); t.append(time.perf_counter())
+            for k in range(4):
+                call_ms[k] += 1e3 * (t[k + 1] - t[k])
             return int(solver.iters.sum())
 
+        call_ms = [0.0] * 4
         step_e2e()
         env.barrier()
+        call_ms = [0.0] * 4
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record(stream)
@@ -295,12 +300,13 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
         ms_e = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
         nnz = int(g.rowptr[-1])
         h2d = 2 * n * 16 + n * 8 * 6                     # 2 x positions + mass, rho, c2, P, v(2)
-        # bytes that cross PCIe: the pipelined mode ships 20 B per edge (start vertex + label word, + 16 B per 2^20-edge
+        # bytes that cross PCIe: the pipelined mode ships 20 B per edge (start vertex + label word, + 16 B per 2^18-edge
         # chunk) and host threads of the library expand them into the 40-byte records the caller reads
         per_edge = 20 if E2E_MODE == "pipeline" else 40
         d2h = 2 * ((n + 1) * 8 + nnz * per_edge + n * 8 + n * 16) + n * 8  # 2 x (rowptr, edges, area, centroid) + P
         e2e = {"value": n * steps / (ms_e / 1e3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / steps, "mode": E2E_MODE,
+               "host_wall_ms_per_call": dict(zip(("remesh_1", "remesh_2", "find_pressure", "wait_edges"), (c / steps for c in call_ms))),
                "contract": "positions + fields up; rowptr, 40-B edge records, areas, centroids (x2) and P delivered into the caller's "
                            "host buffers" + ("; pipelined: uploads overlap the queued clip kernel, edges cross PCIe as 20 B and are "
                                              "expanded by host threads of the library" if E2E_MODE == "pipeline" else "")}

@@ -69,8 +69,10 @@ __device__ __forceinline__ double ring_influence_rr(Ring<MAXE, BLOCK> &p, double
     return rr;
 }
 
-template <int MAXE, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntiles) {
+// LV_CLIP_STATS=1 (diagnostics): per-phase warp iterations and active lanes of the tile kernel, printed to stderr
+#define LV_STAT(...) do { if (STATS) { __VA_ARGS__ } } while (0)
+template <int MAXE, int BLOCK, int MINB, bool STATS = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntiles, unsigned long long *stats = nullptr) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2 *sv = (double2 *)smem;
     int *sl = (int *)(sv + MAXE * BLOCK);
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    unsigned long long st_a_it = 0, st_a_ln = 0, st_b_it = 0, st_b_ln = 0, st_c_it = 0, st_c_ln = 0, st_rounds = 0, st_alive = 0;
 
     for (;;) {
         int tile = 0;
@@ -171,7 +174,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         }
         __syncwarp();
     }
+    if (STATS && lane == 0) {
+        const unsigned long long v[8] = {st_a_it, st_a_ln, st_b_it, st_b_ln, st_c_it, st_c_ln, st_rounds, st_alive};
+        for (int k = 0; k < 8; k++) atomicAdd(&stats[k], v[k]);
+    }
 }
+#undef LV_STAT
+#define LV_STAT(...)
 
 template <int MAXE, int BLOCK, int MINB>
 static int launch_fast(LvContext *c, const ClipArgs &a) {
@@ -186,6 +195,23 @@ static int launch_fast(LvContext *c, const ClipArgs &a) {
     long long grid = (long long)c->num_sms * per_sm;
     const long long need = (ntiles + (BLOCK / 32) - 1) / (BLOCK / 32);
     if (grid > need) grid = need;
+    static const bool stats = [] { const char *m = getenv("LV_CLIP_STATS"); return m && m[0] == '1'; }();
+    if (stats) { // diagnostics: one instrumented launch, synchronous, printed
+        unsigned long long *d = nullptr, h[8];
+        LV_CUDA(c, cudaMalloc((void **)&d, sizeof(h)));
+        LV_CUDA(c, cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+        LV_CUDA(c, cudaFuncSetAttribute(k_clip_fast<MAXE, BLOCK, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_clip_fast<MAXE, BLOCK, MINB, true><<<(int)grid, BLOCK, smem, c->stream>>>(a, ntiles, d);
+        LV_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+        fprintf(stderr, "[clip stats] tiles %d  rounds/tile %.2f alive/round %.2f | A events/tile %.1f lanes %.2f | B iters/tile %.1f lanes %.2f | "
+                        "C cuts/tile %.1f lanes %.2f\n", ntiles, (double)h[6] / ntiles, (double)h[7] / (h[6] ? h[6] : 1), (double)h[0] / ntiles,
+                (double)h[1] / (h[0] ? h[0] : 1), (double)h[2] / ntiles, (double)h[3] / (h[2] ? h[2] : 1), (double)h[4] / ntiles,
+                (double)h[5] / (h[4] ? h[4] : 1));
+        c->launches++;
+        return LV_OK;
+    }
     k_clip_fast<MAXE, BLOCK, MINB><<<(int)grid, BLOCK, smem, c->stream>>>(a, ntiles);
     c->launches++;
     LV_CUDA(c, cudaGetLastError());

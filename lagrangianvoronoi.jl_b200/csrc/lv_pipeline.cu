@@ -22,6 +22,7 @@
 // vertices of records the GPU produced.
 #include "lv_internal.cuh"
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -32,8 +33,11 @@
 #include <immintrin.h>
 #endif
 
-#define PIPE_CH (1 << 20) // edges per chunk of the wire format (16 MiB of vertices + 4 MiB of label words)
-#define PIPE_RING 8       // pinned chunk buffers
+// Chunk = unit of the device->host copies and of the host-side expansion.  A worker expands 2^18 edges in ~1.2 ms and the
+// copy engine delivers one in ~0.1 ms, so the ring must hold more chunks than there are workers or the ring, not PCIe,
+// sets the pace (measured: 8 slots of 2^20 edges capped the download at 33 GB/s).
+#define PIPE_CH (1 << 18) // edges per chunk of the wire format (4 MiB of vertices + 1 MiB of label words)
+#define PIPE_RING 40      // pinned chunk buffers (200 MiB)
 #define WIRE_END 0x80000000u
 #define WIRE_WALL 0x40000000u
 #define WIRE_PAYLOAD 0x3fffffffu
@@ -103,7 +107,15 @@ struct LvPipe {
     std::thread downloader;
     std::vector<std::thread> workers;
     int64_t bytes_d2h = 0; // wire bytes of the finished jobs (diagnostics)
+    // LV_PIPE_TRACE=1: per-job timeline on stderr
+    bool trace = false;
+    std::chrono::steady_clock::time_point epoch;
+    double tr_expand_ms = 0, tr_evwait_ms = 0; // summed over the workers, per job
 };
+
+static inline double pipe_now_ms(const LvPipe *P) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P->epoch).count();
+}
 
 // ---- device side: label-order wire format -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pipe_deg(int64_t n, const int *__restrict__ prim, const unsigned char *__restrict__ rdeg,
@@ -223,14 +235,18 @@ static void pipe_worker(LvPipe *P) {
             t = P->tasks.front();
             P->tasks.pop_front();
         }
+        const double tw0 = P->trace ? pipe_now_ms(P) : 0.0;
         cudaError_t e = cudaEventSynchronize(P->ring_ev[t.slot]);
+        const double tw1 = P->trace ? pipe_now_ms(P) : 0.0;
         if (e == cudaSuccess) {
             const double2 *V = (const double2 *)P->ring[t.slot];
             const unsigned *lab = (const unsigned *)(P->ring[t.slot] + sizeof(double2) * (size_t)(PIPE_CH + 1));
             expand_chunk(V, lab, t.len, t.has_next, t.rs, t.job->edges + t.k0);
         }
+        const double tw2 = P->trace ? pipe_now_ms(P) : 0.0;
         {
             std::lock_guard<std::mutex> lk(P->mu);
+            P->tr_evwait_ms += tw1 - tw0; P->tr_expand_ms += tw2 - tw1;
             if (e != cudaSuccess && t.job->err_code == LV_OK) {
                 t.job->err_code = LV_ECUDA;
                 t.job->err = std::string("edge download failed: ") + cudaGetErrorString(e);
@@ -255,6 +271,9 @@ static int pipe_run_job(LvPipe *P, PipeJob *j) {
     if (e != cudaSuccess) { job_fail(P, j, LV_ECUDA, std::string("remesh failed: ") + cudaGetErrorString(e)); return -1; }
     const int *hf = j->snap;
     if (hf[LVF_NAN] || hf[LVF_DESTROYED] || hf[LVF_OVERFLOW] || hf[9]) return 2; // lv_pipe_finish deals with all of these
+    const double tr0 = P->trace ? pipe_now_ms(P) : 0.0;
+    double tr1 = 0.0;
+    if (P->trace) { std::lock_guard<std::mutex> lk(P->mu); P->tr_expand_ms = P->tr_evwait_ms = 0.0; }
     const int64_t n = j->n, nnz = hf[LVF_NNZ];
     if (j->edges && j->cap < nnz) {
         char buf[128];
@@ -303,6 +322,7 @@ static int pipe_run_job(LvPipe *P, PipeJob *j) {
         }
         P->cv_tasks.notify_one();
     }
+    if (P->trace) tr1 = pipe_now_ms(P);
     // records of one mesh must be complete before the next mesh may write into the same caller buffers
     {
         std::unique_lock<std::mutex> lk(P->mu);
@@ -312,6 +332,9 @@ static int pipe_run_job(LvPipe *P, PipeJob *j) {
     if (e != cudaSuccess) job_fail(P, j, LV_ECUDA, std::string("mesh download failed: ") + cudaGetErrorString(e));
     std::lock_guard<std::mutex> lk(P->mu);
     P->bytes_d2h += (int64_t)sizeof(long long) * (n + 1) + 24 * n + 20 * (j->edges ? nnz : 0);
+    if (P->trace)
+        fprintf(stderr, "[pipe] job sb=%d nnz=%lld: kernels done %.1f ms, copies issued %.1f, delivered %.1f | workers: expand %.1f ms, event wait %.1f ms (summed over %d threads)\n",
+                j->sb, (long long)nnz, tr0, tr1, pipe_now_ms(P), P->tr_expand_ms, P->tr_evwait_ms, (int)P->workers.size());
     return j->err_code == LV_OK ? 1 : -1;
 }
 
@@ -369,6 +392,8 @@ int lv_pipe_enable(LvContext *c) {
         LV_CUDA(c, cudaHostAlloc((void **)&P->ring[s], slot_bytes, cudaHostAllocPortable));
         LV_CUDA(c, cudaEventCreateWithFlags(&P->ring_ev[s], cudaEventDisableTiming));
     }
+    { const char *t = getenv("LV_PIPE_TRACE"); P->trace = t && t[0] == '1'; }
+    P->epoch = std::chrono::steady_clock::now();
     P->downloader = std::thread(pipe_downloader, P);
     const int nw = host_threads_default();
     for (int k = 0; k < nw; k++) P->workers.emplace_back(pipe_worker, P);
@@ -527,6 +552,7 @@ int lv_pipe_remesh(LvContext *c, int64_t n, const double *xy, int64_t *rowptr, L
         }
         P->cap_xy = n + n / 16 + 64;
     }
+    if (P->trace) fprintf(stderr, "[pipe] remesh enter %.1f ms\n", pipe_now_ms(P));
     double2 *dst = P->d_xy_alt[P->xy_cur ^= 1];
     LV_CUDA(c, cudaMemcpyAsync(dst, xy, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, P->up_stream));
     LV_CUDA(c, cudaEventRecord(P->ev_up, P->up_stream));
@@ -546,6 +572,7 @@ int lv_pipe_remesh(LvContext *c, int64_t n, const double *xy, int64_t *rowptr, L
     P->pend_rowptr = rowptr; P->pend_edges = edges; P->pend_cap = cap; P->pend_area = area; P->pend_cen = centroid;
     LV_TRY(pipe_queue_download(c, rowptr, edges, cap, area, centroid));
     c->pipe_pending = true;
+    if (P->trace) fprintf(stderr, "[pipe] remesh queued %.1f ms\n", pipe_now_ms(P));
     return LV_OK;
 }
 
@@ -557,6 +584,7 @@ int lv_pipe_finish(LvContext *c) {
     c->pipe_pending = false;
     const int sb = P->pend_sb;
     LV_CUDA(c, cudaEventSynchronize(P->ev_conv[sb]));
+    if (P->trace) fprintf(stderr, "[pipe] finish: clip + conversion done %.1f ms\n", pipe_now_ms(P));
     int snap[16];
     memcpy(snap, P->snap[sb], sizeof(snap));
     bool replayed = false;

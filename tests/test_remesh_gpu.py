@@ -198,7 +198,7 @@ def test_lazy_edge_download_is_identical(lv):
 def test_pipelined_mode_delivers_the_same_bytes(lv, monkeypatch):
     """lv_set_async_edges(h, 3): remesh returns with the clip kernel queued, the mesh crosses PCIe as 20 B/edge and host
     threads of the library expand it.  After wait_edges every output is the synchronous path's, byte for byte -- on a mesh
-    of several wire chunks (> 2^20 edges), with walls, and through find_pressure (fields uploaded before the pending
+    of several wire chunks (> 2^18 edges), with walls, and through find_pressure (fields uploaded before the pending
     remesh is completed)."""
     for kind, n_side, per in (("jitter", 480, True), ("poisson", 64, False), ("rect2x1", 40, False)):
         xy, dr, bmin, bmax = make_points(kind, n_side, 4)
@@ -233,7 +233,13 @@ def test_pipelined_mode_on_degenerate_and_replayed_meshes(lv, monkeypatch):
     for name, xy in _degenerate_sets(3).items():
         g = lv.VoronoiGrid(lv.Rectangle((0, 0), (1, 1)), 1 / 24)
         g.set_points(xy)
-        lv.remesh(g)
+        try:
+            lv.remesh(g)
+        except lv.LvError:                                        # this input destroys the mesh: so must the deferred remesh
+            lv.remesh(g, lazy="pipeline")
+            with pytest.raises(lv.LvError):
+                lv.wait_edges(g)
+            continue
         ref = (g.rowptr.copy(), g.edges.copy(), lv.area(g).copy())
         g.edges[...] = 0; g.rowptr[...] = 0
         lv.remesh(g, lazy="pipeline")
