@@ -16,6 +16,8 @@
 // (dynamic tile ids from a ticket counter guarantee forward progress), so edges are written
 // straight to their final position: no second pass over the mesh.
 #include "lv_clip.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <cstdlib>
 #include <cstring>
 
@@ -303,6 +305,13 @@ static int clip_attempt(LvContext *c, int level, int64_t need_nnz) {
     a.cap_nnz = c->cap_nnz;
     a.park_v = nullptr; a.park_l = nullptr; a.park_nxt = nullptr; a.park_hdr = nullptr;
     { const char *fa = getenv("LV_CLIP_FORCE_ANOMALY"); a.force_anomaly = fa && fa[0] == '1'; }
+    {
+        int reach = 0;
+        for (int k = 0; k < c->gp.npath; k++) reach = std::max(reach, std::max(std::abs(c->h_path[k].i1), std::abs(c->h_path[k].i2)));
+        a.wreach = (double)(reach + 2) * c->gp.h; // a candidate's bucket is at most `reach` buckets away: |q - x| < (reach + 1) h
+        a.wlo = make_double2(c->bmin[0], c->bmin[1]);
+        a.whi = make_double2(c->bmax[0], c->bmax[1]);
+    }
     {
         LvProfScope prof(c, LV_PROF_CLIP);
         if (level <= 1) LV_TRY(lv_clip_launch_fast(c, a, level));

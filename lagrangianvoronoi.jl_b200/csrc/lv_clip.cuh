@@ -33,6 +33,10 @@ struct ClipArgs {
     unsigned long long *park_nxt;
     int *park_hdr;
     int force_anomaly; // test hook (LV_CLIP_FORCE_ANOMALY=1): pretend some polygons are not generic
+    // phase A of the linked-slot kernel: generators further than wreach from the lines x = wlo / whi (the domain edges)
+    // cannot meet a candidate across the periodic seam
+    double2 wlo, whi;
+    double wreach;
 };
 
 

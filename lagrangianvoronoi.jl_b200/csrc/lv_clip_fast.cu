@@ -40,7 +40,8 @@
 typedef unsigned long long u64;
 
 #define QCAP 4 // queued candidates per lane
-#define EV 8   // scan events per lane and round
+#define EV 4   // scan events per lane and round
+#define QLOW 1 // a scan pass starts (and goes on) only while some lane has at most this many candidates queued
 
 template <int MAXE, int BLOCK>
 struct Ring {
@@ -110,6 +111,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         int qh = 0, qn = 0; // queue = positions [qh, qn) modulo QCAP
         const double hpx = 0.5 * g.xperiod, hpy = 0.5 * g.yperiod;
         const double slack = 2e-15 * (fabs(x.x) + fabs(x.y)); // 2 * rounding bound of x - (x + v), see phase A
+        // The periodic shift of phase A can only fire for a candidate more than half a period away, i.e. for a polygon
+        // within the reach of the path table (wreach = (max |i| + 1) h) of the domain edge: warp-uniform switch.
+        const bool wrapx = g.xper && __any_sync(FULL, active && !(x.x - a.wlo.x > a.wreach && a.whi.x - x.x > a.wreach && a.wreach < hpx));
+        const bool wrapy = g.yper && __any_sync(FULL, active && !(x.y - a.wlo.y > a.wreach && a.whi.y - x.y > a.wreach && a.wreach < hpy));
 #include "lv_clip_init.inc"
         // ---- voronoicut!(grid, poly)  voronoigrid.jl:53-81
         while (__any_sync(FULL, alive)) {
@@ -179,8 +184,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_fast(ClipArgs a, int ntile
         for (int k = 0; k < 8; k++) atomicAdd(&stats[k], v[k]);
     }
 }
-#undef LV_STAT
-#define LV_STAT(...)
+
+static void clip_stats_print(const char *what, const unsigned long long *h, int ntiles) {
+    fprintf(stderr, "[clip stats %s] tiles %d  rounds/tile %.2f alive/round %.2f | A events/tile %.1f lanes %.2f | B iters/tile %.1f lanes %.2f | "
+                    "C cuts/tile %.1f lanes %.2f\n", what, ntiles, (double)h[6] / ntiles, (double)h[7] / (h[6] ? h[6] : 1), (double)h[0] / ntiles,
+            (double)h[1] / (h[0] ? h[0] : 1), (double)h[2] / ntiles, (double)h[3] / (h[2] ? h[2] : 1), (double)h[4] / ntiles,
+            (double)h[5] / (h[4] ? h[4] : 1));
+}
 
 template <int MAXE, int BLOCK, int MINB>
 static int launch_fast(LvContext *c, const ClipArgs &a) {
@@ -205,10 +215,7 @@ static int launch_fast(LvContext *c, const ClipArgs &a) {
         LV_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         LV_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(d);
-        fprintf(stderr, "[clip stats] tiles %d  rounds/tile %.2f alive/round %.2f | A events/tile %.1f lanes %.2f | B iters/tile %.1f lanes %.2f | "
-                        "C cuts/tile %.1f lanes %.2f\n", ntiles, (double)h[6] / ntiles, (double)h[7] / (h[6] ? h[6] : 1), (double)h[0] / ntiles,
-                (double)h[1] / (h[0] ? h[0] : 1), (double)h[2] / ntiles, (double)h[3] / (h[2] ? h[2] : 1), (double)h[4] / ntiles,
-                (double)h[5] / (h[4] ? h[4] : 1));
+        clip_stats_print("tile", h, ntiles);
         c->launches++;
         return LV_OK;
     }
@@ -229,8 +236,8 @@ static int launch_fast(LvContext *c, const ClipArgs &a) {
 #define RF_CHUNK 256 // slots per ticket
 #define RF_THR 6     // lanes without a live polygon that trigger a park + refill pass
 
-template <int MAXE, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_clip_refill(ClipArgs a, int nchunks) {
+template <int MAXE, int BLOCK, int MINB, bool STATS = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_clip_refill(ClipArgs a, int nchunks, unsigned long long *stats = nullptr) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2 *sv = (double2 *)smem;
     int *sl = (int *)(sv + MAXE * BLOCK);
@@ -253,6 +260,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_refill(ClipArgs a, int nch
     double prr = 0.0, slack = 0.0;
     int slot = -1, k1 = 0, k2 = 0, t_scan = -1, s = 0, s_end = 0, t_end = g.npath, t_chk = -1, qh = 0, qn = 0;
     int chunk_next = 0, chunk_end = 0; // the warp's current chunk (same values in every lane)
+    const bool wrapx = g.xper != 0, wrapy = g.yper != 0;
+    unsigned long long st_a_it = 0, st_a_ln = 0, st_b_it = 0, st_b_ln = 0, st_c_it = 0, st_c_ln = 0, st_rounds = 0, st_alive = 0;
 
     for (;;) {
         // ---- park finished polygons
@@ -310,7 +319,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_clip_refill(ClipArgs a, int nch
             if (!nowork && __popc(~al) >= RF_THR) break;
         }
     }
+    if (STATS && lane == 0) {
+        const unsigned long long v[8] = {st_a_it, st_a_ln, st_b_it, st_b_ln, st_c_it, st_c_ln, st_rounds, st_alive};
+        for (int k = 0; k < 8; k++) atomicAdd(&stats[k], v[k]);
+    }
 }
+#undef LV_STAT
+#define LV_STAT(...)
 
 // One thread per slot: CSR row + area + centroid from the parked ring.  Same walk, arithmetic and checks as the emission
 // part of k_clip_fast; rows of 32 consecutive slots are contiguous (one atomicAdd per warp).
@@ -394,6 +409,18 @@ static int launch_refill(LvContext *c, ClipArgs a) {
     long long grid = (long long)c->num_sms * per_sm;
     const long long need = ((long long)nchunks * (RF_CHUNK / 32) + (BLOCK / 32) - 1) / (BLOCK / 32);
     if (grid > need) grid = need;
+    static const bool stats = [] { const char *m = getenv("LV_CLIP_STATS"); return m && m[0] == '1'; }();
+    if (stats) {
+        unsigned long long *d = nullptr, h[8];
+        LV_CUDA(c, cudaMalloc((void **)&d, sizeof(h)));
+        LV_CUDA(c, cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+        LV_CUDA(c, cudaFuncSetAttribute(k_clip_refill<MAXE, BLOCK, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_clip_refill<MAXE, BLOCK, MINB, true><<<(int)grid, BLOCK, smem, c->stream>>>(a, nchunks, d);
+        LV_CUDA(c, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+        clip_stats_print("refill", h, (int)((nslot + 31) / 32));
+    } else
     k_clip_refill<MAXE, BLOCK, MINB><<<(int)grid, BLOCK, smem, c->stream>>>(a, nchunks);
     k_clip_emit<MAXE><<<(int)((nslot + 255) / 256), 256, 0, c->stream>>>(a);
     c->launches += 2;
