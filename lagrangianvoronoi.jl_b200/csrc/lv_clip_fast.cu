@@ -42,6 +42,7 @@ typedef unsigned long long u64;
 #define QCAP 4 // queued candidates per lane
 #define EV 4   // scan events per lane and round
 #define QLOW 1 // a scan pass starts (and goes on) only while some lane has at most this many candidates queued
+#define BMAX 2 // candidates a lane may pop per round before the warp moves on to the cut
 
 template <int MAXE, int BLOCK>
 struct Ring {
