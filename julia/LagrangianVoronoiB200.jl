@@ -47,6 +47,7 @@ mutable struct DeviceContext
     area::Vector{Float64}
     centroid::Vector{RealVector}
     fields::Dict{Symbol,Vector}  # gather / scatter staging for the pressure solve
+    pending::Bool                # pipelined mode: the last remesh! is still in flight (see sync_mesh!)
 end
 
 # Page-lock a staging vector so that the library can DMA from / store into it directly (full PCIe rate, and the direct
@@ -65,6 +66,7 @@ end
 const CONTEXTS = IdDict{Any,DeviceContext}()
 const DEVICE = Ref{Int32}(0)
 const ENABLED = Ref(false)
+const PIPELINED = Ref(false)   # pipelined!(true): deferred remesh + 20 B/edge wire format (lv_set_async_edges(h, 3))
 
 function check(ctx, status::Int32)
     status == LV_OK && return
@@ -85,7 +87,8 @@ function context(grid::VoronoiGrid)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         st = ccall((:lv_create, LIB), Int32, (Ref{LvGridDesc}, Int32, Ref{Ptr{Cvoid}}), desc, DEVICE[], h)
         st == LV_OK || check(nothing, st)
-        ctx = DeviceContext(h[], RealVector[], Int64[], Edge[], Float64[], RealVector[], Dict{Symbol,Vector}())
+        ctx = DeviceContext(h[], RealVector[], Int64[], Edge[], Float64[], RealVector[], Dict{Symbol,Vector}(), false)
+        PIPELINED[] && check(ctx, ccall((:lv_set_async_edges, LIB), Int32, (Ptr{Cvoid}, Int32), h[], 3))
         finalizer(c -> ccall((:lv_destroy, LIB), Int32, (Ptr{Cvoid},), c.handle), ctx)
         ctx
     end
@@ -115,6 +118,34 @@ function remesh_b200!(grid::VoronoiGrid)
                    ctx.handle, ctx.rowptr, ctx.edges, length(ctx.edges), ctx.area, ctx.centroid)
     end
     check(ctx, st)
+    if PIPELINED[]          # lv_set_async_edges(h, 3): the clip kernel is only queued; the edge view is scattered by sync_mesh!
+        ctx.pending = true
+        return
+    end
+    scatter_edges!(grid, ctx)
+    return
+end
+
+# Pipelined mode (include/lv_capi.h, lv_set_async_edges(h, 3)): remesh! returns with its kernel queued, the next remesh! /
+# find_pressure! uploads while it runs, and the mesh arrives as 20 B/edge expanded by the library's host threads.  The first
+# consumer of p.edges (pressure_step!, export_grid, ...) calls sync_mesh!(grid); errors of the deferred remesh surface there
+# or at the next device call, with the reference's messages.
+function pipelined!(on::Bool = true)
+    for ctx in values(CONTEXTS)
+        check(ctx, ccall((:lv_set_async_edges, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.handle, on ? 3 : 0))
+    end
+    PIPELINED[] = on
+end
+function sync_mesh!(grid::VoronoiGrid)
+    ctx = context(grid)
+    ctx.pending || return
+    check(ctx, ccall((:lv_mesh_wait, LIB), Int32, (Ptr{Cvoid},), ctx.handle))
+    ctx.pending = false
+    scatter_edges!(grid, ctx)
+end
+
+function scatter_edges!(grid::VoronoiGrid, ctx::DeviceContext)
+    n = length(grid.polygons)
     # p.edges keeps its concrete type FastVector{Edge} (polygon.jl:23-27): copy each row into the
     # polygon's own buffer.  (Zero-copy alternative, a two-line change in celldefs.jl:24 and
     # polygon.jl:33: make `edges` a `SubArray` of ctx.edges -- see INTEGRATION.md.)

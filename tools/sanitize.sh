@@ -5,7 +5,7 @@ set -x
 CS=/usr/local/cuda/bin/compute-sanitizer
 OUT=${1:-gpurun_out}
 for tool in memcheck racecheck synccheck; do
-  timeout 900 $CS --tool $tool --error-exitcode 9 --print-limit 20 python tools/sanitize_case.py 32 > $OUT/r2_sanitize_$tool.log 2>&1
+  timeout 900 $CS --tool $tool --error-exitcode 9 --print-limit 20 python tools/sanitize_case.py ${SAN_M:-32} > $OUT/r2_sanitize_$tool.log 2>&1
   echo "$tool exit $?" >> $OUT/r2_sanitize_$tool.log
   tail -4 $OUT/r2_sanitize_$tool.log
 done

@@ -20,11 +20,16 @@ rng = np.random.default_rng(0)
 xy = lv.synthetic.jittered_lattice(M, 0)
 g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), dr, xperiodic=True, yperiodic=True)
 g.set_points(xy)
-for lazy in (False, True, "all"):
+for lazy in (False, True, "all", "pipeline"):
     lv.remesh(g, lazy=lazy)
     lv.wait_edges(g)
-lv.remesh(g)
+# pipelined mode: deferred remesh completed by the next remesh / by find_pressure (uploads on their own stream)
 v, P = lv.synthetic.taylor_green_fields(xy)
+lv.remesh(g, lazy="pipeline"); lv.remesh(g, lazy="pipeline")
+g.rho[...] = 1.0; g.mass[...] = 1.0 / len(xy); g.c2[...] = 100.0; g.v[...] = v; g.P[...] = P
+lv.find_pressure(lv.PressureSolver(g), 0.1 * dr, 2)
+lv.wait_edges(g)
+lv.remesh(g)
 g.rho[...] = 1.0; g.mass[...] = lv.area(g); g.c2[...] = 100.0; g.v[...] = v; g.P[...] = P
 for kry in ("cg", "minres"):
     s = lv.PressureSolver(g, solver=kry)
