@@ -308,6 +308,7 @@ static int ensure_generators(LvContext *c, int64_t n, bool need_xy) {
 
 } // extern "C"
 int lv_remesh_common(LvContext *c, int64_t n) {
+    if (c->pipe) LV_TRY(lv_pipe_settle(c)); // a pipelined download of the mesh about to be replaced may need full records
     c->mesh_valid = false;
     c->assembled = false;
     // the pressure fields live in slot order and every remesh re-sorts the slots: whatever was uploaded before is
@@ -519,6 +520,9 @@ int32_t lv_mesh_wait(LvHandle c) {
 int32_t lv_mesh_download(LvHandle c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
     if (!c) return LV_EINVAL;
     LV_ENTER(c);
+    // pipelined mode: 20 B/edge wire format + host-side expansion in the background (NO output may be read before lv_mesh_wait)
+    if (c->pipe_mode && c->mesh_valid && c->n > 0 && (rowptr || edges || area || centroid))
+        return lv_pipe_download(c, rowptr, edges, cap, area, centroid);
     return lv_mesh_to_labels(c, rowptr, edges, cap, area, centroid);
 }
 

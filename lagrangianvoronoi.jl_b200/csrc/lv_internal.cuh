@@ -230,6 +230,8 @@ int lv_pipe_enable(LvContext *c);
 int lv_pipe_remesh(LvContext *c, int64_t n, const double *xy, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid);
 int lv_pipe_wait(LvContext *c);  // deferred remesh completed and every queued download delivered
 int lv_pipe_drain(LvContext *c); // every queued download delivered
+int lv_pipe_settle(LvContext *c); // queued downloads that declined (open chain) are delivered as full records, now
+int lv_pipe_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid);
 bool lv_pipe_busy(const LvContext *c);
 void lv_pipe_destroy(LvContext *c);
 int lv_pipe_upload_begin(LvContext *c, const double *const src[5], const int nc[5], const double *dev[5]);

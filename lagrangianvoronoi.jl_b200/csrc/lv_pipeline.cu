@@ -60,6 +60,9 @@ struct PipeJob {
     const int *snap = nullptr; // status words of the clip attempt + [9] = "chains are not closed"
     cudaEvent_t ev_conv = nullptr;
     // results
+    int64_t nnz_known = -1; // >= 0: download of a mesh that already stands (lv_pipe_download); the snapshot only carries [9]
+    int decided = 0; // 0 not yet, 1 the job delivers the mesh, 2 it will not (status becomes 2)
+    bool handled = false; // a skipped job whose mesh was delivered synchronously (lv_pipe_finish / lv_pipe_settle)
     int status = 0; // 0 queued / running, 1 done, 2 skipped (lv_pipe_finish replays or downloads synchronously), < 0 error
     int err_code = LV_OK;
     std::string err;
@@ -92,6 +95,7 @@ struct LvPipe {
     PipeJob *job[2] = {nullptr, nullptr}; // last job of each staging buffer
     int stage_cur = 0;
     cudaEvent_t ev_hdr = nullptr;
+    int *d_clean_flags = nullptr; // 8 zero words: "status" of a mesh that already stands (lv_pipe_download)
     // deferred remesh: staging buffer / snapshot index and the caller's output buffers
     int pend_sb = 0;
     int64_t *pend_rowptr = nullptr;
@@ -268,13 +272,26 @@ static void job_fail(LvPipe *P, PipeJob *j, int code, const std::string &msg) {
 static int pipe_run_job(LvPipe *P, PipeJob *j) {
     LvContext *c = P->c;
     cudaError_t e = cudaEventSynchronize(j->ev_conv);
-    if (e != cudaSuccess) { job_fail(P, j, LV_ECUDA, std::string("remesh failed: ") + cudaGetErrorString(e)); return -1; }
+    if (e != cudaSuccess) {
+        job_fail(P, j, LV_ECUDA, std::string("remesh failed: ") + cudaGetErrorString(e));
+        { std::lock_guard<std::mutex> lk(P->mu); j->decided = 2; j->handled = true; }
+        P->cv_done.notify_all();
+        return -1;
+    }
     const int *hf = j->snap;
-    if (hf[LVF_NAN] || hf[LVF_DESTROYED] || hf[LVF_OVERFLOW] || hf[9]) return 2; // lv_pipe_finish deals with all of these
+    {
+        const bool skip = hf[LVF_NAN] || hf[LVF_DESTROYED] || hf[LVF_OVERFLOW] || hf[9]; // lv_pipe_finish / lv_pipe_settle deal with these
+        {
+            std::lock_guard<std::mutex> lk(P->mu);
+            j->decided = skip ? 2 : 1;
+        }
+        P->cv_done.notify_all();
+        if (skip) return 2;
+    }
     const double tr0 = P->trace ? pipe_now_ms(P) : 0.0;
     double tr1 = 0.0;
     if (P->trace) { std::lock_guard<std::mutex> lk(P->mu); P->tr_expand_ms = P->tr_evwait_ms = 0.0; }
-    const int64_t n = j->n, nnz = hf[LVF_NNZ];
+    const int64_t n = j->n, nnz = j->nnz_known >= 0 ? j->nnz_known : hf[LVF_NNZ];
     if (j->edges && j->cap < nnz) {
         char buf[128];
         snprintf(buf, sizeof(buf), "edge buffer too small: nnz = %lld, cap = %lld", (long long)nnz, (long long)j->cap);
@@ -365,7 +382,9 @@ static int host_threads_default() {
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = (unsigned)CPU_COUNT(&set);
 #endif
-    int t = (int)hc - 2;
+    int ranks = 1; // torchrun: the ranks of a node share its cores
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) ranks = v; }
+    int t = ((int)hc - 2) / ranks;
     if (t < 2) t = 2;
     if (t > 16) t = 16;
     return t;
@@ -394,6 +413,8 @@ int lv_pipe_enable(LvContext *c) {
     }
     { const char *t = getenv("LV_PIPE_TRACE"); P->trace = t && t[0] == '1'; }
     P->epoch = std::chrono::steady_clock::now();
+    LV_CUDA(c, cudaMalloc((void **)&P->d_clean_flags, sizeof(int) * 8));
+    LV_CUDA(c, cudaMemset(P->d_clean_flags, 0, sizeof(int) * 8));
     P->downloader = std::thread(pipe_downloader, P);
     const int nw = host_threads_default();
     for (int k = 0; k < nw; k++) P->workers.emplace_back(pipe_worker, P);
@@ -452,6 +473,7 @@ void lv_pipe_destroy(LvContext *c) {
         if (P->ev_conv[k]) cudaEventDestroy(P->ev_conv[k]);
         if (P->d_xy_alt[k]) cudaFree(P->d_xy_alt[k]);
     }
+    if (P->d_clean_flags) cudaFree(P->d_clean_flags);
     if (P->ev_up) cudaEventDestroy(P->ev_up);
     if (P->ev_hdr) cudaEventDestroy(P->ev_hdr);
     if (P->up_stream) cudaStreamDestroy(P->up_stream);
@@ -463,8 +485,12 @@ void lv_pipe_destroy(LvContext *c) {
 
 // ---- the deferred remesh ------------------------------------------------------------------------------------------------
 // queue conversion + snapshot behind the clip attempt and hand the download to the thread pool
-static int pipe_queue_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
+static int pipe_queue_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid,
+                               int64_t nnz_known = -1) {
     LvPipe *P = c->pipe;
+    // status words the conversion looks at: those of the clip attempt just queued, or "clean" for a mesh that stands
+    // (d_flags is reused by the stepping and strip kernels after a remesh)
+    const int *flags = nnz_known >= 0 ? P->d_clean_flags : c->d_flags;
     const int64_t n = c->n, capz = c->cap_nnz;
     const int sb = (P->stage_cur ^= 1);
     // the previous user of this staging buffer (two remeshes ago) must be through with it
@@ -509,13 +535,13 @@ static int pipe_queue_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int
     unsigned *lab = (unsigned *)(base + off_lab);
     const int nb = (int)((n + 256) / 256);
     LV_CUDA(c, cudaMemsetAsync(open_chain, 0, sizeof(int), c->stream));
-    k_pipe_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_deg, c->d_flags, deg);
+    k_pipe_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_deg, flags, deg);
     c->launches++;
     LV_TRY(lv_exclusive_scan_i32(c, deg, rl, n));
     k_pipe_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
-                                           c->d_area, c->d_cen, c->d_flags, r64, vout, lab, area_l, cen_l, open_chain);
-    k_pipe_hdr<<<(int)((nchunks_cap + 127) / 128), 128, 0, c->stream>>>(n, rl, vout, c->d_flags, (int)nchunks_cap, hdr);
-    k_pipe_publish<<<1, 32, 0, c->stream>>>(c->d_flags, open_chain, P->snap[sb]);
+                                           c->d_area, c->d_cen, flags, r64, vout, lab, area_l, cen_l, open_chain);
+    k_pipe_hdr<<<(int)((nchunks_cap + 127) / 128), 128, 0, c->stream>>>(n, rl, vout, flags, (int)nchunks_cap, hdr);
+    k_pipe_publish<<<1, 32, 0, c->stream>>>(flags, open_chain, P->snap[sb]);
     c->launches += 3;
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(P->ev_conv[sb], c->stream));
@@ -525,6 +551,7 @@ static int pipe_queue_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int
     j->rowptr = rowptr; j->edges = edges; j->cap = cap; j->area = area; j->centroid = centroid;
     j->snap = P->snap[sb];
     j->ev_conv = P->ev_conv[sb];
+    j->nnz_known = nnz_known;
     {
         std::lock_guard<std::mutex> lk(P->mu);
         P->job[sb] = j;
@@ -558,6 +585,7 @@ int lv_pipe_remesh(LvContext *c, int64_t n, const double *xy, int64_t *rowptr, L
     LV_CUDA(c, cudaEventRecord(P->ev_up, P->up_stream));
     // 2. complete the previous remesh (host waits for its kernel; errors of that remesh surface here)
     LV_TRY(lv_pipe_finish(c));
+    LV_TRY(lv_pipe_settle(c));
     LV_CUDA(c, cudaStreamWaitEvent(c->stream, P->ev_up, 0));
     c->xy = dst;
     c->owned_mask = nullptr;
@@ -596,6 +624,7 @@ int lv_pipe_finish(LvContext *c) {
     {
         std::unique_lock<std::mutex> lk(P->mu);
         P->cv_done.wait(lk, [&] { return !P->job[sb] || P->job[sb]->status != 0; });
+        if (P->job[sb]) P->job[sb]->handled = true;
     }
     LV_TRY(lv_pipe_drain(c));
     if (P->pend_rowptr || P->pend_edges || P->pend_area || P->pend_cen)
@@ -603,8 +632,39 @@ int lv_pipe_finish(LvContext *c) {
     return LV_OK;
 }
 
+// A download of the CURRENT mesh queued outside lv_pipe_remesh (lv_mesh_download in pipelined mode): the mesh stands, so
+// the only way the job can decline is an open chain; lv_pipe_settle then delivers full records while the mesh is still
+// there -- every remesh calls it before it touches the mesh arrays.
+int lv_pipe_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int64_t cap, double *area, double *centroid) {
+    if (edges && cap < c->nnz) return lv_set_error(c, LV_ECAPACITY, "edge buffer too small: nnz = %lld, cap = %lld", (long long)c->nnz, (long long)cap);
+    return pipe_queue_download(c, rowptr, edges, cap, area, centroid, c->nnz);
+}
+int lv_pipe_settle(LvContext *c) {
+    LvPipe *P = c->pipe;
+    if (!P) return LV_OK;
+    for (int k = 0; k < 2; k++) {
+        PipeJob *j = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(P->mu);
+            if (!P->job[k]) continue;
+            P->cv_done.wait(lk, [&] { return P->job[k]->decided != 0 || P->job[k]->status != 0; });
+            if (P->job[k]->decided == 2 && !P->job[k]->handled && P->job[k]->err_code == LV_OK) { j = P->job[k]; j->handled = true; }
+        }
+        if (!j) continue;
+        // wait for the job to leave the thread pool, then deliver synchronously (the staging buffers are shared)
+        {
+            std::unique_lock<std::mutex> lk(P->mu);
+            P->cv_done.wait(lk, [&] { return j->status != 0; });
+        }
+        int64_t *r = j->rowptr; LvEdge *e = j->edges; const int64_t cp = j->cap; double *a = j->area, *ce = j->centroid;
+        if (c->mesh_valid) LV_TRY(lv_mesh_to_labels(c, r, e, cp, a, ce)); // drains (and frees) the jobs first
+    }
+    return LV_OK;
+}
+
 int lv_pipe_wait(LvContext *c) {
     LV_TRY(lv_pipe_finish(c));
+    LV_TRY(lv_pipe_settle(c));
     return lv_pipe_drain(c);
 }
 

@@ -195,6 +195,8 @@ class VoronoiGrid:
         ar = _host_empty((n,), np.float64)
         ce = _host_empty((n, 2), np.float64)
         check(self._L.lv_mesh_download(self._h, ptr(rowptr), ptr(e), nnz, ptr(ar), ptr(ce)), self._h)
+        if getattr(self, "_lazy_edges", 0) == 3:  # pipelined mode: the download runs in the background
+            check(self._L.lv_mesh_wait(self._h), self._h)
         return rowptr, e, ar, ce
 
 

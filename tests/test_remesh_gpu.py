@@ -223,6 +223,14 @@ def test_pipelined_mode_delivers_the_same_bytes(lv, monkeypatch):
             assert np.array_equal(g.rowptr, ref[0]) and g.edges.tobytes() == ref[1].tobytes()
             assert np.array_equal(lv.area(g), ref[2]) and np.array_equal(lv.centroid(g), ref[3])
             assert np.array_equal(s.iters, it_ref) and np.array_equal(g.P, P_ref)
+        # an explicit download of the standing mesh takes the wire format too (lv_mesh_download in mode 3), also after
+        # device-resident remeshes, and is settled before the next remesh replaces the mesh
+        from lvb200._capi import check
+        check(g._L.lv_set_async_edges(g._h, 3), g._h)
+        g._lazy_edges = 3
+        g.remesh_dev(__import__("torch").from_numpy(xy).cuda())
+        rp, ed, ar, ce = g.mesh_download(len(xy))
+        assert np.array_equal(rp, ref[0]) and ed.tobytes() == ref[1].tobytes() and np.array_equal(ar, ref[2])
         lv.remesh(g)                                              # back to the synchronous mode
         assert g.edges.tobytes() == ref[1].tobytes()
 
