@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--e2e-mode", default="pipeline", choices=["pipeline", "all"],
                     help="host-buffer leg: pipeline = lv_set_async_edges(h, 3) (deferred remesh, 20 B/edge wire format), all = mode 2")
     ap.add_argument("--no-strong", action="store_true", help="skip the 64M strong-scaling leg")
+    ap.add_argument("--no-shuffle", action="store_true", help="N = 1: skip the shuffled-label leg (worst case of Lagrangian drift)")
     ap.add_argument("--strong-side", type=int, default=STRONG_SIDE)
     ap.add_argument("--strong-steps", type=int, default=5, help="timed steps of the strong leg (min with --steps)")
     ap.add_argument("--sweep", action="store_true", help="N = 1: also time the 1M / 4M sizes and c0 = 1000 (submetrics.sweep)")
@@ -228,14 +229,18 @@ def expected_hash(M, My, seed):
         return None
 
 
-def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
-    """One GPU, the whole periodic unit box through the plain VoronoiGrid / PressureSolver handles."""
+def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True, shuffle_labels=False):
+    """One GPU, the whole periodic unit box through the plain VoronoiGrid / PressureSolver handles.
+    shuffle_labels: the same generators under a random permutation of their labels -- the limit of Lagrangian drift, where
+    a label says nothing about the position any more (label-ordered inputs scatter over the whole cell list)."""
     import torch
     lv, dev, stream = env.lv, env.dev, env.stream
     dr = 1.0 / M
     dt = 0.1 * dr
     n = M * M
     xy = lv.synthetic.jittered_lattice(M, args.seed)
+    if shuffle_labels:
+        xy = np.ascontiguousarray(xy[np.random.default_rng(args.seed).permutation(n)])
     g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), dr, xperiodic=True, yperiodic=True, device=env.local)
     g.set_stream(stream.cuda_stream)
     g.set_points(xy)
@@ -260,7 +265,7 @@ def leg_single(env, args, M, steps, warmup, c0, with_e2e, profile=True):
     out.update(n=n, n_total=n, parallelism="single GPU", M=M, My=M)
     hv = (C_uint64 * 6)()
     lvcheck(g._L.lv_mesh_hash(g._h, None, hv), g)
-    out["checks"] = mesh_checks(env, hv, float(area.sum()), 1.0, n, M, M, args.seed, periodic=True)
+    out["checks"] = mesh_checks(env, hv, float(area.sum()), 1.0, n, M, M, None if shuffle_labels else args.seed, periodic=True)
 
     if with_e2e:
         # every step must solve the same problem (cold P), so the initial P is staged once per step in pinned host memory
@@ -571,6 +576,15 @@ def run_ours(args):
         r2 = leg_single(env, a2, M, max(1, min(args.steps, 3)), 2, args.c0, with_e2e=False)
         line["submetrics"]["plain_cg"] = {"ms_per_step": r2["ms_max"] / r2["steps"], "krylov_iters_per_step": r2["iters_total"] // r2["steps"],
                                           "phase_ms_per_step": {k: v[0] / r2["steps"] for k, v in r2["prof"].items()}}
+
+    # ---- worst case of Lagrangian drift: labels carry no spatial information (N = 1 only; a few steps) -----------------
+    if world == 1 and not args.no_shuffle:
+        r3 = leg_single(env, args, M, max(1, min(args.steps, 3)), 2, args.c0, with_e2e=False, shuffle_labels=True)
+        line["submetrics"]["shuffled_labels"] = {
+            "what": "same generators, labels randomly permuted (limit of Lagrangian drift: label order unrelated to position)",
+            "ms_per_step": r3["ms_max"] / r3["steps"], "krylov_iters_per_step": r3["iters_total"] // r3["steps"],
+            "phase_ms_per_step": {k: v[0] / r3["steps"] for k, v in r3["prof"].items()},
+            "rows_eq_cells": r3["checks"].get("rows_eq_cells"), "euler_sum_deg_eq_6n": r3["checks"].get("euler_sum_deg_eq_6n")}
 
     # ---- CPU sample beside it (rank 0, N = 1 only) -------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -385,7 +385,7 @@ static int host_threads_default() {
     int ranks = 1; // torchrun: the ranks of a node share its cores
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) ranks = v; }
     int t = ((int)hc - 2) / ranks;
-    if (t < 2) t = 2;
+    if (t < 3) t = 3; // the workers mostly wait (events, memory): a little oversubscription beats a starved download
     if (t > 16) t = 16;
     return t;
 }

@@ -3,7 +3,11 @@ warp-scheduling policies of the GPU clipping kernel (K2, lv_clip_fast.cu) and co
 calibrated on the kernel's own counters (LV_CLIP_STATS=1) and its ncu instruction attribution.
 
   python oracle/experiments/clip_sim.py /tmp/trace.bin tile            # the production tile kernel
-  python oracle/experiments/clip_sim.py /tmp/trace.bin refill          # lane refill, ...
+  python oracle/experiments/clip_sim.py /tmp/trace.bin tile_v1         # the kernel before the scan-policy changes
+  python oracle/experiments/clip_sim.py /tmp/trace.bin refill          # lane refill (old round), tile_merged, refill_merged
+
+Measured after the scan-policy changes (QLOW=1, EV=4, BMAX=2): rounds/tile 21.02, alive/round 23.00, A 64.4 @ 18.50,
+B 34.0 @ 16.75, C 17.4 @ 17.81 -- the simulator says 21.04 / 23.23 / 64.4 @ 18.70 / 34.2 @ 16.87 / 17.6 @ 17.85.
 
 Measured on B200 at 16.8M cells (tile kernel): rounds/tile 16.99, alive/round 21.81, A 98.4 events/tile @ 12.17 lanes,
 B 51.4 iterations/tile @ 11.70 lanes, C 15.1 cuts/tile @ 20.59 lanes, 970 warp instructions per cell
@@ -76,8 +80,54 @@ class Lane:
         return adv, tst
 
 
+def sim_tile_policy(lanes, QCAP=4, EV=4, QLOW=1, BMAX=2, skip_self=True, stats=None):
+    """The production kernel (lv_clip_round.inc): a scan pass runs only while some lane has <= QLOW candidates queued, EV
+    events per pass, the generator's own entry never queued, at most BMAX pops per lane and round, then the cut."""
+    cost = 0.0
+    for l in lanes:
+        l.plus = -1
+    while any(l.alive for l in lanes):
+        if any(l.alive and not l.scan_done and len(l.q) <= QLOW for l in lanes):
+            for _ in range(EV):
+                sc = [l for l in lanes if l.alive and not l.scan_done and len(l.q) < QCAP
+                      and not (l.kind[l.i] == 5 and not l.d2[l.i] > l.prr)]
+                if not sc or not any(len(l.q) <= QLOW for l in sc):
+                    break
+                for l in sc:
+                    l.scan_event()
+                    if skip_self and l.q and l.kind[l.q[-1]] == 1:
+                        l.q.pop()
+                stats["a_it"] += 1; stats["a_ln"] += len(sc)
+                cost += COST["A"]
+        b_max = b_sum = 0
+        for l in lanes:
+            nb = 0
+            while l.alive and l.q and l.plus < 0 and nb < BMAX:
+                j = l.q.pop(0)
+                nb += 1
+                k = l.kind[j]
+                if k == 1 or l.d2[j] > l.prr:
+                    continue
+                if k == 4:
+                    l.plus = j
+            b_max = max(b_max, nb); b_sum += nb
+            if l.alive and l.plus < 0 and l.scan_done and not l.q:
+                l.alive = False
+        stats["b_it"] += b_max; stats["b_ln"] += b_sum
+        cost += COST["B"] * b_max
+        stats["rounds"] += 1; stats["alive"] += sum(l.alive for l in lanes)
+        cut = [l for l in lanes if l.alive and l.plus >= 0]
+        if cut:
+            for l in cut:
+                l.prr = l.pa[l.plus]; l.plus = -1
+            stats["c_it"] += 1; stats["c_ln"] += len(cut)
+            cost += COST["C"]
+        cost += COST["ROUND"]
+    return cost + COST["EMIT"]
+
+
 def sim_tile_kernel(lanes, QCAP=4, EV=8, stats=None):
-    """The production kernel: rounds of A (scan ahead) / B (pop until a vertex is outside) / C (cut)."""
+    """The round-1 / first-session kernel: rounds of A (scan whenever a queue has room) / B (pop until a vertex is outside) / C."""
     cost = 0.0
     while any(l.alive for l in lanes):
         # phase A
@@ -260,8 +310,13 @@ def main():
     if what == "tile":
         for ti in range(ntiles):
             lanes = [Lane(p[2], p[3]) for p in polys[32 * ti: 32 * ti + 32]]
+            total += sim_tile_policy(lanes, stats=stats)
+        report("tile (production: QLOW=1 EV=4 BMAX=2)", stats, ntiles, total)
+    elif what == "tile_v1":
+        for ti in range(ntiles):
+            lanes = [Lane(p[2], p[3]) for p in polys[32 * ti: 32 * ti + 32]]
             total += sim_tile_kernel(lanes, stats=stats)
-        report("tile", stats, ntiles, total)
+        report("tile_v1 (scan whenever there is room, EV=8, pop until a cut)", stats, ntiles, total)
     elif what == "tile_merged":
         for ti in range(ntiles):
             lanes = [Lane(p[2], p[3]) for p in polys[32 * ti: 32 * ti + 32]]

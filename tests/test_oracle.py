@@ -339,3 +339,40 @@ def test_per_edge_wall_data_reduces_to_the_per_wall_constants(oracle):
     og.set("v", v_before)
     og.bdary_friction_ex(0.01, vwall=vw, wall_on=np.zeros(4, np.uint8))          # every wall switched off: nothing happens
     assert np.array_equal(og.get("v"), v_before)
+
+
+def test_clip_scheduling_simulator_reproduces_the_kernels_counters(lv, oracle, tmp_path):
+    """oracle/experiments: the neighbour-walk traces of the restatement, replayed under the clipping kernel's warp
+    scheduling policy, reproduce the per-phase counters the kernel reports on the GPU (LV_CLIP_STATS=1, 16.8M cells:
+    old policy 17.0 rounds / 98.4 scan events @ 12.2 lanes / 51.4 pops @ 11.7 / 15.1 cuts @ 20.6; production policy
+    21.0 / 64.4 @ 18.5 / 34.0 @ 16.8 / 17.4 @ 17.8).  This is what the K2 scan policy was tuned with."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "clip_trace")
+    src = os.path.join(ROOT, "oracle", "experiments", "clip_trace.c")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-w", "-o", exe, src, "-lm"], check=True)
+    M = 96
+    xy = lv.synthetic.jittered_lattice(M, 0)
+    trace = str(tmp_path / "trace.bin")
+    subprocess.run([exe, str(M), "0", trace], input=xy.tobytes(), check=True, capture_output=True)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "experiments"))
+    import clip_sim as cs
+    polys = cs.load(trace)
+    ntiles = len(polys) // 32
+    cuts = np.mean([(p[2]["kind"] == 4).sum() for p in polys])
+    assert 9.0 < cuts < 10.5                                       # cuts per polygon on the jittered lattice
+
+    def run(policy):
+        st = dict(rounds=0, alive=0, a_it=0, a_ln=0, b_it=0, b_ln=0, c_it=0, c_ln=0)
+        cost = sum(policy([cs.Lane(p[2], p[3]) for p in polys[32 * t: 32 * t + 32]], stats=st) for t in range(ntiles))
+        return {"rounds": st["rounds"] / ntiles, "a": st["a_it"] / ntiles, "a_ln": st["a_ln"] / st["a_it"], "b": st["b_it"] / ntiles,
+                "b_ln": st["b_ln"] / st["b_it"], "c": st["c_it"] / ntiles, "c_ln": st["c_ln"] / st["c_it"], "instr": cost / ntiles / 32}
+
+    old, new = run(cs.sim_tile_kernel), run(cs.sim_tile_policy)
+    for got, want in ((old, dict(rounds=17.0, a=98.4, a_ln=12.2, b=51.4, b_ln=11.7, c=15.1, c_ln=20.6, instr=970)),
+                      (new, dict(rounds=21.0, a=64.4, a_ln=18.5, b=34.0, b_ln=16.8, c=17.4, c_ln=17.8, instr=850))):
+        for k, v in want.items():
+            assert abs(got[k] - v) <= 0.05 * v, (k, got[k], v)    # within 5 % of the GPU's own counters
+    assert new["instr"] < 0.9 * old["instr"]
