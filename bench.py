@@ -475,7 +475,10 @@ def e2e_strips(env, args, sg, solver, g, dt, n_total, steps, c0, edges):
     edge_h = _host_empty((cap,), EDGE_DTYPE) if edges else None
     # pipeline: 20 B/edge wire format expanded by host threads of the library (the ranks of a node share its cores);
     # all: 40-byte records copied lazily on a second stream
-    wire = edges and E2E_MODE == "pipeline"
+    # The expansion needs host cores: with 8 ranks on a 16-core host (2 per rank) the wire format measured SLOWER than plain
+    # 40-byte DMA (945 vs 805 ms per step), with 2 ranks (7 per rank) faster (264 vs 284 ms) -- so it is used from 6 cores per rank.
+    cores_per_rank = host_threads() / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    wire = edges and E2E_MODE == "pipeline" and cores_per_rank >= 6
     if edges:
         check(g._L.lv_set_async_edges(g._h, 3 if wire else 1), g._h)
 
@@ -507,7 +510,7 @@ def e2e_strips(env, args, sg, solver, g, dt, n_total, steps, c0, edges):
     ms = float(te.item())
     return {"value": n_total * steps / (ms / 1e3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(byt[0]),
             "d2h_bytes_per_step": int(byt[1]), "ms_per_step": ms / steps,
-            "mode": E2E_MODE if edges else None,
+            "mode": ("pipeline" if wire else "all") if edges else None, "host_cores_per_rank": cores_per_rank,
             "contract": ("strip API, per rank: positions + fields up; rowptr, "
                          + ("40-B edge records" + (" (20 B on the wire, expanded by host threads), " if wire else ", ") if edges else "")
                          + "areas, centroids (x2) and P down"

@@ -106,7 +106,9 @@ int32_t lv_mesh_download(LvHandle h, int64_t *rowptr, LvEdge *edges, int64_t cap
  * PCIe as 20 B per edge (start vertex + 32-bit label word; the end vertex of an edge is the start vertex of its successor
  * in the chain sort_edges! leaves, checked bit for bit on the device) and host threads of the library (LV_HOST_THREADS,
  * default min(16, cores - 2)) expand it into the caller's 40-byte records; a mesh with an open chain is delivered as full
- * records instead.  NO output buffer may be read before lv_mesh_wait.
+ * records instead.  NO output buffer may be read before lv_mesh_wait.  lv_mesh_download in this mode sends the mesh that
+ * stands (after lv_remesh_dev / lv_strip_remesh) the same way and returns at once; the next remesh first settles such a
+ * download (full records if the chains are open) before it replaces the mesh.
  * Environment switches (diagnostics): LV_DIRECT_STORE=0 disables the direct stores, LV_FLAG_MODE=memcpy reads status
  * words with cudaMemcpy instead of mapped memory. */
 int32_t lv_set_async_edges(LvHandle h, int32_t on);

@@ -235,6 +235,49 @@ def test_pipelined_mode_delivers_the_same_bytes(lv, monkeypatch):
         assert g.edges.tobytes() == ref[1].tobytes()
 
 
+def test_pipelined_mode_survives_resizing_and_the_strip_api(lv):
+    """One handle, generator sets of growing and shrinking size (the position buffers, the chunk-header buffers and the
+    staging areas of the pipelined mode are re-allocated on the way), then the strip API's local mesh through the wire
+    format: every delivery equals the synchronous one."""
+    import torch
+    from lvb200._capi import check
+    from lvb200.distributed import StripGrid
+    g = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), 1 / 64, xperiodic=True, yperiodic=True)
+    for M in (20, 64, 33, 330, 48):
+        xy = lv.synthetic.jittered_lattice(M, M)
+        g2 = lv.VoronoiGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), 1 / M, xperiodic=True, yperiodic=True)
+        g2.set_points(xy)
+        lv.remesh(g2)
+        ref = (g2.rowptr.copy(), g2.edges.copy(), lv.area(g2).copy())
+        # the pipelined handle keeps its cell list (dr = 1/64): same generators, another bucket size -> compare on its own terms
+        g.set_points(xy)
+        lv.remesh(g, lazy="pipeline")
+        lv.remesh(g, lazy="pipeline")
+        lv.wait_edges(g)
+        got = (g.rowptr.copy(), g.edges.copy(), lv.area(g).copy())
+        lv.remesh(g)
+        assert np.array_equal(got[0], g.rowptr) and got[1].tobytes() == g.edges.tobytes() and np.array_equal(got[2], lv.area(g))
+        if M == 64:
+            assert np.array_equal(got[0], ref[0]) and got[1].tobytes() == ref[1].tobytes()
+    # strip API on one rank: the local mesh of a StripGrid, downloaded in mode 0 and in mode 3
+    M = 96
+    xy = lv.synthetic.jittered_lattice(M, 3)
+    sg = StripGrid(lv.Rectangle((0.0, 0.0), (1.0, 1.0)), 1 / M, xperiodic=True, yperiodic=True, device=0)
+    sg.set_owned(xy, np.arange(1, len(xy) + 1))
+    sg.remesh()
+    rp0, e0, a0, c0 = sg.mesh_download()
+    check(sg.grid._L.lv_set_async_edges(sg.grid._h, 3), sg.grid._h)
+    sg.grid._lazy_edges = 3
+    sg.remesh()
+    rp1, e1, a1, c1 = sg.mesh_download()
+    assert np.array_equal(rp0, rp1) and e0.tobytes() == e1.tobytes() and np.array_equal(a0, a1) and np.array_equal(c0, c1)
+    sg.remesh()                                                    # settles the previous download before the mesh is replaced
+    check(sg.grid._L.lv_set_async_edges(sg.grid._h, 0), sg.grid._h)
+    sg.grid._lazy_edges = 0
+    sg.close()
+    torch.cuda.synchronize()
+
+
 def test_pipelined_mode_on_degenerate_and_replayed_meshes(lv, monkeypatch):
     """The deferred remesh climbs the same ladder: anomalies replay with the edge-list kernel when the remesh is completed,
     meshes whose chains are not closed bit for bit come back as full records, and a destroyed mesh raises at the wait."""
