@@ -109,7 +109,7 @@ struct LvContext {
     double *d_mass = nullptr, *d_rho = nullptr, *d_c2 = nullptr, *d_P = nullptr;
     double2 *d_v = nullptr, *d_GP = nullptr;
     double *d_diag = nullptr, *d_w = nullptr; // operator: diagonal [nslot], weights [nnz]
-    double *d_dinv = nullptr;                 // [nslot] 1/A_ii: Jacobi preconditioner of LV_SOLVER_PCG
+    double *d_dinv = nullptr;                 // [nslot] 1/A_ii, stored as FLOAT (the buffer is sized for doubles): Jacobi preconditioner of LV_SOLVER_PCG
     double *d_lrr = nullptr;                  // [nnz] lr_ratio of the edge (polygon.jl:228)
     double2 *d_mx = nullptr, *d_mz = nullptr; // [nnz] m - p.x and m - z (pressure.jl:178,198)
     double *d_bvel = nullptr;                 // [nslot] P-independent part of the right-hand side
