@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(256) k_pipe_deg(int64_t n, const int *__restri
     deg[i] = (!bad && s >= 0) ? rdeg[s] : 0;
 }
 
+// CHECK: compare every end vertex with its successor's start vertex.  The linked-slot kernel (levels 0-1) emits v2 as the
+// very value it emits as the successor's v1, so its chains are closed by construction and the 16 B/edge of v2 stay unread;
+// the edge-list kernel (levels 2-4) chains with ==, where -0.0 == 0.0.
+template <bool CHECK>
 __global__ void __launch_bounds__(256) k_pipe_copy(int64_t n, const int *__restrict__ prim, const int *__restrict__ rowptr,
                                                    const unsigned char *__restrict__ rdeg, const int *__restrict__ rowptr_l,
                                                    const int *__restrict__ col, const double2 *__restrict__ v1, const double2 *__restrict__ v2,
@@ -151,10 +155,12 @@ __global__ void __launch_bounds__(256) k_pipe_copy(int64_t n, const int *__restr
     cen_l[i] = cen[s];
     bool open = false;
     for (int k = 0; k < d; k++) {
-        const double2 a = v1[r0 + k], b = v2[r0 + k];
-        const double2 nx = v1[r0 + (k + 1 < d ? k + 1 : 0)];
-        // bitwise: -0.0 == 0.0 chains for sort_edges! but is not the same record
-        open |= (__double_as_longlong(b.x) != __double_as_longlong(nx.x)) | (__double_as_longlong(b.y) != __double_as_longlong(nx.y));
+        const double2 a = v1[r0 + k];
+        if (CHECK) {
+            const double2 b = v2[r0 + k], nx = v1[r0 + (k + 1 < d ? k + 1 : 0)];
+            // bitwise: -0.0 == 0.0 chains for sort_edges! but is not the same record
+            open |= (__double_as_longlong(b.x) != __double_as_longlong(nx.x)) | (__double_as_longlong(b.y) != __double_as_longlong(nx.y));
+        }
         const int cc = col[r0 + k];
         unsigned w = cc >= 0 ? ((ent_label[cc] & ~LV_IMAGE_BIT) + 1u) : (WIRE_WALL | (unsigned)(-cc));
         if (k == d - 1) w |= WIRE_END;
@@ -538,8 +544,12 @@ static int pipe_queue_download(LvContext *c, int64_t *rowptr, LvEdge *edges, int
     k_pipe_deg<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_deg, flags, deg);
     c->launches++;
     LV_TRY(lv_exclusive_scan_i32(c, deg, rl, n));
-    k_pipe_copy<<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
-                                           c->d_area, c->d_cen, flags, r64, vout, lab, area_l, cen_l, open_chain);
+    if (c->clip_last_level >= 2)
+        k_pipe_copy<true><<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
+                                                     c->d_area, c->d_cen, flags, r64, vout, lab, area_l, cen_l, open_chain);
+    else
+        k_pipe_copy<false><<<nb, 256, 0, c->stream>>>(n, c->d_prim_of_label, c->d_rowptr, c->d_deg, rl, c->d_col, c->d_v1, c->d_v2, c->d_ent_label,
+                                                      c->d_area, c->d_cen, flags, r64, vout, lab, area_l, cen_l, open_chain);
     k_pipe_hdr<<<(int)((nchunks_cap + 127) / 128), 128, 0, c->stream>>>(n, rl, vout, flags, (int)nchunks_cap, hdr);
     k_pipe_publish<<<1, 32, 0, c->stream>>>(flags, open_chain, P->snap[sb]);
     c->launches += 3;
