@@ -139,15 +139,123 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble(LvGridParams g, int nslot
     dinv[i] = aii > 0.0 ? (float)(1.0 / aii) : 0.0f;
 }
 
+// Edge-parallel form of k_assemble (same values, bit for bit).  The rows of an aligned group of 32 slots are contiguous in
+// the edge arrays, in slot order (every clipping kernel places the rows of a warp / block with one prefix sum), so a warp
+// walks the group's edges with consecutive lanes on consecutive edges: every load of col / v1 / v2 and every store of
+// w / lrr / mx / mz is coalesced (the row-parallel kernel writes 6 consecutive entries per lane, i.e. 96-byte strides).
+// The owner row of an edge comes from a 5-step search over the group's 32 row offsets in shared memory; the row's own
+// position and density travel by shuffle; the row sums A_ii are taken from staged weights in edge order, as before.
+#define AS_MAXT 512 // staged weights per group; a group with more edges (polygons of the edge-list kernel) takes the row loop
+__global__ void __launch_bounds__(PR_BLOCK) k_assemble_tile(LvGridParams g, int nslot, double dt, const unsigned char *__restrict__ own,
+                                                            const double2 *__restrict__ ent_xy, const int *__restrict__ rowptr, const unsigned char *__restrict__ rdeg,
+                                                            const int *__restrict__ col, const double2 *__restrict__ v1,
+                                                            const double2 *__restrict__ v2, const double *__restrict__ mass,
+                                                            const double *__restrict__ rho, const double *__restrict__ c2,
+                                                            double *__restrict__ diag, double *__restrict__ w, double *__restrict__ lrr_out,
+                                                            double2 *__restrict__ mx_out, double2 *__restrict__ mz_out, float *__restrict__ dinv) {
+    __shared__ int s_off[PR_BLOCK / 32][32];
+    __shared__ double s_w[PR_BLOCK / 32][AS_MAXT];
+    const unsigned FULL = 0xffffffffu;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const bool mine = i < nslot && own[i];
+    const int d = mine ? rdeg[i] : 0;
+    const int r0 = mine ? rowptr[i] : 0;
+    double ri = 1.0, dg = 0.0;
+    double2 x = make_double2(0.0, 0.0);
+    if (mine) {
+        ri = rho[i];
+        dg = mass[i] / (((ri * ri) * c2[i]) * (dt * dt)); // pressure.jl:110
+        x = ent_xy[i];
+    }
+    int off = d;
+#pragma unroll
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int t = __shfl_up_sync(FULL, off, o2);
+        if (lane >= o2) off += t;
+    }
+    const int T = __shfl_sync(FULL, off, 31);
+    off -= d;
+    const unsigned has = __ballot_sync(FULL, d > 0);
+    if (i < nslot && !mine) { diag[i] = 0.0; dinv[i] = 0.0f; }
+    if (T == 0) {
+        if (mine) { diag[i] = dg; dinv[i] = dg > 0.0 ? (float)(1.0 / dg) : 0.0f; }
+        return;
+    }
+    const int E0 = __shfl_sync(FULL, r0 - off, __ffs(has) - 1); // first edge of the group
+    // rows of the group must be contiguous in slot order (see above); anything else takes the row loop
+    const bool contiguous = __all_sync(FULL, d == 0 || r0 == E0 + off);
+    double aii = dg;
+    if (contiguous && T <= AS_MAXT) {
+        s_off[wp][lane] = off;
+        __syncwarp();
+        for (int e = lane; e < ((T + 31) & ~31); e += 32) {
+            int lo = 0;
+#pragma unroll
+            for (int st = 16; st; st >>= 1)
+                if (s_off[wp][lo + st] <= (e < T ? e : T - 1)) lo += st;
+            const double xx = __shfl_sync(FULL, x.x, lo), xy_ = __shfl_sync(FULL, x.y, lo), rio = __shfl_sync(FULL, ri, lo);
+            if (e >= T) continue;
+            const int k = E0 + e;
+            const int j = col[k];
+            const double2 a = v1[k], b = v2[k];
+            const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y); // midpoint(e)  geometry.jl:145-147
+            mx_out[k] = make_double2(mx - xx, my - xy_);
+            double wk = 0.0;
+            if (j < 0) { w[k] = 0.0; lrr_out[k] = 0.0; mz_out[k] = make_double2(0.0, 0.0); } // wall edge: not in neighbors(p, grid)
+            else {
+                const double2 xo = make_double2(xx, xy_);
+                const double2 y = lv_neighbor_pos(g, xo, ent_xy[j]);
+                const double ex = a.x - b.x, ey = a.y - b.y, dx = xx - y.x, dy = xy_ - y.y;
+                const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy)); // lr_ratio  polygon.jl:228-232
+                lrr_out[k] = lrr;
+                wk = lrr * (0.5 / rio + 0.5 / rho[j]);                              // pressure.jl:113
+                w[k] = wk;
+                const double zx = 0.5 * (xx + y.x), zy = 0.5 * (xy_ + y.y);         // midpoint(p.x, y)  pressure.jl:196
+                mz_out[k] = make_double2(mx - zx, my - zy);
+            }
+            s_w[wp][e] = wk;
+        }
+        __syncwarp();
+        for (int k = 0; k < d; k++) aii += s_w[wp][off + k]; // wall edges contribute 0.0, exactly like the row loop skipping them
+    } else if (mine) {
+        for (int k = r0; k < r0 + d; k++) {
+            const int j = col[k];
+            const double2 a = v1[k], b = v2[k];
+            const double mx = 0.5 * (a.x + b.x), my = 0.5 * (a.y + b.y);
+            mx_out[k] = make_double2(mx - x.x, my - x.y);
+            if (j < 0) { w[k] = 0.0; lrr_out[k] = 0.0; mz_out[k] = make_double2(0.0, 0.0); continue; }
+            const double2 y = lv_neighbor_pos(g, x, ent_xy[j]);
+            const double ex = a.x - b.x, ey = a.y - b.y, dx = x.x - y.x, dy = x.y - y.y;
+            const double lrr = sqrt((ex * ex + ey * ey) / (dx * dx + dy * dy));
+            lrr_out[k] = lrr;
+            const double wk = lrr * (0.5 / ri + 0.5 / rho[j]);
+            w[k] = wk;
+            aii += wk;
+            const double zx = 0.5 * (x.x + y.x), zy = 0.5 * (x.y + y.y);
+            mz_out[k] = make_double2(mx - zx, my - zy);
+        }
+    }
+    if (mine) {
+        diag[i] = dg;
+        dinv[i] = aii > 0.0 ? (float)(1.0 / aii) : 0.0f;
+    }
+}
+
 int lv_pr_assemble(LvContext *c, double dt) {
     LV_TRY(lv_pr_ensure(c));
     if (!c->pr_valid) return lv_set_error(c, LV_EINVAL, "fields not uploaded: call lv_fields_upload first");
     LvProfScope prof(c, LV_PROF_ASSEMBLE);
     const int ns = (int)c->nslot;
     if (ns > 0) {
-        k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
-                                                                             c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
-                                                                             c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, (float *)c->d_dinv);
+        static const bool rows = [] { const char *e = getenv("LV_ASSEMBLE"); return e && !strcmp(e, "rows"); }(); // A/B switch
+        if (rows)
+            k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
+                                                                                 c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
+                                                                                 c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, (float *)c->d_dinv);
+        else
+            k_assemble_tile<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
+                                                                                      c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
+                                                                                      c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, (float *)c->d_dinv);
         c->launches++;
         LV_CUDA(c, cudaGetLastError());
     }
