@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble_tile(LvGridParams g, int 
                                                             const double2 *__restrict__ v2, const double *__restrict__ mass,
                                                             const double *__restrict__ rho, const double *__restrict__ c2,
                                                             double *__restrict__ diag, double *__restrict__ w, double *__restrict__ lrr_out,
-                                                            double2 *__restrict__ mx_out, double2 *__restrict__ mz_out, float *__restrict__ dinv) {
+                                                            double2 *__restrict__ mx_out, double2 *__restrict__ mz_out, float *__restrict__ dinv, int maxt) {
     __shared__ int s_off[PR_BLOCK / 32][32];
     __shared__ double s_w[PR_BLOCK / 32][AS_MAXT];
     const unsigned FULL = 0xffffffffu;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(PR_BLOCK) k_assemble_tile(LvGridParams g, int 
     // rows of the group must be contiguous in slot order (see above); anything else takes the row loop
     const bool contiguous = __all_sync(FULL, d == 0 || r0 == E0 + off);
     double aii = dg;
-    if (contiguous && T <= AS_MAXT) {
+    if (contiguous && T <= maxt) {
         s_off[wp][lane] = off;
         __syncwarp();
         for (int e = lane; e < ((T + 31) & ~31); e += 32) {
@@ -248,6 +248,9 @@ int lv_pr_assemble(LvContext *c, double dt) {
     const int ns = (int)c->nslot;
     if (ns > 0) {
         static const bool rows = [] { const char *e = getenv("LV_ASSEMBLE"); return e && !strcmp(e, "rows"); }(); // A/B switch
+        // test hook: groups with more than LV_ASSEMBLE_MAXT edges take the kernel's row loop (default: the staging capacity)
+        int maxt = AS_MAXT;
+        if (const char *e = getenv("LV_ASSEMBLE_MAXT")) { const int v = atoi(e); if (v >= 0 && v < AS_MAXT) maxt = v; }
         if (rows)
             k_assemble<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                                  c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
@@ -255,7 +258,7 @@ int lv_pr_assemble(LvContext *c, double dt) {
         else
             k_assemble_tile<<<(ns + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, c->stream>>>(c->gp, ns, dt, c->d_own, c->d_ent_xy, c->d_rowptr, c->d_deg,
                                                                                       c->d_col, c->d_v1, c->d_v2, c->d_mass, c->d_rho, c->d_c2,
-                                                                                      c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, (float *)c->d_dinv);
+                                                                                      c->d_diag, c->d_w, c->d_lrr, c->d_mx, c->d_mz, (float *)c->d_dinv, maxt);
         c->launches++;
         LV_CUDA(c, cudaGetLastError());
     }
