@@ -67,8 +67,21 @@ int main(int argc, char **argv) {
                 if (veq(x, y)) { buf[ne++] = (ev_t){(int32_t)t, 1, d2, prr, prr, nv, 0}; continue; }
                 if (d2 > prr) { buf[ne++] = (ev_t){(int32_t)t, 2, d2, prr, prr, nv, 0}; continue; }
                 double before = prr;
-                if (voronoicut_poly(poly, y, i)) { prr = influence_rr(poly); buf[ne++] = (ev_t){(int32_t)t, 4, d2, before, prr, nv, 0}; }
-                else buf[ne++] = (ev_t){(int32_t)t, 3, d2, before, prr, nv, 0};
+                /* would an axis-aligned bounding box of the vertices (relative to x) already rule the cut out?
+                 * cut <=> some vertex v has d.(v - x) > |d|^2 / 2 (+ eps); the box gives an upper bound of d.(v - x) */
+                int boxrej = 0;
+                {
+                    double lx = 1e300, hx = -1e300, ly = 1e300, hy = -1e300;
+                    for (int64_t k = 0; k < poly->edges.last; k++) {
+                        double vx = poly->edges.data[k].v1.x - x.x, vy = poly->edges.data[k].v1.y - x.y;
+                        if (vx < lx) lx = vx; if (vx > hx) hx = vx; if (vy < ly) ly = vy; if (vy > hy) hy = vy;
+                    }
+                    double dx = y.x - x.x, dy = y.y - x.y;
+                    double ub = dx * (dx > 0 ? hx : lx) + dy * (dy > 0 ? hy : ly);
+                    boxrej = ub <= 0.5 * (dx * dx + dy * dy) * (1.0 - 1e-9);
+                }
+                if (voronoicut_poly(poly, y, i)) { prr = influence_rr(poly); buf[ne++] = (ev_t){(int32_t)t, 4, d2, before, prr, nv, boxrej}; }
+                else buf[ne++] = (ev_t){(int32_t)t, 3, d2, before, prr, nv, boxrej};
             }
         }
         if (t == g->npath) buf[ne++] = (ev_t){(int32_t)t, 6, 0, prr, prr, 0, 0};
