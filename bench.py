@@ -488,10 +488,12 @@ def e2e_strips(env, args, sg, solver, g, dt, n_total, steps, c0, edges):
     edge_h = _host_empty((cap,), EDGE_DTYPE) if edges else None
     # pipeline: 20 B/edge wire format expanded by host threads of the library (the ranks of a node share its cores);
     # all: 40-byte records copied lazily on a second stream
-    # The expansion needs host cores: with 8 ranks on a 16-core host (2 per rank) the wire format measured SLOWER than plain
-    # 40-byte DMA (945 vs 805 ms per step), with 2 ranks (7 per rank) faster (264 vs 284 ms) -- so it is used from 6 cores per rank.
-    cores_per_rank = host_threads() / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
-    wire = edges and E2E_MODE == "pipeline" and cores_per_rank >= 6
+    # The expansion needs host cores AND host memory bandwidth, which the ranks of a node share: measured per step, wire format
+    # against plain 40-byte DMA: 2 ranks / 16 cores 261 vs 284 ms; 4 ranks / 32 cores 511 vs 410 ms; 8 ranks / 16 cores 945 vs
+    # 805 ms -- so it is used with at most 2 ranks per node and at least 6 cores per rank.
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    cores_per_rank = host_threads() / local_world
+    wire = edges and E2E_MODE == "pipeline" and local_world <= 2 and cores_per_rank >= 6
     if edges:
         check(g._L.lv_set_async_edges(g._h, 3 if wire else 1), g._h)
 
