@@ -110,3 +110,48 @@ def test_wire_format_decoder_rebuilds_the_oracles_edge_records(lv, oracle):
     # a list that stops inside a row is refused
     bad = np.zeros(1, np.uint32)
     assert L.lv_wire_expand(ptr(np.zeros(2)), ptr(bad), 1, 0, ptr(np.zeros(2)), ptr(np.zeros(1, EDGE_DTYPE))) != 0
+
+
+def test_wire_format_decoder_property(lv):
+    """Property test of lv_wire_expand: random row structures (empty rows, rows of 3..12 edges, wall labels), random chunk
+    boundaries -- the decoded records always equal the records the wire format was derived from."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+    from lvb200._capi import EDGE_DTYPE, load_library, ptr
+    L = load_library()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.sampled_from([0, 0, 3, 4, 5, 6, 7, 9, 12]), min_size=1, max_size=40), st.integers(1, 50), st.integers(0, 2**31 - 1))
+    def check(degs, chunk, seed):
+        rng = np.random.default_rng(seed)
+        degs = np.array(degs)
+        rowptr = np.concatenate([[0], np.cumsum(degs)])
+        nnz = int(rowptr[-1])
+        if nnz == 0:
+            return
+        edges = np.zeros(nnz, EDGE_DTYPE)
+        edges["v1"] = rng.standard_normal((nnz, 2))
+        lab = rng.integers(1, 2**30 - 1, nnz)
+        wall = rng.random(nnz) < 0.2
+        lab[wall] = -rng.integers(1, 5, int(wall.sum()))
+        edges["label"] = lab
+        for i in range(len(degs)):                                   # closed chains: v2 = successor's v1, last -> first
+            a, b = rowptr[i], rowptr[i + 1]
+            if b > a:
+                edges["v2"][a:b] = np.roll(edges["v1"][a:b], -1, axis=0)
+        v1 = np.ascontiguousarray(edges["v1"])
+        word = np.where(lab > 0, lab, (1 << 30) | (-lab)).astype(np.uint32)
+        word[rowptr[1:][degs > 0] - 1] |= np.uint32(1 << 31)
+        row_of = np.repeat(np.arange(len(degs)), degs)
+        out = np.zeros(nnz, EDGE_DTYPE)
+        for k0 in range(0, nnz, chunk):
+            ln = min(chunk, nnz - k0)
+            has_next = k0 + ln < nnz
+            vv = np.ascontiguousarray(v1[k0:k0 + ln + has_next])
+            ww = np.ascontiguousarray(word[k0:k0 + ln])
+            rs = np.ascontiguousarray(v1[rowptr[row_of[k0]]])
+            seg = out[k0:k0 + ln]
+            assert L.lv_wire_expand(ptr(vv), ptr(ww), ln, int(has_next), ptr(rs), ptr(seg)) == 0
+        assert out.tobytes() == edges.tobytes()
+
+    check()
