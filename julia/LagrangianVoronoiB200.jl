@@ -203,6 +203,9 @@ function find_pressure_b200!(solver::PressureSolver, dt::Float64, niter::Int64 =
     grid = solver.grid
     ctx = context(grid)
     n = length(grid.polygons)
+    # a boundary_velocity closure is evaluated on p.edges: in the pipelined mode the edge view must have arrived first
+    # (with the default zero closure the solve starts while the mesh is still on its way)
+    boundary_velocity === LagrangianVoronoi.zero_vbc || sync_mesh!(grid)
     mass = staging(ctx, :mass, Float64, n); rho = staging(ctx, :rho, Float64, n); c2 = staging(ctx, :c2, Float64, n)
     P = staging(ctx, :P, Float64, n); v = staging(ctx, :v, RealVector, n)
     foreach(pin!, (mass, rho, c2, P, v))
