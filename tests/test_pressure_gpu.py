@@ -119,6 +119,30 @@ def test_assembly_variants_give_the_same_operator(lv, oracle, monkeypatch, env):
         assert a.tobytes() == b.tobytes()
 
 
+def test_fused_sweeps_of_find_pressure_match_the_split_calls(lv, oracle):
+    """find_pressure! runs the fused sweeps (GP + A.P in one walk, b + CG initialisation in the other); the split API
+    (rhs + solve) runs the unfused kernels.  Same passes, same tolerances: the pressures must agree to rounding of the Krylov
+    iterates, and both match the oracle."""
+    g, og, xy, dr = _setup(lv, oracle, "rect2x1", 40, True, False, 2, 10.0, True)
+    dt = 0.1 * dr
+    P0 = g.P.copy()
+    s = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    lv.find_pressure(s, dt, 3)
+    P_fused = g.P.copy()
+    g.P[...] = P0
+    s2 = lv.PressureSolver(g, rtol=1e-12, atol=0.0, itmax=20000)
+    s2.upload_fields(g.mass, g.rho, g.c2, P0, g.v)
+    P = P0
+    for it in range(3):
+        b, _ = s2.rhs(dt, it > 0, None)
+        P, _, _ = s2.solve(b, P, rtol=1e-12, atol=0.0, itmax=20000)
+    og.find_pressure(dt, 3, rtol=1e-12, atol=0.0, itmax=20000, solver="cg")
+    Pref = og.get("P")
+    scale = np.abs(Pref).max()
+    assert np.abs(P_fused - Pref).max() <= 1e-8 * scale
+    assert np.abs(P_fused - P).max() <= 1e-9 * scale
+
+
 @pytest.mark.parametrize("c0,n_side", [(10.0, 64), (1000.0, 48)])
 def test_solve_matches_oracle(lv, oracle, c0, n_side):
     """Solve A P = b to a true relative residual of 1e-10 on both sides; P must agree to 1e-8 relative
