@@ -16,7 +16,8 @@
  *    wall codes UP=-1 RIGHT=-2 DOWN=-3 LEFT=-4 (polygon.jl:4-7)
  *  - positions / vectors are interleaved double[2n] (= Vector{SVector{2,Float64}})
  *  - LvEdge is the 40-byte isbits layout of `Edge` (geometry.jl:82-87)
- *  - host-buffer calls are synchronous; *_dev calls are asynchronous on the handle's stream
+ *  - host-buffer calls are synchronous (lv_set_async_edges switches the lazy / pipelined modes on); *_dev calls are
+ *    asynchronous on the handle's stream
  *    and report device-side failures at the next lv_sync()/host-buffer call
  *  - one caller thread per handle; no callbacks cross the boundary
  */
