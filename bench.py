@@ -9,7 +9,10 @@ SURVEY.md section 8(d) (splitmix64 lattice jitter, Taylor-Green fields, rho = 1,
 
   value     device-resident throughput (inputs already in HBM), Mcell-steps/s over all ranks; the headline leg is the
             16.8M-cell box on one GPU and, for N > 1, 16.8M cells per GPU (weak scaling, box [0,1] x [0,N])
-  e2e       the same step through the host-buffer C ABI (pinned host arrays, H2D/D2H inside the timed region)
+  e2e       the same step through the host-buffer C ABI (pinned host arrays, H2D/D2H inside the timed region), in the
+            library's pipelined mode: uploads overlap the queued clipping kernel, the mesh crosses PCIe as 20 B/edge and host
+            threads of the library expand it into the 40-byte Edge records (--e2e-mode all: plain lazy downloads)
+  submetrics.plain_cg / shuffled_labels   N = 1: the same leg with unpreconditioned CG / with randomly permuted labels
   roofline  the dominant kernel (CSR Voronoi-Laplacian matvec) against the measured HBM peak
   submetrics.strong_64M   second timed leg in EVERY run: the fixed 8192^2 = 67.1M-cell box split into N y-strips
             (N = 1 included), the north star's strong-scaling configuration, with its own e2e and mesh witness
